@@ -1,0 +1,693 @@
+/*
+ * oracle/stitch_oracle.c  --  TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT.
+ *
+ * Plain-C, single-threaded CPU restatement of the arithmetic the reference executes on its
+ * compositing hot path.  The reference (OpenStitching/stitching v0.7.0) is 150 lines of
+ * Python that forward to OpenCV:
+ *     stitching/warper.py:43-52   Warper.warp_image        -> cv.PyRotationWarper.warp(LINEAR, REFLECT)
+ *     stitching/warper.py:58-68   create_and_warp_mask     -> cv.PyRotationWarper.warp(NEAREST, CONSTANT)
+ *     stitching/warper.py:79-82   warp_roi                 -> cv.PyRotationWarper.warpRoi
+ *     stitching/blender.py:23-38  Blender.prepare          -> resultRoi, MultiBand/Feather/NO ::prepare
+ *     stitching/blender.py:40-41  Blender.feed             -> cv.detail_*Blender.feed (int16x3, u8 mask)
+ *     stitching/blender.py:43-48  Blender.blend            -> ::blend + cv.convertScaleAbs
+ * The arithmetic itself lives in the un-vendored third-party wheel opencv-python
+ * (setup.cfg:21 "opencv-python>=4.0.1,<6"); it is restated here from its published algorithm
+ *  and PINNED against cv2 4.13.0 run in the build container through
+ * the unmodified reference classes: tests/golden/gen_golden.py generates the fixtures,
+ * tests/test_oracle_golden.py replays them (bit-exact).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this file.
+ * Build: oracle/Makefile  (gcc -O2 -ffp-contract=off; FMA contraction would break parity).
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SO_API __attribute__((visibility("default")))
+
+enum { SO_SPHERICAL = 0, SO_CYLINDRICAL = 1, SO_PLANE = 2, SO_AFFINE = 3 };
+
+/* ------------------------------------------------------------------------------------------
+ * A.1  projector set-up  (OpenCV ProjectorBase::setCameraParams; reached from warper.py:44-51)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float k[9], rinv[9], r_kinv[9], k_rinv[9], t[3], scale;
+    int type; /* SO_SPHERICAL / SO_CYLINDRICAL / SO_PLANE (affine is folded into plane) */
+} so_proj;
+
+/* plain fp32 3x3 product, each multiply and add separately rounded, left to right
+ * (OpenCV gemm's small-matrix path: float t = a0*b0 + a1*b1 + a2*b2) */
+static void mat3_mul(const float *A, const float *B, float *C)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float s = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j];
+            C[i * 3 + j] = s + A[i * 3 + 2] * B[2 * 3 + j];
+        }
+}
+
+/* cv::invert, 3x3 CV_32F closed form: cofactors and determinant in double, rounded once */
+static void mat3_inv(const float *S, float *D)
+{
+#define Sf(r, c) ((double)S[(r) * 3 + (c)])
+    double d = Sf(0, 0) * (Sf(1, 1) * Sf(2, 2) - Sf(1, 2) * Sf(2, 1)) -
+               Sf(0, 1) * (Sf(1, 0) * Sf(2, 2) - Sf(1, 2) * Sf(2, 0)) +
+               Sf(0, 2) * (Sf(1, 0) * Sf(2, 1) - Sf(1, 1) * Sf(2, 0));
+    if (d != 0.) d = 1. / d;
+    D[0] = (float)((Sf(1, 1) * Sf(2, 2) - Sf(1, 2) * Sf(2, 1)) * d);
+    D[1] = (float)((Sf(0, 2) * Sf(2, 1) - Sf(0, 1) * Sf(2, 2)) * d);
+    D[2] = (float)((Sf(0, 1) * Sf(1, 2) - Sf(0, 2) * Sf(1, 1)) * d);
+    D[3] = (float)((Sf(1, 2) * Sf(2, 0) - Sf(1, 0) * Sf(2, 2)) * d);
+    D[4] = (float)((Sf(0, 0) * Sf(2, 2) - Sf(0, 2) * Sf(2, 0)) * d);
+    D[5] = (float)((Sf(0, 2) * Sf(1, 0) - Sf(0, 0) * Sf(1, 2)) * d);
+    D[6] = (float)((Sf(1, 0) * Sf(2, 1) - Sf(1, 1) * Sf(2, 0)) * d);
+    D[7] = (float)((Sf(0, 1) * Sf(2, 0) - Sf(0, 0) * Sf(2, 1)) * d);
+    D[8] = (float)((Sf(0, 0) * Sf(1, 1) - Sf(0, 1) * Sf(1, 0)) * d);
+#undef Sf
+}
+
+static void proj_setup(so_proj *p, int type, float scale, const float *K, const float *R_in)
+{
+    float R[9], T[3] = {0.f, 0.f, 0.f}, kinv[9];
+    memcpy(R, R_in, sizeof R);
+    if (type == SO_AFFINE) {
+        /* AffineWarper::getRTfromHomogeneous: T = H[:,2] (z=0); R = H with [0,2]=[1,2]=0;
+         * R = R^T; T = -(R*T) */
+        float Tt[3] = {R[2], R[5], 0.f}, Rt[9];
+        R[2] = 0.f;
+        R[5] = 0.f;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+        memcpy(R, Rt, sizeof R);
+        for (int i = 0; i < 3; ++i) {
+            float s = R[i * 3 + 0] * Tt[0] + R[i * 3 + 1] * Tt[1];
+            s = s + R[i * 3 + 2] * Tt[2];
+            T[i] = s * -1.f;
+        }
+        type = SO_PLANE;
+    }
+    p->type = type;
+    p->scale = scale;
+    memcpy(p->k, K, sizeof p->k);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) p->rinv[i * 3 + j] = R[j * 3 + i];
+    mat3_inv(K, kinv);
+    mat3_mul(R, kinv, p->r_kinv);
+    mat3_mul(K, p->rinv, p->k_rinv);
+    memcpy(p->t, T, sizeof T);
+}
+
+static const float PI_F = 3.14159274101257324f; /* static_cast<float>(CV_PI) */
+
+static void map_forward(const so_proj *p, float x, float y, float *u, float *v)
+{
+    const float *r = p->r_kinv;
+    float x_ = r[0] * x + r[1] * y + r[2];
+    float y_ = r[3] * x + r[4] * y + r[5];
+    float z_ = r[6] * x + r[7] * y + r[8];
+    if (p->type == SO_SPHERICAL) {
+        *u = p->scale * atan2f(x_, z_);
+        float w = y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_);
+        *v = p->scale * (PI_F - acosf(w == w ? w : 0.f));
+    } else if (p->type == SO_CYLINDRICAL) {
+        *u = p->scale * atan2f(x_, z_);
+        *v = p->scale * y_ / sqrtf(x_ * x_ + z_ * z_);
+    } else {
+        x_ = p->t[0] + x_ / z_ * (1.f - p->t[2]);
+        y_ = p->t[1] + y_ / z_ * (1.f - p->t[2]);
+        *u = p->scale * x_;
+        *v = p->scale * y_;
+    }
+}
+
+static void map_backward(const so_proj *p, float u, float v, float *x, float *y)
+{
+    const float *k = p->k_rinv;
+    float x_, y_, z_, z;
+    if (p->type == SO_SPHERICAL) {
+        u /= p->scale;
+        v /= p->scale;
+        float sinv = sinf(PI_F - v);
+        x_ = sinv * sinf(u);
+        y_ = cosf(PI_F - v);
+        z_ = sinv * cosf(u);
+    } else if (p->type == SO_CYLINDRICAL) {
+        u /= p->scale;
+        v /= p->scale;
+        x_ = sinf(u);
+        y_ = v;
+        z_ = cosf(u);
+    } else {
+        x_ = u / p->scale - p->t[0];
+        y_ = v / p->scale - p->t[1];
+        z_ = 1.f - p->t[2];
+    }
+    *x = k[0] * x_ + k[1] * y_ + k[2] * z_;
+    *y = k[3] * x_ + k[4] * y_ + k[5] * z_;
+    z = k[6] * x_ + k[7] * y_ + k[8] * z_;
+    if (p->type == SO_PLANE) {
+        *x /= z;
+        *y /= z;
+    } else if (z > 0.f) {
+        *x /= z;
+        *y /= z;
+    } else {
+        *x = *y = -1.f;
+    }
+}
+
+#define UPD(u, v)                      \
+    do {                               \
+        if ((u) < tl_u) tl_u = (u);    \
+        if ((v) < tl_v) tl_v = (v);    \
+        if ((u) > br_u) br_u = (u);    \
+        if ((v) > br_v) br_v = (v);    \
+    } while (0)
+
+/* RotationWarperBase::detectResultRoi* ; results truncated toward zero like static_cast<int> */
+static void detect_roi(const so_proj *p, int W, int H, int *tlx, int *tly, int *brx, int *bry)
+{
+    float tl_u = 3.402823466e+38f, tl_v = 3.402823466e+38f;
+    float br_u = -3.402823466e+38f, br_v = -3.402823466e+38f, u, v;
+    if (p->type == SO_PLANE) {
+        map_forward(p, 0.f, 0.f, &u, &v); UPD(u, v);
+        map_forward(p, 0.f, (float)(H - 1), &u, &v); UPD(u, v);
+        map_forward(p, (float)(W - 1), 0.f, &u, &v); UPD(u, v);
+        map_forward(p, (float)(W - 1), (float)(H - 1), &u, &v); UPD(u, v);
+    } else {
+        for (int x = 0; x < W; ++x) {
+            map_forward(p, (float)x, 0.f, &u, &v); UPD(u, v);
+            map_forward(p, (float)x, (float)(H - 1), &u, &v); UPD(u, v);
+        }
+        for (int y = 0; y < H; ++y) {
+            map_forward(p, 0.f, (float)y, &u, &v); UPD(u, v);
+            map_forward(p, (float)(W - 1), (float)y, &u, &v); UPD(u, v);
+        }
+    }
+    *tlx = (int)tl_u; *tly = (int)tl_v; *brx = (int)br_u; *bry = (int)br_v;
+    if (p->type == SO_SPHERICAL) {
+        tl_u = (float)*tlx; tl_v = (float)*tly; br_u = (float)*brx; br_v = (float)*bry;
+        for (int pass = 0; pass < 2; ++pass) {
+            float x = p->rinv[1];
+            float y = pass == 0 ? p->rinv[4] : -p->rinv[4];
+            float z = p->rinv[7];
+            if (y > 0.f) {
+                float x_ = (p->k[0] * x + p->k[1] * y) / z + p->k[2];
+                float y_ = p->k[4] * y / z + p->k[5];
+                if (x_ > 0.f && x_ < W && y_ > 0.f && y_ < H) {
+                    float pole = pass == 0 ? (float)(3.14159265358979323846 * p->scale) : 0.f;
+                    if (0.f < tl_u) tl_u = 0.f;
+                    if (pole < tl_v) tl_v = pole;
+                    if (0.f > br_u) br_u = 0.f;
+                    if (pole > br_v) br_v = pole;
+                }
+            }
+        }
+        *tlx = (int)tl_u; *tly = (int)tl_v; *brx = (int)br_u; *bry = (int)br_v;
+    }
+}
+
+/* warper.py:79-82 -> PyRotationWarper::warpRoi: (tl.x, tl.y, br.x-tl.x+1, br.y-tl.y+1) */
+SO_API int so_warp_roi(int type, float scale, const float *K, const float *R, int src_w, int src_h,
+                       int rect[4])
+{
+    so_proj p;
+    int tlx, tly, brx, bry;
+    proj_setup(&p, type, scale, K, R);
+    detect_roi(&p, src_w, src_h, &tlx, &tly, &brx, &bry);
+    rect[0] = tlx; rect[1] = tly; rect[2] = brx - tlx + 1; rect[3] = bry - tly + 1;
+    return 0;
+}
+
+/* PyRotationWarper::warpPoint == mapForward (used to pin r_kinv and the libm calls) */
+SO_API int so_warp_point(int type, float scale, const float *K, const float *R, float x, float y,
+                         float uv[2])
+{
+    so_proj p;
+    proj_setup(&p, type, scale, K, R);
+    map_forward(&p, x, y, &uv[0], &uv[1]);
+    return 0;
+}
+
+/* RotationWarperBase::buildMaps: float maps over the roi; xmap/ymap are rect[3] x rect[2] */
+SO_API int so_build_maps(int type, float scale, const float *K, const float *R, int src_w, int src_h,
+                         const int rect[4], float *xmap, float *ymap)
+{
+    so_proj p;
+    proj_setup(&p, type, scale, K, R);
+    (void)src_w; (void)src_h;
+    for (int j = 0; j < rect[3]; ++j)
+        for (int i = 0; i < rect[2]; ++i)
+            map_backward(&p, (float)(rect[0] + i), (float)(rect[1] + j),
+                         &xmap[(size_t)j * rect[2] + i], &ymap[(size_t)j * rect[2] + i]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.2  cv::remap restatement
+ * ---------------------------------------------------------------------------------------- */
+static int cv_round(float v) /* cvRound(float) = cvtss2si: half-to-even, INT_MIN when unrepresentable */
+{
+    if (!(v > -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
+    return (int)nearbyintf(v);
+}
+static int sat_s16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+static int reflect(int p, int n) /* BORDER_REFLECT  fedcba|abcdefgh|hgfedcb */
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p - 1 : 2 * n - 1 - p;
+    return p;
+}
+static int reflect101(int p, int n) /* BORDER_REFLECT_101  gfedcb|abcdefgh|gfedcba */
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+/* fixed-point bilinear, coordinates quantised to 1/32 px, 15-bit weights, BORDER_REFLECT */
+static void remap_linear_px(const uint8_t *src, int W, int H, size_t pitch, int cn, float x, float y,
+                            uint8_t *out)
+{
+    int sx = cv_round(x * 32.f), sy = cv_round(y * 32.f);
+    int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
+    int fx = sx & 31, fy = sy & 31;
+    int x0 = reflect(ix, W), x1 = reflect(ix + 1, W), y0 = reflect(iy, H), y1 = reflect(iy + 1, H);
+    int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32;
+    int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    for (int c = 0; c < cn; ++c) {
+        int v = src[y0 * pitch + x0 * cn + c] * w00 + src[y0 * pitch + x1 * cn + c] * w01 +
+                src[y1 * pitch + x0 * cn + c] * w10 + src[y1 * pitch + x1 * cn + c] * w11;
+        v = (v + (1 << 14)) >> 15;
+        out[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+/* nearest, BORDER_CONSTANT(0), source = all-255 mask of size WxH (warper.py:60) */
+static uint8_t remap_nearest_mask_px(int W, int H, float x, float y)
+{
+    int ix = sat_s16(cv_round(x)), iy = sat_s16(cv_round(y));
+    return (ix >= 0 && ix < W && iy >= 0 && iy < H) ? 255 : 0;
+}
+
+SO_API int so_remap_linear_u8(const uint8_t *src, int W, int H, size_t pitch, int cn, const float *xmap,
+                              const float *ymap, int dw, int dh, uint8_t *dst, size_t dst_pitch)
+{
+    for (int j = 0; j < dh; ++j)
+        for (int i = 0; i < dw; ++i)
+            remap_linear_px(src, W, H, pitch, cn, xmap[(size_t)j * dw + i], ymap[(size_t)j * dw + i],
+                            dst + j * dst_pitch + (size_t)i * cn);
+    return 0;
+}
+
+/* warper.py:43-52 + 58-68 fused: image (nullable) and mask (nullable) over the roi */
+SO_API int so_warp(int type, float scale, const float *K, const float *R, const uint8_t *src, int src_w,
+                   int src_h, size_t src_pitch, uint8_t *dst, size_t dst_pitch, uint8_t *mask,
+                   size_t mask_pitch, int rect[4])
+{
+    so_proj p;
+    int tlx, tly, brx, bry;
+    proj_setup(&p, type, scale, K, R);
+    detect_roi(&p, src_w, src_h, &tlx, &tly, &brx, &bry);
+    rect[0] = tlx; rect[1] = tly; rect[2] = brx - tlx + 1; rect[3] = bry - tly + 1;
+    if (!dst && !mask) return 0;
+    for (int j = 0; j < rect[3]; ++j)
+        for (int i = 0; i < rect[2]; ++i) {
+            float x, y;
+            map_backward(&p, (float)(tlx + i), (float)(tly + j), &x, &y);
+            if (dst) remap_linear_px(src, src_w, src_h, src_pitch, 3, x, y, dst + j * dst_pitch + (size_t)i * 3);
+            if (mask) mask[j * mask_pitch + i] = remap_nearest_mask_px(src_w, src_h, x, y);
+        }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.3  pyramids (cv::pyrDown / cv::pyrUp as used by MultiBandBlender::feed / ::blend)
+ * ---------------------------------------------------------------------------------------- */
+/* int16, cn interleaved channels, 5x5 [1 4 6 4 1]^2, REFLECT_101, (s+128)>>8 */
+SO_API void so_pyrdown_s16(const int16_t *src, int W, int H, int cn, int16_t *dst)
+{
+    int dw = (W + 1) / 2, dh = (H + 1) / 2;
+    int *row = (int *)malloc(sizeof(int) * (size_t)dw * cn * 5);
+    for (int y = 0; y < dh; ++y) {
+        for (int k = 0; k < 5; ++k) {
+            const int16_t *s = src + (size_t)reflect101(2 * y + k - 2, H) * W * cn;
+            int *r = row + (size_t)k * dw * cn;
+            for (int x = 0; x < dw; ++x) {
+                int i0 = reflect101(2 * x - 2, W), i1 = reflect101(2 * x - 1, W), i2 = 2 * x < W ? 2 * x : reflect101(2 * x, W);
+                int i3 = reflect101(2 * x + 1, W), i4 = reflect101(2 * x + 2, W);
+                for (int c = 0; c < cn; ++c)
+                    r[x * cn + c] = s[i2 * cn + c] * 6 + (s[i1 * cn + c] + s[i3 * cn + c]) * 4 + s[i0 * cn + c] + s[i4 * cn + c];
+            }
+        }
+        for (int x = 0; x < dw * cn; ++x) {
+            int v = row[2 * dw * cn + x] * 6 + (row[1 * dw * cn + x] + row[3 * dw * cn + x]) * 4 + row[x] + row[4 * dw * cn + x];
+            dst[(size_t)y * dw * cn + x] = (int16_t)((v + 128) >> 8);
+        }
+    }
+    free(row);
+}
+
+/* float32 single channel.  OpenCV's summation order is position dependent: the wheel's baseline is
+ * SSE3 (4 float lanes, v_muladd = mul then add, no FMA) and pyramids.cpp is not in the dispatch list,
+ * so the SIMD body uses one association and the scalar borders / tails another.  Pinned bit-exact
+ * against cv.pyrDown (tests/test_oracle_golden.py). */
+SO_API void so_pyrdown_f32(const float *src, int W, int H, float *dst)
+{
+    int dw = (W + 1) / 2, dh = (H + 1) / 2;
+    int width0 = (W - 3) / 2 + 1;
+    if (width0 > dw) width0 = dw;
+    int hs_end = 1; /* horizontal SIMD body covers x in [1, hs_end) */
+    while (hs_end <= width0 - 4) hs_end += 4;
+    int vs_end = (dw / 4) * 4; /* vertical SIMD body covers x in [0, vs_end) */
+    float *row = (float *)malloc(sizeof(float) * (size_t)dw * 5);
+    const float scale = 1.f / 256;
+    for (int y = 0; y < dh; ++y) {
+        for (int k = 0; k < 5; ++k) {
+            const float *s = src + (size_t)reflect101(2 * y + k - 2, H) * W;
+            float *r = row + (size_t)k * dw;
+            for (int x = 0; x < dw; ++x) {
+                float s0 = s[reflect101(2 * x - 2, W)], s1 = s[reflect101(2 * x - 1, W)], s2 = s[reflect101(2 * x, W)];
+                float s3 = s[reflect101(2 * x + 1, W)], s4 = s[reflect101(2 * x + 2, W)];
+                if (x >= 1 && x < hs_end) {
+                    float a = (s1 + s3) * 4.f + (s0 + s4);
+                    r[x] = s2 * 6.f + a;
+                } else {
+                    r[x] = s2 * 6.f + (s1 + s3) * 4.f + s0 + s4;
+                }
+            }
+        }
+        const float *r0 = row, *r1 = row + dw, *r2 = row + 2 * dw, *r3 = row + 3 * dw, *r4 = row + 4 * dw;
+        for (int x = 0; x < dw; ++x) {
+            if (x < vs_end) {
+                float a = ((r1[x] + r3[x]) + r2[x]) * 4.f;
+                float b = (r0[x] + r4[x]) + (r2[x] + r2[x]);
+                dst[(size_t)y * dw + x] = (a + b) * scale;
+            } else {
+                dst[(size_t)y * dw + x] = (r2[x] * 6.f + (r1[x] + r3[x]) * 4.f + r0[x] + r4[x]) * scale;
+            }
+        }
+    }
+    free(row);
+}
+
+/* int16 pyrUp to exactly (2W, 2H): prev = reflect-101 at left/top, next = replicate at right/bottom,
+ * even = prev + 6 cur + next, odd = 4 (cur + next), x then y, (v+32)>>6 */
+SO_API void so_pyrup_s16(const int16_t *src, int W, int H, int cn, int16_t *dst)
+{
+    int DW = 2 * W;
+    int *rows = (int *)malloc(sizeof(int) * (size_t)DW * cn * H);
+    for (int y = 0; y < H; ++y) {
+        const int16_t *s = src + (size_t)y * W * cn;
+        int *r = rows + (size_t)y * DW * cn;
+        for (int x = 0; x < W; ++x) {
+            int xp = x > 0 ? x - 1 : (W > 1 ? 1 : 0), xn = x + 1 < W ? x + 1 : W - 1;
+            for (int c = 0; c < cn; ++c) {
+                int cur = s[x * cn + c], prev = s[xp * cn + c], next = s[xn * cn + c];
+                r[(2 * x) * cn + c] = prev + 6 * cur + next;
+                r[(2 * x + 1) * cn + c] = 4 * (cur + next);
+            }
+        }
+    }
+    for (int y = 0; y < H; ++y) {
+        int yp = y > 0 ? y - 1 : (H > 1 ? 1 : 0), yn = y + 1 < H ? y + 1 : H - 1;
+        const int *rc = rows + (size_t)y * DW * cn, *rp = rows + (size_t)yp * DW * cn, *rn = rows + (size_t)yn * DW * cn;
+        int16_t *d0 = dst + (size_t)(2 * y) * DW * cn, *d1 = d0 + (size_t)DW * cn;
+        for (int x = 0; x < DW * cn; ++x) {
+            d0[x] = (int16_t)((rp[x] + 6 * rc[x] + rn[x] + 32) >> 6);
+            d1[x] = (int16_t)((4 * (rc[x] + rn[x]) + 32) >> 6);
+        }
+    }
+    free(rows);
+}
+
+static int16_t sat16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+/* static_cast<short>(float) as x86 compiles it: cvttss2si (INT_MIN when unrepresentable), low 16 bits */
+static int16_t f2s_trunc(float v)
+{
+    int i = (v > -2147483648.0f && v < 2147483648.0f) ? (int)v : INT_MIN;
+    return (int16_t)(uint16_t)(uint32_t)i;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.4  MultiBandBlender  (blender.py:30-32 prepare, :41 feed, :46 blend)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int nb, x, y, w, h, wp, hp;
+    int16_t **lap; /* [nb+1] int16x3 */
+    float **wt;    /* [nb+1] f32 */
+    int *lw, *lh;
+} so_mb;
+
+SO_API void *so_mb_create(int num_bands_requested, int x, int y, int w, int h)
+{
+    so_mb *m = (so_mb *)calloc(1, sizeof *m);
+    double max_len = (double)(w > h ? w : h);
+    int lim = (int)ceil(log(max_len) / log(2.0));
+    m->nb = num_bands_requested < lim ? num_bands_requested : lim;
+    int a = 1 << m->nb;
+    m->x = x; m->y = y; m->w = w; m->h = h;
+    m->wp = w + (a - w % a) % a;
+    m->hp = h + (a - h % a) % a;
+    m->lap = (int16_t **)calloc(m->nb + 1, sizeof *m->lap);
+    m->wt = (float **)calloc(m->nb + 1, sizeof *m->wt);
+    m->lw = (int *)calloc(m->nb + 1, sizeof(int));
+    m->lh = (int *)calloc(m->nb + 1, sizeof(int));
+    int lw = m->wp, lh = m->hp;
+    for (int l = 0; l <= m->nb; ++l) {
+        m->lw[l] = lw; m->lh[l] = lh;
+        m->lap[l] = (int16_t *)calloc((size_t)lw * lh * 3, sizeof(int16_t));
+        m->wt[l] = (float *)calloc((size_t)lw * lh, sizeof(float));
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    return m;
+}
+SO_API int so_mb_num_bands(void *h) { return ((so_mb *)h)->nb; }
+SO_API void so_mb_destroy(void *h)
+{
+    so_mb *m = (so_mb *)h;
+    if (!m) return;
+    for (int l = 0; l <= m->nb; ++l) { free(m->lap[l]); free(m->wt[l]); }
+    free(m->lap); free(m->wt); free(m->lw); free(m->lh); free(m);
+}
+
+/* the padded rect of one feed (A.4 step 1); out = tl'.x, tl'.y, width, height (pano-absolute) */
+static int mb_feed_rect(const so_mb *m, int w, int h, int tx, int ty, int out[4])
+{
+    int nb = m->nb, a = 1 << nb, gap = 3 * a;
+    int brx_roi = m->x + m->wp, bry_roi = m->y + m->hp;
+    int tlx = tx - gap > m->x ? tx - gap : m->x, tly = ty - gap > m->y ? ty - gap : m->y;
+    int brx = tx + w + gap < brx_roi ? tx + w + gap : brx_roi, bry = ty + h + gap < bry_roi ? ty + h + gap : bry_roi;
+    tlx = m->x + (((tlx - m->x) >> nb) << nb);
+    tly = m->y + (((tly - m->y) >> nb) << nb);
+    int width = brx - tlx, height = bry - tly;
+    width += (a - width % a) % a;
+    height += (a - height % a) % a;
+    brx = tlx + width; bry = tly + height;
+    int dy = bry - bry_roi > 0 ? bry - bry_roi : 0, dx = brx - brx_roi > 0 ? brx - brx_roi : 0;
+    tlx -= dx; tly -= dy;
+    out[0] = tlx; out[1] = tly; out[2] = width; out[3] = height;
+    if (ty - tly < 0 || tx - tlx < 0 || tly + height - ty - h < 0 || tlx + width - tx - w < 0) return -1;
+    return 0;
+}
+SO_API int so_mb_feed_rect(void *h, int w, int hh, int tx, int ty, int out[4]) { return mb_feed_rect((so_mb *)h, w, hh, tx, ty, out); }
+
+SO_API int so_mb_feed(void *hnd, const int16_t *img, size_t img_pitch_elems, const uint8_t *mask,
+                      size_t mask_pitch, int w, int h, int tx, int ty)
+{
+    so_mb *m = (so_mb *)hnd;
+    int rc[4], nb = m->nb;
+    if (mb_feed_rect(m, w, h, tx, ty, rc)) return -1;
+    int PW = rc[2], PH = rc[3], left = tx - rc[0], top = ty - rc[1];
+    int16_t **g = (int16_t **)calloc(nb + 1, sizeof *g);
+    float **wm = (float **)calloc(nb + 1, sizeof *wm);
+    g[0] = (int16_t *)malloc(sizeof(int16_t) * 3 * (size_t)PW * PH);
+    wm[0] = (float *)malloc(sizeof(float) * (size_t)PW * PH);
+    const float inv255 = (float)(1. / 255.);
+    for (int y = 0; y < PH; ++y) {
+        int sy = reflect(y - top, h), inside_y = (y - top >= 0 && y - top < h);
+        for (int x = 0; x < PW; ++x) {
+            int sx = reflect(x - left, w), inside = inside_y && (x - left >= 0 && x - left < w);
+            for (int c = 0; c < 3; ++c) g[0][((size_t)y * PW + x) * 3 + c] = img[(size_t)sy * img_pitch_elems + sx * 3 + c];
+            wm[0][(size_t)y * PW + x] = inside ? (float)mask[(size_t)(y - top) * mask_pitch + (x - left)] * inv255 : 0.f;
+        }
+    }
+    int lw = PW, lh = PH;
+    for (int l = 0; l < nb; ++l) {
+        int nw = (lw + 1) / 2, nh = (lh + 1) / 2;
+        g[l + 1] = (int16_t *)malloc(sizeof(int16_t) * 3 * (size_t)nw * nh);
+        wm[l + 1] = (float *)malloc(sizeof(float) * (size_t)nw * nh);
+        so_pyrdown_s16(g[l], lw, lh, 3, g[l + 1]);
+        so_pyrdown_f32(wm[l], lw, lh, wm[l + 1]);
+        lw = nw; lh = nh;
+    }
+    lw = PW; lh = PH;
+    int x0 = rc[0] - m->x, y0 = rc[1] - m->y;
+    for (int l = 0; l <= nb; ++l) {
+        int16_t *up = NULL;
+        if (l < nb) {
+            up = (int16_t *)malloc(sizeof(int16_t) * 3 * (size_t)lw * lh);
+            so_pyrup_s16(g[l + 1], lw / 2, lh / 2, 3, up);
+        }
+        for (int y = 0; y < lh; ++y)
+            for (int x = 0; x < lw; ++x) {
+                float wv = wm[l][(size_t)y * lw + x];
+                size_t di = (size_t)(y0 + y) * m->lw[l] + (x0 + x);
+                for (int c = 0; c < 3; ++c) {
+                    int16_t L = g[l][((size_t)y * lw + x) * 3 + c];
+                    if (up) L = sat16((int)L - (int)up[((size_t)y * lw + x) * 3 + c]);
+                    m->lap[l][di * 3 + c] = (int16_t)(m->lap[l][di * 3 + c] + f2s_trunc((float)L * wv));
+                }
+                m->wt[l][di] += wv;
+            }
+        free(up);
+        lw /= 2; lh /= 2; x0 /= 2; y0 /= 2;
+    }
+    for (int l = 0; l <= nb; ++l) { free(g[l]); free(wm[l]); }
+    free(g); free(wm);
+    return 0;
+}
+
+/* blend(): dst int16x3 [h][w], dst_mask u8 [h][w]  (consumes the accumulators) */
+SO_API int so_mb_blend(void *hnd, int16_t *dst, uint8_t *dst_mask)
+{
+    so_mb *m = (so_mb *)hnd;
+    int nb = m->nb;
+    const float eps = 1e-5f;
+    for (int l = 0; l <= nb; ++l) {
+        size_t n = (size_t)m->lw[l] * m->lh[l];
+        for (size_t i = 0; i < n; ++i) {
+            float w = m->wt[l][i] + eps;
+            for (int c = 0; c < 3; ++c) m->lap[l][i * 3 + c] = f2s_trunc((float)m->lap[l][i * 3 + c] / w);
+        }
+    }
+    for (int l = nb; l >= 1; --l) {
+        size_t n = (size_t)m->lw[l - 1] * m->lh[l - 1] * 3;
+        int16_t *up = (int16_t *)malloc(sizeof(int16_t) * n);
+        so_pyrup_s16(m->lap[l], m->lw[l], m->lh[l], 3, up);
+        for (size_t i = 0; i < n; ++i) m->lap[l - 1][i] = sat16((int)up[i] + (int)m->lap[l - 1][i]);
+        free(up);
+    }
+    for (int y = 0; y < m->h; ++y)
+        for (int x = 0; x < m->w; ++x) {
+            size_t si = (size_t)y * m->wp + x, di = (size_t)y * m->w + x;
+            int on = m->wt[0][si] > eps;
+            dst_mask[di] = on ? 255 : 0;
+            for (int c = 0; c < 3; ++c) dst[di * 3 + c] = on ? m->lap[0][si * 3 + c] : 0;
+        }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.5  FeatherBlender and the default (NO) Blender  (blender.py:27-28, 34-36)
+ * ---------------------------------------------------------------------------------------- */
+/* distanceTransform(mask, DIST_L1, 3): exact city-block distance to the nearest zero pixel inside
+ * the image (the image border is not a zero); "no zero anywhere" -> huge. */
+SO_API void so_dist_l1(const uint8_t *mask, size_t pitch, int w, int h, float *dist)
+{
+    const int INF = 1 << 29;
+    int *d = (int *)malloc(sizeof(int) * (size_t)w * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int v = mask[y * pitch + x] ? INF : 0;
+            if (v) {
+                if (x > 0 && d[(size_t)y * w + x - 1] + 1 < v) v = d[(size_t)y * w + x - 1] + 1;
+                if (y > 0 && d[(size_t)(y - 1) * w + x] + 1 < v) v = d[(size_t)(y - 1) * w + x] + 1;
+            }
+            d[(size_t)y * w + x] = v;
+        }
+    for (int y = h - 1; y >= 0; --y)
+        for (int x = w - 1; x >= 0; --x) {
+            int v = d[(size_t)y * w + x];
+            if (x + 1 < w && d[(size_t)y * w + x + 1] + 1 < v) v = d[(size_t)y * w + x + 1] + 1;
+            if (y + 1 < h && d[(size_t)(y + 1) * w + x] + 1 < v) v = d[(size_t)(y + 1) * w + x] + 1;
+            d[(size_t)y * w + x] = v;
+        }
+    for (size_t i = 0; i < (size_t)w * h; ++i) dist[i] = d[i] >= INF ? 3.402823466e+38f : (float)d[i];
+    free(d);
+}
+
+typedef struct {
+    int kind; /* 0 = NO, 1 = feather */
+    int x, y, w, h;
+    float sharpness;
+    int16_t *acc;
+    float *wsum;
+    uint8_t *msk;
+} so_sb;
+
+SO_API void *so_sb_create(int kind, float sharpness, int x, int y, int w, int h)
+{
+    so_sb *b = (so_sb *)calloc(1, sizeof *b);
+    b->kind = kind; b->sharpness = sharpness; b->x = x; b->y = y; b->w = w; b->h = h;
+    b->acc = (int16_t *)calloc((size_t)w * h * 3, sizeof(int16_t));
+    b->wsum = (float *)calloc((size_t)w * h, sizeof(float));
+    b->msk = (uint8_t *)calloc((size_t)w * h, 1);
+    return b;
+}
+SO_API void so_sb_destroy(void *h)
+{
+    so_sb *b = (so_sb *)h;
+    if (!b) return;
+    free(b->acc); free(b->wsum); free(b->msk); free(b);
+}
+SO_API int so_sb_feed(void *hnd, const int16_t *img, size_t img_pitch_elems, const uint8_t *mask,
+                      size_t mask_pitch, int w, int h, int tx, int ty)
+{
+    so_sb *b = (so_sb *)hnd;
+    int dx = tx - b->x, dy = ty - b->y;
+    if (dx < 0 || dy < 0 || dx + w > b->w || dy + h > b->h) return -1;
+    if (b->kind == 0) {
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                size_t di = (size_t)(dy + y) * b->w + dx + x;
+                uint8_t mv = mask[y * mask_pitch + x];
+                if (mv) for (int c = 0; c < 3; ++c) b->acc[di * 3 + c] = img[(size_t)y * img_pitch_elems + x * 3 + c];
+                b->msk[di] |= mv;
+            }
+        return 0;
+    }
+    float *wm = (float *)malloc(sizeof(float) * (size_t)w * h);
+    so_dist_l1(mask, mask_pitch, w, h, wm);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float wv = wm[(size_t)y * w + x] * b->sharpness;
+            if (wv > 1.f) wv = 1.f; /* threshold(THRESH_TRUNC, 1) */
+            size_t di = (size_t)(dy + y) * b->w + dx + x;
+            for (int c = 0; c < 3; ++c)
+                b->acc[di * 3 + c] = (int16_t)(b->acc[di * 3 + c] + f2s_trunc((float)img[(size_t)y * img_pitch_elems + x * 3 + c] * wv));
+            b->wsum[di] += wv;
+        }
+    free(wm);
+    return 0;
+}
+SO_API int so_sb_blend(void *hnd, int16_t *dst, uint8_t *dst_mask)
+{
+    so_sb *b = (so_sb *)hnd;
+    size_t n = (size_t)b->w * b->h;
+    const float eps = 1e-5f;
+    for (size_t i = 0; i < n; ++i) {
+        int on;
+        if (b->kind == 0) {
+            on = b->msk[i] != 0;
+            dst_mask[i] = b->msk[i];
+            for (int c = 0; c < 3; ++c) dst[i * 3 + c] = on ? b->acc[i * 3 + c] : 0;
+        } else {
+            float w = b->wsum[i] + eps;
+            on = b->wsum[i] > eps;
+            dst_mask[i] = on ? 255 : 0;
+            for (int c = 0; c < 3; ++c) dst[i * 3 + c] = on ? f2s_trunc((float)b->acc[i * 3 + c] / w) : 0;
+        }
+    }
+    return 0;
+}
+
+/* cv.convertScaleAbs on int16 (blender.py:47): min(|v|, 255) */
+SO_API void so_convert_scale_abs_s16(const int16_t *src, size_t n, uint8_t *dst)
+{
+    for (size_t i = 0; i < n; ++i) {
+        int v = src[i] < 0 ? -(int)src[i] : src[i];
+        dst[i] = (uint8_t)(v > 255 ? 255 : v);
+    }
+}
