@@ -1,0 +1,159 @@
+/*
+ * stitch_b200.h -- C ABI of libstitch_b200.so: the B200-native (sm_100a) compositing hot path of
+ * OpenStitching/stitching, i.e. what stitching/warper.py and stitching/blender.py reach in OpenCV.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every int-returning entry returns SB_OK (0) or a
+ *     negative sb_status, and sb_last_error() gives the text for the calling thread.
+ *   - host pointers belong to the caller for the duration of a call; nothing is retained after
+ *     return except inside opaque handles.  Device memory is owned by the library.
+ *   - images are uint8 HxWx3 interleaved with a row pitch in BYTES; masks are uint8 HxW.
+ *   - K and R are row-major float32 3x3 (warper.py:84-94 get_K, camera.R).
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry fails with
+ *     SB_ERR_NO_DEVICE.
+ *
+ * Each entry cites the reference interface it replaces (file:line in OpenStitching/stitching v0.7.0).
+ */
+#ifndef STITCH_B200_H
+#define STITCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_API __attribute__((visibility("default")))
+
+typedef enum {
+    SB_OK = 0,
+    SB_ERR_INVALID = -1,   /* bad argument (what cv2 would assert on) */
+    SB_ERR_NO_DEVICE = -2, /* no CUDA device / not sm_100 */
+    SB_ERR_CUDA = -3,      /* CUDA runtime failure, see sb_last_error */
+    SB_ERR_STATE = -4,     /* call order violation (feed before prepare, blend twice, ...) */
+    SB_ERR_NOMEM = -5,
+    SB_ERR_COMM = -6       /* NCCL failure */
+} sb_status;
+
+/* warper.py:10-27 WARP_TYPE_CHOICES; the four projections on the hot path */
+typedef enum { SB_WARP_SPHERICAL = 0, SB_WARP_CYLINDRICAL = 1, SB_WARP_PLANE = 2, SB_WARP_AFFINE = 3 } sb_warp_type;
+/* blender.py:8-12 BLENDER_CHOICES */
+typedef enum { SB_BLEND_NO = 0, SB_BLEND_FEATHER = 1, SB_BLEND_MULTIBAND = 2 } sb_blend_kind;
+
+SB_API const char *sb_last_error(void);
+SB_API const char *sb_version(void);
+
+/* Select the CUDA device of this process (one process per GPU).  Must be called before any other
+ * compute entry; calling it again with the same ordinal is a no-op. */
+SB_API int sb_init(int device_ordinal);
+/* name, SM count, compute capability of the selected device (any pointer may be NULL) */
+SB_API int sb_device_info(char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
+SB_API unsigned long long sb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Warper  (stitching/warper.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* warper.py:79-82  Warper.warp_roi -> cv.PyRotationWarper.warpRoi.
+ * Host-only (libm) -- out_rect = {tl.x, tl.y, width, height}. */
+SB_API int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h,
+                       int out_rect[4]);
+
+/* warper.py:43-52 Warper.warp_image   -> PyRotationWarper.warp(INTER_LINEAR, BORDER_REFLECT)
+ * warper.py:58-68 create_and_warp_mask -> PyRotationWarper.warp(INTER_NEAREST, BORDER_CONSTANT) on a 255 mask
+ * Both outputs come from ONE kernel pass.  dst_img / dst_mask may each be NULL; their extents must be
+ * out_rect[3] rows x out_rect[2] columns as given by sb_warp_roi for the same arguments.
+ * src may be NULL when dst_img is NULL (mask only needs the source size). */
+SB_API int sb_warp(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w,
+                   int src_h, size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask,
+                   size_t mask_pitch, int out_rect[4]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Blender  (stitching/blender.py)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sb_blender sb_blender;
+
+/* blender.py:27-36: kind + setNumBands(num_bands) / setSharpness(sharpness) */
+SB_API sb_blender *sb_blender_create(int kind, int num_bands, float sharpness);
+SB_API void sb_blender_destroy(sb_blender *b);
+/* blender.py:38 blender.prepare(dst_roi): dst_roi = cv.detail.resultRoi(corners, sizes) (blender.py:24) */
+SB_API int sb_blender_prepare(sb_blender *b, int x, int y, int w, int h);
+/* effective number of bands after MultiBandBlender::prepare's clipping (valid after prepare) */
+SB_API int sb_blender_num_bands(const sb_blender *b);
+/* blender.py:40-41 Blender.feed(img, mask, corner).  img is uint8 HxWx3 (img_is_s16 = 0) or int16 HxWx3
+ * (img_is_s16 = 1, pitch still in bytes); mask uint8 HxW with gray values 0..255.
+ * The feed is recorded and uploaded; arithmetic is deferred to sb_blender_blend, which applies the
+ * feeds in call order (results are identical to eager accumulation). */
+SB_API int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_pitch, const uint8_t *mask,
+                           size_t mask_pitch, int w, int h, int tl_x, int tl_y);
+/* blender.py:43-48 Blender.blend(): ::blend + cv.convertScaleAbs.  dst is uint8 HxWx3 of the prepared
+ * roi size, dst_mask uint8 HxW; dst_s16 (nullable) additionally receives the int16 result before
+ * convertScaleAbs (pitch in bytes).  The blender returns to the un-prepared state. */
+SB_API int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch,
+                            int16_t *dst_s16, size_t s16_pitch);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused compositor: warp + blend with every intermediate resident in HBM.
+ * The call sequence replaces stitcher.py:178-189 (warp_final_resolution) + :241-259 (prepare / feed /
+ * blend) for a fixed rig; one compositor = one rig geometry (plan), run once per batch of frames.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sb_compositor sb_compositor;
+
+typedef struct {
+    int n_images;
+    int warp_type;        /* sb_warp_type */
+    float scale;          /* Warper.scale * aspect (warper.py:44) */
+    int blend_kind;       /* sb_blend_kind */
+    float blend_strength; /* blender.py:14 DEFAULT_BLEND_STRENGTH = 5; num_bands / sharpness derived as blender.py:25-36 */
+    const int *src_w;     /* [n] */
+    const int *src_h;     /* [n] */
+    const float *K;       /* [n][9] */
+    const float *R;       /* [n][9] */
+    int mask_mode;        /* 0: blend mask = warped validity mask (seam finder "no"); 1: masks supplied via sb_compositor_set_mask */
+} sb_rig;
+
+SB_API sb_compositor *sb_compositor_create(const sb_rig *rig);
+SB_API void sb_compositor_destroy(sb_compositor *c);
+/* geometry of the plan: per image warped rect {x,y,w,h} (== sb_warp_roi) and the pano roi {x,y,w,h} */
+SB_API int sb_compositor_geometry(const sb_compositor *c, int *rects /*[n][4]*/, int pano_roi[4], int *num_bands);
+/* bytes moved by one run according to the compulsory-traffic model, for the roofline */
+SB_API int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_stage /*[8]*/);
+/* host -> device copy of source image i (uint8 HxWx3); asynchronous on the compositor stream when
+ * `pinned` != 0 (caller guarantees page-locked memory and keeps it alive until sync) */
+SB_API int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pitch, int pinned);
+/* optional per-image blend mask in warped coordinates (mask_mode 1), uint8 h' x w' */
+SB_API int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t pitch);
+/* enqueue warp + blend on the compositor stream (no host sync) */
+SB_API int sb_compositor_run(sb_compositor *c);
+/* device -> host copy of the panorama (uint8 HxWx3 + uint8 mask); synchronises */
+SB_API int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch);
+/* device -> host copy of warped image i / its mask (for parity tests of the fused path) */
+SB_API int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask,
+                                         size_t mask_pitch);
+SB_API int sb_compositor_sync(sb_compositor *c);
+/* time `iters` back-to-back runs with CUDA events on the compositor stream; flush_l2 != 0 writes a
+ * buffer larger than L2 between runs (outside the timed intervals).  ms_total = sum of the intervals. */
+SB_API int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_total);
+/* per-kernel-family device time of the last sb_compositor_time call, averaged per run:
+ * names[] receives up to `cap` static strings, ms[] the matching times.  Returns count. */
+SB_API int sb_compositor_stage_times(sb_compositor *c, const char **names, float *ms, int cap);
+
+/* page-locked host memory for the e2e path */
+SB_API void *sb_host_alloc(size_t bytes);
+SB_API void sb_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU): images are sharded over ranks, each rank composites its shard
+ * and the per-band accumulators of overlapping footprints are exchanged with NCCL.
+ * ------------------------------------------------------------------------------------------- */
+#define SB_COMM_ID_BYTES 128
+SB_API int sb_comm_unique_id(uint8_t id[SB_COMM_ID_BYTES]);
+SB_API int sb_comm_init(const uint8_t id[SB_COMM_ID_BYTES], int rank, int world);
+SB_API int sb_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STITCH_B200_H */

@@ -1,0 +1,38 @@
+"""stitching_b200 -- the compositing hot path of OpenStitching/stitching on NVIDIA B200 (sm_100a).
+
+Drop-in replacements for `stitching.warper.Warper` and `stitching.blender.Blender` (same interface) backed
+by hand-written CUDA kernels behind a C ABI (include/stitch_b200.h), plus a fused `Compositor`.
+`install()` swaps them into an installed `stitching` package so that Stitcher / AffineStitcher / the CLI run
+unchanged.
+"""
+from .blender import Blender  # noqa: F401
+from .compositor import Compositor  # noqa: F401
+from .stitching_error import StitchingError, StitchingWarning  # noqa: F401
+from .warper import Warper  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def install(stitching_module=None):
+    """Route `stitching.Stitcher` (and cropper / seam finder / verbose callers) through the B200 classes.
+
+    The reference modules bind the class names at import time (`from .warper import Warper` in
+    stitcher.py, cropper.py, seam_finder.py, verbose.py), so the names are patched in each of them.
+    """
+    import importlib
+
+    if stitching_module is None:
+        stitching_module = importlib.import_module("stitching")
+    pkg = stitching_module.__name__
+    for mod, names in (
+        ("warper", ("Warper",)), ("blender", ("Blender",)), ("stitcher", ("Warper", "Blender")),
+        ("cropper", ("Blender",)), ("seam_finder", ("Blender",)), ("verbose", ("Warper", "Blender")),
+    ):
+        try:
+            m = importlib.import_module(f"{pkg}.{mod}")
+        except Exception:
+            continue
+        for name in names:
+            if hasattr(m, name):
+                setattr(m, name, {"Warper": Warper, "Blender": Blender}[name])
+    return stitching_module

@@ -1,0 +1,121 @@
+"""Fused warp + blend on one B200 with every intermediate resident in HBM (sb_compositor_* in the C ABI).
+
+Equivalent to running, for a fixed rig, stitcher.py:178-189 (Warper.warp_images / create_and_warp_masks /
+warp_rois at final resolution) and stitcher.py:241-259 (Blender.prepare / feed / blend) -- with the warped
+validity mask as blend mask (seam finder "no") -- but with one host->device copy of the sources and one
+device->host copy of the panorama.
+"""
+import ctypes as C
+from statistics import median
+
+import numpy as np
+
+from . import _lib
+from .stitching_error import StitchingError
+from .warper import Warper
+
+
+class Compositor:
+    def __init__(self, cameras, sizes, warper_type="spherical", blender_type="multiband", blend_strength=5, scale=None,
+                 aspect=1):
+        """cameras: objects with .focal, .K(), .R (cv.detail.CameraParams or rigs.Camera); sizes: [(w, h)]."""
+        n = len(cameras)
+        if n == 0 or len(sizes) != n:
+            raise StitchingError("Compositor needs one size per camera")
+        if warper_type not in _lib.WARP_TYPES:
+            raise StitchingError(f"warper type '{warper_type}' is not on the B200 path")
+        if blender_type not in _lib.BLEND_KINDS:
+            raise StitchingError(f"unknown blender type '{blender_type}'")
+        self.n = n
+        self.sizes = [(int(w), int(h)) for w, h in sizes]
+        if scale is None:
+            scale = median([cam.focal for cam in cameras])  # Warper.set_scale
+        self.scale = scale * aspect
+        self._K = np.ascontiguousarray(np.stack([Warper.get_K(c, aspect) for c in cameras]).astype(np.float32))
+        self._R = np.ascontiguousarray(np.stack([np.asarray(c.R, np.float32) for c in cameras]))
+        self._w = (C.c_int * n)(*[s[0] for s in self.sizes])
+        self._h = (C.c_int * n)(*[s[1] for s in self.sizes])
+        rig = _lib.Rig(n, _lib.WARP_TYPES[warper_type], np.float32(self.scale), _lib.BLEND_KINDS[blender_type],
+                       np.float32(blend_strength), self._w, self._h, self._K.ctypes.data_as(_lib.c_float_p),
+                       self._R.ctypes.data_as(_lib.c_float_p), 0)
+        L = _lib.lib()
+        self._c = L.sb_compositor_create(C.byref(rig))
+        if not self._c:
+            _lib.check(-1, "sb_compositor_create")
+        rects = (C.c_int * (4 * n))()
+        roi = (C.c_int * 4)()
+        nb = C.c_int()
+        _lib.check(L.sb_compositor_geometry(self._c, rects, roi, C.byref(nb)), "sb_compositor_geometry")
+        self.rects = [tuple(rects[4 * i: 4 * i + 4]) for i in range(n)]
+        self.roi = tuple(roi)
+        self.num_bands = nb.value
+        self._pinned = []
+
+    # -- data movement ---------------------------------------------------------------------------
+    def upload(self, images, pinned=False):
+        L = _lib.lib()
+        for i, img in enumerate(images):
+            img = np.asarray(img)
+            if img.dtype != np.uint8 or img.shape != (self.sizes[i][1], self.sizes[i][0], 3):
+                raise StitchingError(f"image {i}: expected uint8 {self.sizes[i][1]}x{self.sizes[i][0]}x3")
+            if img.strides[2] != 1 or img.strides[1] != 3:
+                img = np.ascontiguousarray(img)
+            _lib.check(L.sb_compositor_upload(self._c, i, img.ctypes.data_as(C.c_void_p), img.strides[0], int(pinned)),
+                       "sb_compositor_upload")
+
+    def run(self):
+        _lib.check(_lib.lib().sb_compositor_run(self._c), "sb_compositor_run")
+
+    def sync(self):
+        _lib.check(_lib.lib().sb_compositor_sync(self._c), "sb_compositor_sync")
+
+    def download(self, out=None, out_mask=None):
+        _, _, w, h = self.roi
+        pano = np.empty((h, w, 3), np.uint8) if out is None else out
+        mask = np.empty((h, w), np.uint8) if out_mask is None else out_mask
+        _lib.check(_lib.lib().sb_compositor_download(self._c, pano.ctypes.data_as(C.c_void_p), pano.strides[0],
+                                                     mask.ctypes.data_as(C.c_void_p), mask.strides[0]),
+                   "sb_compositor_download")
+        return pano, mask
+
+    def download_warped(self, i):
+        _, _, w, h = self.rects[i]
+        img = np.empty((h, w, 3), np.uint8)
+        mask = np.empty((h, w), np.uint8)
+        _lib.check(_lib.lib().sb_compositor_download_warped(self._c, i, img.ctypes.data_as(C.c_void_p), w * 3,
+                                                            mask.ctypes.data_as(C.c_void_p), w),
+                   "sb_compositor_download_warped")
+        return img, mask
+
+    def composite(self, images):
+        """One call: upload, warp + blend, download.  Returns (uint8 pano, uint8 mask) like Blender.blend()."""
+        self.upload(images)
+        self.run()
+        return self.download()
+
+    # -- measurement -------------------------------------------------------------------------------
+    def time(self, iters, flush_l2=True):
+        """Device time (ms, CUDA events on the compositor stream) of `iters` runs; returns (total_ms, {stage: ms/run})."""
+        ms = C.c_float()
+        _lib.check(_lib.lib().sb_compositor_time(self._c, int(iters), int(flush_l2), C.byref(ms)), "sb_compositor_time")
+        names = (C.c_char_p * 8)()
+        vals = (C.c_float * 8)()
+        k = _lib.lib().sb_compositor_stage_times(self._c, names, vals, 8)
+        return ms.value, {names[i].decode(): vals[i] for i in range(k)}
+
+    def model_bytes(self):
+        tot = C.c_double()
+        st = (C.c_double * 8)()
+        _lib.check(_lib.lib().sb_compositor_model_bytes(self._c, C.byref(tot), st), "sb_compositor_model_bytes")
+        return tot.value, {"warp": st[0], "pyramid": st[1], "collapse": st[2]}
+
+    def close(self):
+        if getattr(self, "_c", None):
+            _lib.lib().sb_compositor_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,293 @@
+// sb_api.cpp -- the C ABI (include/stitch_b200.h): Warper and Blender entry points with host buffers.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "sb_plan.h"
+
+using namespace sb;
+
+namespace {
+
+bool valid_warp_type(int t) { return t >= SB_WARP_SPHERICAL && t <= SB_WARP_AFFINE; }
+
+// temp device buffers freed in stream order when the scope ends
+struct Scratch {
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    ~Scratch()
+    {
+        for (void *p : ptrs) dev_free(p, s);
+    }
+    template <typename T>
+    int get(T **p, size_t count)
+    {
+        void *q = nullptr;
+        int r = dev_alloc(&q, count * sizeof(T), s);
+        if (r == SB_OK) ptrs.push_back(q);
+        *p = (T *)q;
+        return r;
+    }
+};
+
+}  // namespace
+
+namespace sb {
+// shared with the compositor: builds the device tables + job for one image; tables go into `tab` (4 arrays)
+int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, float *tab_dev, WarpJob *job, cudaStream_t s,
+                  std::vector<float> &host_tab)
+{
+    const int w = rect[2], h = rect[3];
+    host_tab.resize((size_t)2 * w + 2 * h);
+    float *colX = host_tab.data(), *colZ = colX + w, *rowA = colZ + w, *rowY = rowA + h;
+    projector_tables(p, rect, colX, colZ, rowA, rowY);
+    SB_CUDA(cudaMemcpyAsync(tab_dev, host_tab.data(), host_tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    std::memset(job, 0, sizeof *job);
+    job->sw = src_w;
+    job->sh = src_h;
+    job->dw = w;
+    job->dh = h;
+    job->colX = tab_dev;
+    job->colZ = tab_dev + w;
+    job->rowA = tab_dev + 2 * w;
+    job->rowY = tab_dev + 2 * w + h;
+    std::memcpy(job->k, p.k_rinv, sizeof job->k);
+    job->always_divide = p.type == SB_WARP_PLANE;
+    return SB_OK;
+}
+}  // namespace sb
+
+extern "C" {
+
+int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h, int out_rect[4])
+{
+    if (!valid_warp_type(warp_type) || !K || !R || !out_rect || src_w <= 0 || src_h <= 0) {
+        set_error("sb_warp_roi: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    Projector p;
+    projector_setup(p, warp_type, scale, K, R);
+    projector_roi(p, src_w, src_h, out_rect);
+    return SB_OK;
+}
+
+int sb_warp(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w, int src_h,
+            size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int out_rect[4])
+{
+    if (!valid_warp_type(warp_type) || !K || !R || !out_rect || src_w <= 0 || src_h <= 0 || (dst_img && !src) ||
+        (src && src_pitch < (size_t)src_w * 3)) {
+        set_error("sb_warp: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    Projector p;
+    projector_setup(p, warp_type, scale, K, R);
+    int rect[4];
+    projector_roi(p, src_w, src_h, rect);
+    std::memcpy(out_rect, rect, sizeof rect);
+    if (!dst_img && !dst_mask) return SB_OK;
+    const int w = rect[2], h = rect[3];
+    if (w <= 0 || h <= 0 || (long long)w * h > (1ll << 31)) {
+        set_error("sb_warp: degenerate result roi %dx%d", w, h);
+        return SB_ERR_INVALID;
+    }
+    if ((dst_img && dst_pitch < (size_t)w * 3) || (dst_mask && mask_pitch < (size_t)w)) {
+        set_error("sb_warp: destination pitch too small for roi width %d", w);
+        return SB_ERR_INVALID;
+    }
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    float *tab = nullptr;
+    uint8_t *d_src = nullptr, *d_img = nullptr, *d_mask = nullptr;
+    WarpJob *d_job = nullptr;
+    SB_TRY(tmp.get(&tab, (size_t)2 * w + 2 * h));
+    SB_TRY(tmp.get(&d_job, 1));
+    std::vector<float> host_tab;
+    WarpJob job;
+    SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));
+    if (dst_img) {
+        SB_TRY(tmp.get(&d_src, (size_t)src_w * 3 * src_h));
+        SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
+        SB_CUDA(cudaMemcpy2DAsync(d_src, (size_t)src_w * 3, src, src_pitch, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, s));
+        job.src = d_src;
+        job.spitch = (long long)src_w * 3;
+        job.dst_rgb = d_img;
+        job.dst_pitch = (long long)w * 3;
+    }
+    if (dst_mask) {
+        SB_TRY(tmp.get(&d_mask, (size_t)w * h));
+        job.dst_mask = d_mask;
+        job.mask_pitch = w;
+    }
+    SB_CUDA(cudaMemcpyAsync(d_job, &job, sizeof job, cudaMemcpyHostToDevice, s));
+    SB_TRY(launch_warp(d_job, 1, w, h, s));
+    if (dst_img) SB_CUDA(cudaMemcpy2DAsync(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));
+    if (dst_mask) SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Blender
+// -------------------------------------------------------------------------------------------------
+struct sb_blender {
+    int kind;
+    int num_bands;
+    float sharpness;
+    bool prepared = false;
+    BlendPlan plan;
+    std::vector<void *> level0;  // device buffers of the recorded feeds
+};
+
+sb_blender *sb_blender_create(int kind, int num_bands, float sharpness)
+{
+    if (kind < SB_BLEND_NO || kind > SB_BLEND_MULTIBAND) {
+        set_error("sb_blender_create: unknown kind %d", kind);
+        return nullptr;
+    }
+    sb_blender *b = new sb_blender;
+    b->kind = kind;
+    b->num_bands = num_bands;
+    b->sharpness = sharpness;
+    return b;
+}
+
+static void blender_drop_feeds(sb_blender *b)
+{
+    cudaStream_t s = default_stream();
+    for (void *p : b->level0) dev_free(p, s);
+    b->level0.clear();
+    b->plan.release(s);
+    b->plan.imgs.clear();
+}
+
+void sb_blender_destroy(sb_blender *b)
+{
+    if (!b) return;
+    blender_drop_feeds(b);
+    delete b;
+}
+
+int sb_blender_prepare(sb_blender *b, int x, int y, int w, int h)
+{
+    if (!b) {
+        set_error("sb_blender_prepare: null handle");
+        return SB_ERR_INVALID;
+    }
+    blender_drop_feeds(b);
+    b->prepared = false;
+    SB_TRY(b->plan.set_geometry(b->kind, b->num_bands, b->sharpness, Rect{x, y, w, h}));
+    b->prepared = true;
+    return SB_OK;
+}
+
+int sb_blender_num_bands(const sb_blender *b) { return b ? b->plan.nb : -1; }
+
+int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_pitch, const uint8_t *mask, size_t mask_pitch,
+                    int w, int h, int tl_x, int tl_y)
+{
+    if (!b || !img || !mask || w <= 0 || h <= 0) {
+        set_error("sb_blender_feed: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    if (!b->prepared) {
+        set_error("sb_blender_feed: prepare() has not been called");
+        return SB_ERR_STATE;
+    }
+    const size_t px_bytes = img_is_s16 ? 6 : 3;
+    if (img_pitch < (size_t)w * px_bytes || mask_pitch < (size_t)w) {
+        set_error("sb_blender_feed: pitch smaller than a row");
+        return SB_ERR_INVALID;
+    }
+    FeedDesc f;
+    std::memset(&f, 0, sizeof f);
+    f.w = w; f.h = h; f.tlx = tl_x; f.tly = tl_y;
+    // geometry first (host only) so that an out-of-roi feed fails before any device work
+    SB_TRY(b->plan.add_feed(f));
+    FeedImage &im = b->plan.imgs.back();
+    auto upload = [&]() -> int {
+        SB_TRY(ensure_device());
+        cudaStream_t s = default_stream();
+        uint8_t *d_mask = nullptr;
+        void *d_img = nullptr;
+        SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
+        b->level0.push_back(d_mask);
+        SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
+        SB_TRY(dev_alloc(&d_img, (size_t)w * h * px_bytes, s));
+        b->level0.push_back(d_img);
+        SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * px_bytes, img, img_pitch, (size_t)w * px_bytes, h, cudaMemcpyHostToDevice, s));
+        if (img_is_s16) {
+            im.s16 = (const int16_t *)d_img;
+            im.s16_pitch = (long long)w * 3;
+            im.mask = d_mask;
+            im.mask_pitch = w;
+        } else {
+            uint32_t *d_rgbm = nullptr;
+            SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)w * h * 4, s));
+            b->level0.push_back(d_rgbm);
+            SB_TRY(launch_pack_rgbm((const uint8_t *)d_img, (long long)w * 3, d_mask, w, d_rgbm, w, w, h, s));
+            im.rgbm = d_rgbm;
+            im.rgbm_pitch = w;
+        }
+        // the caller's buffers may be reused as soon as we return
+        SB_CUDA(cudaStreamSynchronize(s));
+        return SB_OK;
+    };
+    const int rc = upload();
+    if (rc != SB_OK) b->plan.imgs.pop_back();
+    return rc;
+}
+
+int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int16_t *dst_s16,
+                     size_t s16_pitch)
+{
+    if (!b) {
+        set_error("sb_blender_blend: null handle");
+        return SB_ERR_INVALID;
+    }
+    if (!b->prepared) {
+        set_error("sb_blender_blend: prepare() has not been called (or blend() was already called)");
+        return SB_ERR_STATE;
+    }
+    const int w = b->plan.roi.w, h = b->plan.roi.h;
+    if ((dst && dst_pitch < (size_t)w * 3) || (dst_mask && mask_pitch < (size_t)w) || (dst_s16 && s16_pitch < (size_t)w * 6)) {
+        set_error("sb_blender_blend: destination pitch too small for roi width %d", w);
+        return SB_ERR_INVALID;
+    }
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    PanoOut out;
+    std::memset(&out, 0, sizeof out);
+    out.w = w;
+    out.h = h;
+    if (dst) {
+        SB_TRY(tmp.get(&out.rgb, (size_t)w * 3 * h));
+        out.rgb_pitch = (long long)w * 3;
+    }
+    if (dst_mask) {
+        SB_TRY(tmp.get(&out.mask, (size_t)w * h));
+        out.mask_pitch = w;
+    }
+    if (dst_s16) {
+        SB_TRY(tmp.get(&out.s16, (size_t)w * 3 * h));
+        out.s16_pitch = (long long)w * 3;
+    }
+    int rc = b->plan.allocate(s);
+    if (rc == SB_OK) rc = b->plan.run(out, s);
+    if (rc == SB_OK) {
+        if (dst) SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, out.rgb, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));
+        if (dst_mask) SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, out.mask, w, w, h, cudaMemcpyDeviceToHost, s));
+        if (dst_s16) SB_CUDA(cudaMemcpy2DAsync(dst_s16, s16_pitch, out.s16, (size_t)w * 6, (size_t)w * 6, h, cudaMemcpyDeviceToHost, s));
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    // like OpenCV, blend() consumes the state: a new prepare() is needed before the next feed
+    blender_drop_feeds(b);
+    b->prepared = false;
+    return rc;
+}
+
+}  // extern "C"

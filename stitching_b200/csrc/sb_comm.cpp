@@ -1,0 +1,99 @@
+// sb_comm.cpp -- NCCL plumbing for the multi-GPU path (one process per GPU).  NCCL is resolved with
+// dlopen at first use so that single-GPU users do not need it installed.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "sb_internal.h"
+
+namespace {
+struct ncclUniqueIdRaw { char internal[128]; };
+typedef void *ncclComm_t;
+typedef int (*fn_get_unique_id)(ncclUniqueIdRaw *);
+typedef int (*fn_comm_init_rank)(ncclComm_t *, int, ncclUniqueIdRaw, int);
+typedef int (*fn_comm_destroy)(ncclComm_t);
+typedef const char *(*fn_get_error_string)(int);
+
+void *g_nccl = nullptr;
+fn_get_unique_id p_get_unique_id = nullptr;
+fn_comm_init_rank p_comm_init_rank = nullptr;
+fn_comm_destroy p_comm_destroy = nullptr;
+fn_get_error_string p_err = nullptr;
+ncclComm_t g_comm = nullptr;
+int g_rank = 0, g_world = 1;
+
+int load_nccl()
+{
+    if (g_nccl) return SB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl) break;
+    }
+    if (!g_nccl) {
+        sb::set_error("NCCL not found: %s", dlerror());
+        return SB_ERR_COMM;
+    }
+    p_get_unique_id = (fn_get_unique_id)dlsym(g_nccl, "ncclGetUniqueId");
+    p_comm_init_rank = (fn_comm_init_rank)dlsym(g_nccl, "ncclCommInitRank");
+    p_comm_destroy = (fn_comm_destroy)dlsym(g_nccl, "ncclCommDestroy");
+    p_err = (fn_get_error_string)dlsym(g_nccl, "ncclGetErrorString");
+    if (!p_get_unique_id || !p_comm_init_rank || !p_comm_destroy) {
+        sb::set_error("NCCL library lacks required symbols");
+        return SB_ERR_COMM;
+    }
+    return SB_OK;
+}
+int nccl_fail(int rc, const char *what)
+{
+    sb::set_error("NCCL error %d (%s) in %s", rc, p_err ? p_err(rc) : "?", what);
+    return SB_ERR_COMM;
+}
+}  // namespace
+
+namespace sb {
+void *comm_handle() { return g_comm; }
+void *comm_library() { return g_nccl; }
+int comm_rank() { return g_rank; }
+int comm_world() { return g_world; }
+}  // namespace sb
+
+extern "C" {
+
+int sb_comm_unique_id(uint8_t id[SB_COMM_ID_BYTES])
+{
+    SB_TRY(load_nccl());
+    ncclUniqueIdRaw raw;
+    int rc = p_get_unique_id(&raw);
+    if (rc) return nccl_fail(rc, "ncclGetUniqueId");
+    std::memcpy(id, raw.internal, SB_COMM_ID_BYTES);
+    return SB_OK;
+}
+
+int sb_comm_init(const uint8_t id[SB_COMM_ID_BYTES], int rank, int world)
+{
+    SB_TRY(sb::ensure_device());
+    SB_TRY(load_nccl());
+    if (g_comm) {
+        sb::set_error("sb_comm_init: communicator already initialised");
+        return SB_ERR_STATE;
+    }
+    ncclUniqueIdRaw raw;
+    std::memcpy(raw.internal, id, SB_COMM_ID_BYTES);
+    int rc = p_comm_init_rank(&g_comm, world, raw, rank);
+    if (rc) return nccl_fail(rc, "ncclCommInitRank");
+    g_rank = rank;
+    g_world = world;
+    return SB_OK;
+}
+
+int sb_comm_destroy(void)
+{
+    if (g_comm && p_comm_destroy) p_comm_destroy(g_comm);
+    g_comm = nullptr;
+    g_rank = 0;
+    g_world = 1;
+    return SB_OK;
+}
+
+}  // extern "C"

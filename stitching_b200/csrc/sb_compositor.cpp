@@ -1,0 +1,344 @@
+// sb_compositor.cpp -- fused warp + blend with every intermediate resident in HBM.
+//
+// One compositor is the plan of one rig: what stitcher.py:178-189 (warp_final_resolution -> Warper.warp_images,
+// create_and_warp_masks, warp_rois) and stitcher.py:241-259 (Blender.prepare / feed / blend) compute for a
+// fixed set of cameras.  Creation does the host geometry once (roi detection, trig tables, padded rects,
+// storage); run() enqueues warp -> pyramids -> collapse for a batch of frames without touching the host.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "sb_plan.h"
+
+namespace sb {
+int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, float *tab_dev, WarpJob *job, cudaStream_t s,
+                  std::vector<float> &host_tab);
+}
+using namespace sb;
+
+struct sb_compositor {
+    int n = 0;
+    int warp_type = 0, blend_kind_requested = 0, mask_mode = 0;
+    float scale = 1.f, blend_strength = 5.f;
+    cudaStream_t stream = nullptr;
+    std::vector<int> src_w, src_h;
+    std::vector<Rect> rects;           // warped rects (pano-absolute)
+    std::vector<WarpJob> jobs;         // host copy
+    WarpJob *jobs_dev = nullptr;
+    std::vector<uint8_t *> src_dev;    // u8x3 sources
+    std::vector<uint32_t *> rgbm_dev;  // warped, packed
+    std::vector<float *> tab_dev;
+    std::vector<uint8_t *> usermask_dev;
+    int max_w = 0, max_h = 0;
+    BlendPlan plan;
+    PanoOut out;                       // device outputs
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, warp, pyr, collapse
+    float stage_ms[3] = {0, 0, 0};
+    double warp_bytes = 0;
+};
+
+static void compositor_free(sb_compositor *c)
+{
+    if (!c) return;
+    cudaStream_t s = c->stream ? c->stream : default_stream();
+    if (c->stream) (void)cudaStreamSynchronize(c->stream);
+    for (auto p : c->src_dev) dev_free(p, s);
+    for (auto p : c->rgbm_dev) dev_free(p, s);
+    for (auto p : c->tab_dev) dev_free(p, s);
+    for (auto p : c->usermask_dev) dev_free(p, s);
+    dev_free(c->jobs_dev, s);
+    dev_free(c->out.rgb, s);
+    dev_free(c->out.mask, s);
+    dev_free(c->flush_buf, s);
+    c->plan.release(s);
+    for (auto &e : c->ev)
+        if (e) (void)cudaEventDestroy(e);
+    if (c->stream) {
+        (void)cudaStreamSynchronize(c->stream);
+        (void)cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+static int compositor_build(sb_compositor *c, const sb_rig *rig)
+{
+    const int n = rig->n_images;
+    c->n = n;
+    c->warp_type = rig->warp_type;
+    c->scale = rig->scale;
+    c->blend_kind_requested = rig->blend_kind;
+    c->blend_strength = rig->blend_strength;
+    c->mask_mode = rig->mask_mode;
+    SB_TRY(ensure_device());
+    SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaStream_t s = c->stream;
+    for (auto &e : c->ev) SB_CUDA(cudaEventCreate(&e));
+
+    c->src_w.assign(rig->src_w, rig->src_w + n);
+    c->src_h.assign(rig->src_h, rig->src_h + n);
+    c->rects.resize(n);
+    c->jobs.resize(n);
+    c->src_dev.assign(n, nullptr);
+    c->rgbm_dev.assign(n, nullptr);
+    c->tab_dev.assign(n, nullptr);
+    c->usermask_dev.assign(n, nullptr);
+    std::vector<int> corners(2 * n), sizes(2 * n);
+    std::vector<float> host_tab;
+    for (int i = 0; i < n; ++i) {
+        Projector p;
+        projector_setup(p, rig->warp_type, rig->scale, rig->K + 9 * i, rig->R + 9 * i);
+        int rect[4];
+        projector_roi(p, c->src_w[i], c->src_h[i], rect);
+        if (rect[2] <= 0 || rect[3] <= 0 || (long long)rect[2] * rect[3] > (1ll << 31)) {
+            set_error("compositor: degenerate warped roi %dx%d for image %d", rect[2], rect[3], i);
+            return SB_ERR_INVALID;
+        }
+        c->rects[i] = Rect{rect[0], rect[1], rect[2], rect[3]};
+        corners[2 * i] = rect[0];
+        corners[2 * i + 1] = rect[1];
+        sizes[2 * i] = rect[2];
+        sizes[2 * i + 1] = rect[3];
+        c->max_w = std::max(c->max_w, rect[2]);
+        c->max_h = std::max(c->max_h, rect[3]);
+        SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i], s));
+        SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rect[2] * rect[3] * 4, s));
+        SB_TRY(dev_alloc((void **)&c->tab_dev[i], ((size_t)2 * rect[2] + 2 * rect[3]) * sizeof(float), s));
+        SB_TRY(make_warp_job(p, rect, c->src_w[i], c->src_h[i], c->tab_dev[i], &c->jobs[i], s, host_tab));
+        SB_CUDA(cudaStreamSynchronize(s));  // host_tab is reused by the next image
+        c->jobs[i].src = c->src_dev[i];
+        c->jobs[i].spitch = (long long)c->src_w[i] * 3;
+        c->jobs[i].dst_rgbm = c->rgbm_dev[i];
+        c->jobs[i].rgbm_pitch = rect[2];
+        c->warp_bytes += 3.0 * c->src_w[i] * c->src_h[i] + 4.0 * rect[2] * rect[3];
+    }
+    SB_TRY(dev_alloc((void **)&c->jobs_dev, sizeof(WarpJob) * n, s));
+    SB_CUDA(cudaMemcpyAsync(c->jobs_dev, c->jobs.data(), sizeof(WarpJob) * n, cudaMemcpyHostToDevice, s));
+
+    // Blender.prepare (blender.py:23-38)
+    const Rect roi = result_roi(corners.data(), sizes.data(), n);
+    int kind, nbr;
+    float sharp;
+    derive_blend_params(rig->blend_kind, rig->blend_strength, roi, &kind, &nbr, &sharp);
+    SB_TRY(c->plan.set_geometry(kind, nbr, sharp, roi));
+    for (int i = 0; i < n; ++i) {
+        FeedDesc f;
+        std::memset(&f, 0, sizeof f);
+        f.w = c->rects[i].w;
+        f.h = c->rects[i].h;
+        f.tlx = c->rects[i].x;
+        f.tly = c->rects[i].y;
+        f.rgbm = c->rgbm_dev[i];
+        f.rgbm_pitch = c->rects[i].w;
+        SB_TRY(c->plan.add_feed(f));
+    }
+    SB_TRY(c->plan.allocate(s));
+    std::memset(&c->out, 0, sizeof c->out);
+    c->out.w = roi.w;
+    c->out.h = roi.h;
+    c->out.rgb_pitch = (long long)roi.w * 3;
+    c->out.mask_pitch = roi.w;
+    SB_TRY(dev_alloc((void **)&c->out.rgb, (size_t)roi.w * 3 * roi.h, s));
+    SB_TRY(dev_alloc((void **)&c->out.mask, (size_t)roi.w * roi.h, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+static int compositor_enqueue(sb_compositor *c, bool events)
+{
+    cudaStream_t s = c->stream;
+    if (events) SB_CUDA(cudaEventRecord(c->ev[0], s));
+    SB_TRY(launch_warp(c->jobs_dev, c->n, c->max_w, c->max_h, s));
+    if (events) SB_CUDA(cudaEventRecord(c->ev[1], s));
+    SB_TRY(c->plan.run(c->out, s, events ? &c->ev[2] : nullptr));
+    return SB_OK;
+}
+
+extern "C" {
+
+sb_compositor *sb_compositor_create(const sb_rig *rig)
+{
+    if (!rig || rig->n_images <= 0 || rig->n_images > SB_MAX_IMAGES || !rig->src_w || !rig->src_h || !rig->K || !rig->R ||
+        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_AFFINE || rig->blend_kind < SB_BLEND_NO ||
+        rig->blend_kind > SB_BLEND_MULTIBAND) {
+        set_error("sb_compositor_create: invalid rig");
+        return nullptr;
+    }
+    sb_compositor *c = new sb_compositor;
+    if (compositor_build(c, rig) != SB_OK) {
+        compositor_free(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void sb_compositor_destroy(sb_compositor *c) { compositor_free(c); }
+
+int sb_compositor_geometry(const sb_compositor *c, int *rects, int pano_roi[4], int *num_bands)
+{
+    if (!c) {
+        set_error("sb_compositor_geometry: null handle");
+        return SB_ERR_INVALID;
+    }
+    if (rects)
+        for (int i = 0; i < c->n; ++i) {
+            rects[4 * i] = c->rects[i].x;
+            rects[4 * i + 1] = c->rects[i].y;
+            rects[4 * i + 2] = c->rects[i].w;
+            rects[4 * i + 3] = c->rects[i].h;
+        }
+    if (pano_roi) {
+        pano_roi[0] = c->plan.roi.x;
+        pano_roi[1] = c->plan.roi.y;
+        pano_roi[2] = c->plan.roi.w;
+        pano_roi[3] = c->plan.roi.h;
+    }
+    if (num_bands) *num_bands = c->plan.kind == SB_BLEND_MULTIBAND ? c->plan.nb : -1;
+    return SB_OK;
+}
+
+int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_stage)
+{
+    if (!c) {
+        set_error("sb_compositor_model_bytes: null handle");
+        return SB_ERR_INVALID;
+    }
+    double pyr = 0, col = 0;
+    c->plan.model_bytes(&pyr, &col);
+    if (total_bytes) *total_bytes = c->warp_bytes + pyr + col;
+    if (per_stage) {
+        per_stage[0] = c->warp_bytes;
+        per_stage[1] = pyr;
+        per_stage[2] = col;
+        for (int i = 3; i < 8; ++i) per_stage[i] = 0;
+    }
+    return SB_OK;
+}
+
+int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pitch, int pinned)
+{
+    if (!c || i < 0 || i >= c->n || !src || pitch < (size_t)c->src_w[i] * 3) {
+        set_error("sb_compositor_upload: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    SB_CUDA(cudaMemcpy2DAsync(c->src_dev[i], (size_t)c->src_w[i] * 3, src, pitch, (size_t)c->src_w[i] * 3, c->src_h[i],
+                              cudaMemcpyHostToDevice, c->stream));
+    if (!pinned) SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t pitch)
+{
+    (void)mask;
+    (void)pitch;
+    if (!c || i < 0 || i >= c->n) {
+        set_error("sb_compositor_set_mask: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    set_error("sb_compositor_set_mask: mask_mode 1 is not implemented yet");
+    return SB_ERR_INVALID;
+}
+
+int sb_compositor_run(sb_compositor *c)
+{
+    if (!c) {
+        set_error("sb_compositor_run: null handle");
+        return SB_ERR_INVALID;
+    }
+    return compositor_enqueue(c, false);
+}
+
+int sb_compositor_sync(sb_compositor *c)
+{
+    if (!c) return SB_ERR_INVALID;
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch)
+{
+    if (!c || (dst && dst_pitch < (size_t)c->out.w * 3) || (dst_mask && mask_pitch < (size_t)c->out.w)) {
+        set_error("sb_compositor_download: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    if (dst)
+        SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, c->out.rgb, (size_t)c->out.rgb_pitch, (size_t)c->out.w * 3, c->out.h,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    if (dst_mask)
+        SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, c->out.mask, (size_t)c->out.mask_pitch, c->out.w, c->out.h,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch)
+{
+    if (!c || i < 0 || i >= c->n) {
+        set_error("sb_compositor_download_warped: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    const int w = c->rects[i].w, h = c->rects[i].h;
+    std::vector<uint32_t> tmp((size_t)w * h);
+    SB_CUDA(cudaMemcpyAsync(tmp.data(), c->rgbm_dev[i], tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint32_t p = tmp[(size_t)y * w + x];
+            if (dst) {
+                uint8_t *d = dst + (size_t)y * dst_pitch + (size_t)x * 3;
+                d[0] = p & 255;
+                d[1] = (p >> 8) & 255;
+                d[2] = (p >> 16) & 255;
+            }
+            if (dst_mask) dst_mask[(size_t)y * mask_pitch + x] = (uint8_t)(p >> 24);
+        }
+    return SB_OK;
+}
+
+int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_total)
+{
+    if (!c || iters <= 0 || !ms_total) {
+        set_error("sb_compositor_time: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    cudaStream_t s = c->stream;
+    if (flush_l2 && !c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+        SB_TRY(dev_alloc(&c->flush_buf, c->flush_bytes, s));
+    }
+    float total = 0.f;
+    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        if (flush_l2) SB_TRY(launch_flush_l2(c->flush_buf, c->flush_bytes, s));
+        SB_TRY(compositor_enqueue(c, true));
+        SB_CUDA(cudaEventSynchronize(c->ev[3]));
+        float a = 0, b = 0, d = 0;
+        SB_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        SB_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+        SB_CUDA(cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
+        c->stage_ms[0] += a;
+        c->stage_ms[1] += b;
+        c->stage_ms[2] += d;
+        float t = 0;
+        SB_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[3]));
+        total += t;
+    }
+    for (float &v : c->stage_ms) v /= (float)iters;
+    *ms_total = total;
+    return SB_OK;
+}
+
+int sb_compositor_stage_times(sb_compositor *c, const char **names, float *ms, int cap)
+{
+    if (!c) return 0;
+    static const char *kNames[3] = {"warp", "pyramid", "collapse"};
+    int k = std::min(cap, 3);
+    for (int i = 0; i < k; ++i) {
+        if (names) names[i] = kNames[i];
+        if (ms) ms[i] = c->stage_ms[i];
+    }
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// sb_geometry.cpp -- host-side projection set-up, result-roi detection and the separable trig tables.
+//
+// Replaces the geometry half of cv.PyRotationWarper (reached from stitching/warper.py:44-51, 59-67,
+// 80-82): ProjectorBase::setCameraParams, RotationWarperBase::detectResultRoi*, and the per-pixel
+// trig of mapBackward.  Everything here runs on the host with glibc's libm on purpose: the roi is
+// an integer truncation of fp32 libm results (an independent device trig could change the output
+// SHAPE), and spherical / cylindrical mapBackward is separable -- sin/cos depend only on the output
+// column or only on the output row -- so w'+h' libm calls replace w'*h' of them and the device
+// kernel needs no trig at all.
+//
+// This translation unit MUST be compiled without FMA contraction (-ffp-contract=off): every fp32
+// multiply and add is rounded separately, as in the baseline-SSE OpenCV build.
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "sb_internal.h"
+
+namespace sb {
+
+namespace {
+
+struct Mat3 {
+    float m[9];
+    float &operator()(int r, int c) { return m[r * 3 + c]; }
+    float operator()(int r, int c) const { return m[r * 3 + c]; }
+};
+
+// C = A * B, fp32, (a0*b0 + a1*b1) + a2*b2 with each op rounded
+Mat3 mul(const Mat3 &A, const Mat3 &B)
+{
+    Mat3 C;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            float acc = A(r, 0) * B(0, c) + A(r, 1) * B(1, c);
+            acc = acc + A(r, 2) * B(2, c);
+            C(r, c) = acc;
+        }
+    return C;
+}
+
+Mat3 transpose(const Mat3 &A)
+{
+    Mat3 T;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T(r, c) = A(c, r);
+    return T;
+}
+
+// adjugate / determinant in double, one rounding to float per entry (3x3 float closed-form inverse)
+Mat3 inverse(const Mat3 &A)
+{
+    auto a = [&](int r, int c) { return (double)A(r, c); };
+    double c00 = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1);
+    double c01 = a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0);
+    double c02 = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0);
+    double det = a(0, 0) * c00 - a(0, 1) * c01 + a(0, 2) * c02;
+    double id = det != 0.0 ? 1.0 / det : 0.0;
+    Mat3 I;
+    I(0, 0) = (float)(c00 * id);
+    I(0, 1) = (float)((a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2)) * id);
+    I(0, 2) = (float)((a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1)) * id);
+    I(1, 0) = (float)((a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2)) * id);
+    I(1, 1) = (float)((a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0)) * id);
+    I(1, 2) = (float)((a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2)) * id);
+    I(2, 0) = (float)((a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0)) * id);
+    I(2, 1) = (float)((a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1)) * id);
+    I(2, 2) = (float)((a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0)) * id);
+    return I;
+}
+
+const float kPiF = (float)3.14159265358979323846;
+
+// forward projection of one source pixel (PyRotationWarper::warpPoint)
+inline void forward(const Projector &p, float x, float y, float &u, float &v)
+{
+    const float *m = p.r_kinv;
+    float X = m[0] * x + m[1] * y + m[2];
+    float Y = m[3] * x + m[4] * y + m[5];
+    float Z = m[6] * x + m[7] * y + m[8];
+    switch (p.type) {
+        case SB_WARP_SPHERICAL: {
+            u = p.scale * atan2f(X, Z);
+            float w = Y / sqrtf(X * X + Y * Y + Z * Z);
+            if (w != w) w = 0.f;
+            v = p.scale * (kPiF - acosf(w));
+            break;
+        }
+        case SB_WARP_CYLINDRICAL:
+            u = p.scale * atan2f(X, Z);
+            v = p.scale * Y / sqrtf(X * X + Z * Z);
+            break;
+        default: {
+            float one_minus_t2 = 1.f - p.t[2];
+            X = p.t[0] + X / Z * one_minus_t2;
+            Y = p.t[1] + Y / Z * one_minus_t2;
+            u = p.scale * X;
+            v = p.scale * Y;
+        }
+    }
+}
+
+}  // namespace
+
+void projector_setup(Projector &p, int warp_type, float scale, const float *K, const float *R)
+{
+    Mat3 Km, Rm;
+    std::memcpy(Km.m, K, sizeof Km.m);
+    std::memcpy(Rm.m, R, sizeof Rm.m);
+    float T[3] = {0.f, 0.f, 0.f};
+    p.type = warp_type;
+    if (warp_type == SB_WARP_AFFINE) {
+        // AffineStitcher (stitcher.py:267-287): "R" is a homogeneous 2-D affine H.  Split it into a
+        // rotation-like part and a translation the plane projector understands:
+        //   T0 = (H02, H12, 0);  R = (H with those two entries cleared)^T;  T = -(R * T0)
+        float T0[3] = {Rm(0, 2), Rm(1, 2), 0.f};
+        Rm(0, 2) = 0.f;
+        Rm(1, 2) = 0.f;
+        Rm = transpose(Rm);
+        for (int r = 0; r < 3; ++r) {
+            float acc = Rm(r, 0) * T0[0] + Rm(r, 1) * T0[1];
+            acc = acc + Rm(r, 2) * T0[2];
+            T[r] = acc * -1.f;
+        }
+        p.type = SB_WARP_PLANE;
+    }
+    p.scale = scale;
+    Mat3 Rinv = transpose(Rm);
+    Mat3 RKinv = mul(Rm, inverse(Km));
+    Mat3 KRinv = mul(Km, Rinv);
+    std::memcpy(p.k, Km.m, sizeof p.k);
+    std::memcpy(p.rinv, Rinv.m, sizeof p.rinv);
+    std::memcpy(p.r_kinv, RKinv.m, sizeof p.r_kinv);
+    std::memcpy(p.k_rinv, KRinv.m, sizeof p.k_rinv);
+    std::memcpy(p.t, T, sizeof p.t);
+}
+
+void projector_roi(const Projector &p, int W, int H, int rect[4])
+{
+    float lo_u = std::numeric_limits<float>::max(), lo_v = lo_u, hi_u = -lo_u, hi_v = -lo_u;
+    auto visit = [&](float x, float y) {
+        float u, v;
+        forward(p, x, y, u, v);
+        if (u < lo_u) lo_u = u;
+        if (v < lo_v) lo_v = v;
+        if (u > hi_u) hi_u = u;
+        if (v > hi_v) hi_v = v;
+    };
+    if (p.type == SB_WARP_PLANE) {
+        // a projective plane map sends the rectangle to a quadrilateral: its 4 corners bound it
+        visit(0.f, 0.f);
+        visit(0.f, (float)(H - 1));
+        visit((float)(W - 1), 0.f);
+        visit((float)(W - 1), (float)(H - 1));
+    } else {
+        // curved projections: walk the image border
+        for (int x = 0; x < W; ++x) {
+            visit((float)x, 0.f);
+            visit((float)x, (float)(H - 1));
+        }
+        for (int y = 0; y < H; ++y) {
+            visit(0.f, (float)y);
+            visit((float)(W - 1), (float)y);
+        }
+    }
+    // truncation toward zero, not floor
+    int tlx = (int)lo_u, tly = (int)lo_v, brx = (int)hi_u, bry = (int)hi_v;
+
+    if (p.type == SB_WARP_SPHERICAL) {
+        // a pole of the sphere inside the field of view is not on the border walk: test both poles
+        lo_u = (float)tlx; lo_v = (float)tly; hi_u = (float)brx; hi_v = (float)bry;
+        for (int south = 0; south < 2; ++south) {
+            float x = p.rinv[1];
+            float y = south ? -p.rinv[4] : p.rinv[4];
+            float z = p.rinv[7];
+            if (!(y > 0.f)) continue;
+            float xs = (p.k[0] * x + p.k[1] * y) / z + p.k[2];
+            float ys = p.k[4] * y / z + p.k[5];
+            if (xs > 0.f && xs < (float)W && ys > 0.f && ys < (float)H) {
+                float vpole = south ? 0.f : (float)(3.14159265358979323846 * (double)p.scale);
+                if (0.f < lo_u) lo_u = 0.f;
+                if (0.f > hi_u) hi_u = 0.f;
+                if (vpole < lo_v) lo_v = vpole;
+                if (vpole > hi_v) hi_v = vpole;
+            }
+        }
+        tlx = (int)lo_u; tly = (int)lo_v; brx = (int)hi_u; bry = (int)hi_v;
+    }
+    rect[0] = tlx;
+    rect[1] = tly;
+    rect[2] = brx - tlx + 1;
+    rect[3] = bry - tly + 1;
+}
+
+void projector_tables(const Projector &p, const int rect[4], float *colX, float *colZ, float *rowA, float *rowY)
+{
+    const int w = rect[2], h = rect[3];
+    switch (p.type) {
+        case SB_WARP_SPHERICAL:
+            for (int i = 0; i < w; ++i) {
+                float a = (float)(rect[0] + i) / p.scale;
+                colX[i] = sinf(a);
+                colZ[i] = cosf(a);
+            }
+            for (int j = 0; j < h; ++j) {
+                float b = kPiF - (float)(rect[1] + j) / p.scale;
+                rowA[j] = sinf(b);
+                rowY[j] = cosf(b);
+            }
+            break;
+        case SB_WARP_CYLINDRICAL:
+            for (int i = 0; i < w; ++i) {
+                float a = (float)(rect[0] + i) / p.scale;
+                colX[i] = sinf(a);
+                colZ[i] = cosf(a);
+            }
+            for (int j = 0; j < h; ++j) {
+                rowA[j] = 1.f;
+                rowY[j] = (float)(rect[1] + j) / p.scale;
+            }
+            break;
+        default: {
+            float zc = 1.f - p.t[2];
+            for (int i = 0; i < w; ++i) {
+                colX[i] = (float)(rect[0] + i) / p.scale - p.t[0];
+                colZ[i] = zc;
+            }
+            for (int j = 0; j < h; ++j) {
+                rowA[j] = 1.f;
+                rowY[j] = (float)(rect[1] + j) / p.scale - p.t[1];
+            }
+        }
+    }
+}
+
+}  // namespace sb

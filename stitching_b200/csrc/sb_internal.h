@@ -1,0 +1,130 @@
+// sb_internal.h -- shared declarations of libstitch_b200.so (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/stitch_b200.h"
+
+#define SB_MAX_BANDS 16
+#define SB_MAX_IMAGES 256
+
+namespace sb {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define SB_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return sb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define SB_TRY(call)            \
+    do {                        \
+        int r__ = (call);       \
+        if (r__ != SB_OK) return r__; \
+    } while (0)
+
+int ensure_device();  // SB_OK when sb_init succeeded (or lazily selects device 0)
+int sm_count();
+void count_launch(unsigned n = 1);
+cudaStream_t default_stream();
+
+// stream-ordered device allocation (cudaMallocAsync pool with a high release threshold)
+int dev_alloc(void **p, size_t bytes, cudaStream_t s);
+void dev_free(void *p, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// geometry (host, libm): sb_geometry.cpp
+// ---------------------------------------------------------------------------------------------
+struct Projector {
+    int type;  // SB_WARP_SPHERICAL / CYLINDRICAL / PLANE (affine folded into plane)
+    float scale;
+    float k[9], rinv[9], r_kinv[9], k_rinv[9], t[3];
+};
+void projector_setup(Projector &p, int warp_type, float scale, const float *K, const float *R);
+void projector_roi(const Projector &p, int src_w, int src_h, int rect[4]);
+// Separable backward-map tables: for output column u (absolute, tl.x + i) and row v
+//   x_ = rowA[v] * colX[u];  y_ = rowY[v];  z_ = rowA[v] * colZ[u]
+// (multiplication by an exact 1.0f keeps cylindrical / plane bit-identical to the unfactored form)
+void projector_tables(const Projector &p, const int rect[4], float *colX, float *colZ, float *rowA, float *rowY);
+
+// ---------------------------------------------------------------------------------------------
+// device-side descriptors
+// ---------------------------------------------------------------------------------------------
+struct WarpJob {
+    const uint8_t *src;  // u8x3 interleaved
+    int sw, sh;
+    long long spitch;    // bytes
+    uint8_t *dst_rgb;    // u8x3 interleaved or null
+    long long dst_pitch;
+    uint8_t *dst_mask;   // u8 or null
+    long long mask_pitch;
+    uint32_t *dst_rgbm;  // packed r | g<<8 | b<<16 | mask<<24, or null
+    long long rgbm_pitch;  // elements
+    int dw, dh;
+    const float *colX, *colZ, *rowA, *rowY;
+    float k[9];
+    int always_divide;  // plane / affine: x/z, y/z unconditionally
+};
+
+// one pyramid level of one fed image: planar int16 x3 + float32 weights
+struct Level {
+    int16_t *g;        // [3][h][pitch]
+    float *w;          // [h][pitch]
+    int w_px, h_px;    // level size
+    int pitch;         // elements, both for g rows and w rows
+    long long plane;   // elements between colour planes of g
+};
+
+struct FeedImage {
+    // level 0 (one of the two layouts)
+    const uint32_t *rgbm;  // packed u8x3 + mask
+    long long rgbm_pitch;  // elements
+    const int16_t *s16;    // interleaved int16x3 (generic feed) or null
+    long long s16_pitch;   // elements (int16)
+    const uint8_t *mask;   // with s16 layout
+    long long mask_pitch;
+    int w, h;              // fed image size
+    int left, top;         // image origin inside its padded rect
+    int px, py;            // padded rect origin relative to the padded pano (level 0)
+    int pw, ph;            // padded rect size (multiples of 2^nb)
+    int dx, dy;            // feather / no: image origin relative to the pano roi
+    const float *fw;       // feather weight map [h][w] (dense)
+    Level lv[SB_MAX_BANDS + 1];  // lv[0] unused
+};
+
+struct PanoLevel {
+    int16_t *c;  // collapsed planar int16 x3 [3][h][pitch]
+    int w_px, h_px, pitch;
+    long long plane;
+};
+
+struct PanoOut {
+    uint8_t *rgb; long long rgb_pitch;     // final uint8 HxWx3 (nullable)
+    uint8_t *mask; long long mask_pitch;   // final uint8 mask (nullable)
+    int16_t *s16; long long s16_pitch;     // final int16 HxWx3 before convertScaleAbs (nullable); pitch in elements
+    int w, h;                              // unpadded roi size
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers
+// ---------------------------------------------------------------------------------------------
+int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaStream_t s);
+int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
+                     long long dst_pitch, int w, int h, cudaStream_t s);
+// level `l` -> `l+1` of images [first, first+count)
+int launch_pyrdown(const FeedImage *imgs_dev, int first, int count, int l, int max_w, int max_h, cudaStream_t s);
+// multiband: accumulate + normalise + collapse level l (top-down); at l == 0 writes the final outputs
+int launch_collapse(const FeedImage *imgs_dev, int n, const PanoLevel *pano_dev, int l, int nb, int lw, int lh,
+                    PanoOut out, cudaStream_t s);
+// feather: distance-transform weight maps, then one fused accumulate/normalise pass; NO blender
+int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
+int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
+int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
+
+}  // namespace sb

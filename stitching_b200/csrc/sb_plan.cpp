@@ -1,0 +1,282 @@
+// sb_plan.cpp -- geometry and storage plan of one blend (host logic; no kernels in this file).
+//
+// Restates the bookkeeping of stitching/blender.py:23-38 (Blender.prepare: resultRoi, blend width,
+// num_bands / sharpness) and of MultiBandBlender::prepare / ::feed's rect arithmetic (SURVEY.md A.4
+// steps 0-1): band clipping, padding the pano to a multiple of 2^nb, the per-feed padded rect.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sb_plan.h"
+
+namespace sb {
+
+namespace {
+inline int round_up(int v, int a) { return v + (a - v % a) % a; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int level_pitch(int w) { return (int)align_up((size_t)std::max(w, 1), 64); }  // elements: 128 B of int16
+}  // namespace
+
+Rect result_roi(const int *corners_xy, const int *sizes_wh, int n)
+{
+    int x0 = corners_xy[0], y0 = corners_xy[1], x1 = x0 + sizes_wh[0], y1 = y0 + sizes_wh[1];
+    for (int i = 1; i < n; ++i) {
+        x0 = std::min(x0, corners_xy[2 * i]);
+        y0 = std::min(y0, corners_xy[2 * i + 1]);
+        x1 = std::max(x1, corners_xy[2 * i] + sizes_wh[2 * i]);
+        y1 = std::max(y1, corners_xy[2 * i + 1] + sizes_wh[2 * i + 1]);
+    }
+    return Rect{x0, y0, x1 - x0, y1 - y0};
+}
+
+void derive_blend_params(int requested_kind, float blend_strength, const Rect &roi, int *kind, int *num_bands, float *sharpness)
+{
+    // blender.py:25  blend_width = sqrt(w*h) * strength / 100 (double)
+    const double blend_width = std::sqrt((double)roi.w * (double)roi.h) * (double)blend_strength / 100.0;
+    *num_bands = 0;
+    *sharpness = 0.f;
+    if (requested_kind == SB_BLEND_NO || blend_width < 1.0) {
+        *kind = SB_BLEND_NO;  // blender.py:27-28
+    } else if (requested_kind == SB_BLEND_MULTIBAND) {
+        *kind = SB_BLEND_MULTIBAND;
+        *num_bands = (int)(std::log(blend_width) / std::log(2.0) - 1.0);  // blender.py:32, truncation
+    } else {
+        *kind = SB_BLEND_FEATHER;
+        *sharpness = (float)(1.0 / blend_width);  // blender.py:36
+    }
+}
+
+int BlendPlan::set_geometry(int kind_, int num_bands_requested, float sharpness_, const Rect &roi_)
+{
+    if (roi_.w <= 0 || roi_.h <= 0) {
+        set_error("prepare: empty roi %dx%d", roi_.w, roi_.h);
+        return SB_ERR_INVALID;
+    }
+    kind = kind_;
+    sharpness = sharpness_;
+    roi = roi_;
+    imgs.clear();
+    nb = 0;
+    wp = roi.w;
+    hp = roi.h;
+    if (kind == SB_BLEND_MULTIBAND) {
+        if (num_bands_requested < 0) {
+            set_error("prepare: negative number of bands %d", num_bands_requested);
+            return SB_ERR_INVALID;
+        }
+        // MultiBandBlender::prepare: crop unnecessary bands, then pad the pano so every level halves exactly
+        const double max_len = (double)std::max(roi.w, roi.h);
+        const int limit = (int)std::ceil(std::log(max_len) / std::log(2.0));
+        nb = std::min(num_bands_requested, limit);
+        if (nb > SB_MAX_BANDS) {
+            set_error("prepare: %d bands exceed SB_MAX_BANDS=%d", nb, SB_MAX_BANDS);
+            return SB_ERR_INVALID;
+        }
+        wp = round_up(roi.w, 1 << nb);
+        hp = round_up(roi.h, 1 << nb);
+    }
+    return SB_OK;
+}
+
+int BlendPlan::add_feed(const FeedDesc &f)
+{
+    if (f.w <= 0 || f.h <= 0) {
+        set_error("feed: empty image %dx%d", f.w, f.h);
+        return SB_ERR_INVALID;
+    }
+    if ((int)imgs.size() >= SB_MAX_IMAGES) {
+        set_error("feed: more than %d images", SB_MAX_IMAGES);
+        return SB_ERR_INVALID;
+    }
+    FeedImage im;
+    std::memset(&im, 0, sizeof im);
+    im.rgbm = f.rgbm;
+    im.rgbm_pitch = f.rgbm_pitch;
+    im.s16 = f.s16;
+    im.s16_pitch = f.s16_pitch;
+    im.mask = f.mask;
+    im.mask_pitch = f.mask_pitch;
+    im.w = f.w;
+    im.h = f.h;
+    im.dx = f.tlx - roi.x;
+    im.dy = f.tly - roi.y;
+    if (kind != SB_BLEND_MULTIBAND) {
+        if (im.dx < 0 || im.dy < 0 || im.dx + f.w > roi.w || im.dy + f.h > roi.h) {
+            set_error("feed: image rect (%d,%d %dx%d) leaves the prepared roi (%d,%d %dx%d)", f.tlx, f.tly, f.w, f.h, roi.x, roi.y, roi.w, roi.h);
+            return SB_ERR_INVALID;
+        }
+        imgs.push_back(im);
+        return SB_OK;
+    }
+    // MultiBandBlender::feed: keep the image with a gap of 3*2^nb around it, clipped to the padded pano;
+    // snap the origin down and the extent up to the 2^nb lattice anchored at the pano origin.
+    const int a = 1 << nb, gap = 3 * a;
+    const int rx1 = roi.x + wp, ry1 = roi.y + hp;
+    int x0 = std::max(roi.x, f.tlx - gap), y0 = std::max(roi.y, f.tly - gap);
+    int x1 = std::min(rx1, f.tlx + f.w + gap), y1 = std::min(ry1, f.tly + f.h + gap);
+    x0 = roi.x + (((x0 - roi.x) >> nb) << nb);
+    y0 = roi.y + (((y0 - roi.y) >> nb) << nb);
+    int ww = x1 - x0, hh = y1 - y0;
+    if (ww <= 0 || hh <= 0) {
+        set_error("feed: image rect (%d,%d %dx%d) does not intersect the prepared roi", f.tlx, f.tly, f.w, f.h);
+        return SB_ERR_INVALID;
+    }
+    ww = round_up(ww, a);
+    hh = round_up(hh, a);
+    // shift back inside the padded pano if the rounded rect sticks out (never triggers: the lattice is
+    // anchored at the pano origin and the padded pano size is a lattice multiple; kept for fidelity)
+    const int sx = std::max(x0 + ww - rx1, 0), sy = std::max(y0 + hh - ry1, 0);
+    x0 -= sx;
+    y0 -= sy;
+    im.left = f.tlx - x0;
+    im.top = f.tly - y0;
+    const int right = x0 + ww - f.tlx - f.w, bottom = y0 + hh - f.tly - f.h;
+    if (im.left < 0 || im.top < 0 || right < 0 || bottom < 0) {
+        set_error("feed: image rect (%d,%d %dx%d) leaves the prepared roi (%d,%d %dx%d)", f.tlx, f.tly, f.w, f.h, roi.x, roi.y, roi.w, roi.h);
+        return SB_ERR_INVALID;
+    }
+    im.px = x0 - roi.x;
+    im.py = y0 - roi.y;
+    im.pw = ww;
+    im.ph = hh;
+    imgs.push_back(im);
+    return SB_OK;
+}
+
+int BlendPlan::allocate(cudaStream_t s)
+{
+    release(s);
+    const int n = (int)imgs.size();
+    // carve every buffer out of one arena
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    struct Slot { size_t g, w; };
+    std::vector<std::vector<Slot>> slots(n);
+    std::vector<size_t> fw_off(n, 0);
+    size_t pano_off[SB_MAX_BANDS + 1] = {0};
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (int i = 0; i < n; ++i) {
+            slots[i].resize(nb + 1);
+            for (int l = 1; l <= nb; ++l) {
+                const int w = imgs[i].pw >> l, h = imgs[i].ph >> l, pitch = level_pitch(w);
+                slots[i][l].g = carve((size_t)3 * h * pitch * sizeof(int16_t));
+                slots[i][l].w = carve((size_t)h * pitch * sizeof(float));
+            }
+        }
+        for (int l = 1; l <= nb; ++l) {
+            const int w = wp >> l, h = hp >> l, pitch = level_pitch(w);
+            pano_off[l] = carve((size_t)3 * h * pitch * sizeof(int16_t));
+        }
+    } else if (kind == SB_BLEND_FEATHER) {
+        for (int i = 0; i < n; ++i) fw_off[i] = carve((size_t)imgs[i].w * imgs[i].h * sizeof(float));
+    }
+    const size_t imgs_off = carve(sizeof(FeedImage) * (size_t)std::max(n, 1));
+    const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
+    arena_bytes_ = off;
+    SB_TRY(dev_alloc(&arena_, arena_bytes_, s));
+    char *base = (char *)arena_;
+    std::memset(pano, 0, sizeof pano);
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (int i = 0; i < n; ++i)
+            for (int l = 1; l <= nb; ++l) {
+                Level &L = imgs[i].lv[l];
+                L.w_px = imgs[i].pw >> l;
+                L.h_px = imgs[i].ph >> l;
+                L.pitch = level_pitch(L.w_px);
+                L.plane = (long long)L.h_px * L.pitch;
+                L.g = (int16_t *)(base + slots[i][l].g);
+                L.w = (float *)(base + slots[i][l].w);
+            }
+        for (int l = 1; l <= nb; ++l) {
+            PanoLevel &P = pano[l];
+            P.w_px = wp >> l;
+            P.h_px = hp >> l;
+            P.pitch = level_pitch(P.w_px);
+            P.plane = (long long)P.h_px * P.pitch;
+            P.c = (int16_t *)(base + pano_off[l]);
+        }
+    } else if (kind == SB_BLEND_FEATHER) {
+        for (int i = 0; i < n; ++i) imgs[i].fw = (const float *)(base + fw_off[i]);
+    }
+    imgs_dev = (FeedImage *)(base + imgs_off);
+    pano_dev = (PanoLevel *)(base + panod_off);
+    if (n) SB_CUDA(cudaMemcpyAsync(imgs_dev, imgs.data(), sizeof(FeedImage) * n, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(pano_dev, pano, sizeof pano, cudaMemcpyHostToDevice, s));
+    // the descriptor copies read pageable host memory owned by this object: make them complete now
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+void BlendPlan::release(cudaStream_t s)
+{
+    if (arena_) dev_free(arena_, s);
+    arena_ = nullptr;
+    arena_bytes_ = 0;
+    imgs_dev = nullptr;
+    pano_dev = nullptr;
+}
+
+int BlendPlan::run(const PanoOut &out, cudaStream_t s, cudaEvent_t *ev)
+{
+    const int n = (int)imgs.size();
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (int l = 0; l < nb; ++l) {
+            int mw = 0, mh = 0;
+            for (const FeedImage &im : imgs) {
+                mw = std::max(mw, im.pw >> (l + 1));
+                mh = std::max(mh, im.ph >> (l + 1));
+            }
+            SB_TRY(launch_pyrdown(imgs_dev, 0, n, l, mw, mh, s));
+        }
+        if (ev) SB_CUDA(cudaEventRecord(ev[0], s));
+        for (int l = nb; l >= 0; --l) SB_TRY(launch_collapse(imgs_dev, n, pano_dev, l, nb, wp >> l, hp >> l, out, s));
+        if (ev) SB_CUDA(cudaEventRecord(ev[1], s));
+    } else {
+        if (kind == SB_BLEND_FEATHER) SB_TRY(launch_feather_weights(imgs_dev, imgs.data(), n, sharpness, s));
+        if (ev) SB_CUDA(cudaEventRecord(ev[0], s));
+        SB_TRY(launch_simple_blend(imgs_dev, n, kind == SB_BLEND_FEATHER, out, s));
+        if (ev) SB_CUDA(cudaEventRecord(ev[1], s));
+    }
+    return SB_OK;
+}
+
+// Compulsory HBM traffic of this plan's kernels (every input byte read once, every output byte written
+// once, no accumulator round trips): see DESIGN.md "byte model".
+double BlendPlan::model_bytes(double *pyr, double *collapse) const
+{
+    double bp = 0, bc = 0;
+    const double l0 = imgs.empty() ? 4.0 : (imgs[0].rgbm ? 4.0 : 7.0);  // bytes per level-0 pixel
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (const FeedImage &im : imgs) {
+            const double A = (double)im.pw * im.ph;
+            for (int l = 0; l < nb; ++l) {
+                const double src = A / std::pow(4.0, l), dst = src / 4;
+                bp += (l == 0 ? l0 : 10.0) * src + 10.0 * dst;  // read level l, write level l+1
+            }
+            for (int l = 0; l <= nb; ++l) {
+                const double a = A / std::pow(4.0, l);
+                bc += (l == 0 ? l0 : 10.0) * a;       // G_l, W_l
+                if (l < nb) bc += 6.0 * a / 4;        // G_{l+1} for the pyrUp
+            }
+        }
+        const double P = (double)wp * hp;
+        for (int l = 1; l <= nb; ++l) bc += 2 * 6.0 * P / std::pow(4.0, l);  // C_l written once, read once
+        bc += 4.0 * (double)roi.w * roi.h;  // final uint8x3 + mask
+    } else {
+        for (const FeedImage &im : imgs) {
+            const double m = (double)im.w * im.h;
+            if (kind == SB_BLEND_FEATHER) bp += m * (1 + 4 + 4 + 4 + 4), bc += 4 * m;  // DT passes, weight read
+            bc += l0 * m;
+        }
+        bc += 4.0 * (double)roi.w * roi.h;
+    }
+    if (pyr) *pyr = bp;
+    if (collapse) *collapse = bc;
+    return bp + bc;
+}
+
+}  // namespace sb

@@ -1,0 +1,111 @@
+// sb_warp.cu -- fused backward-map warp: image (fixed-point bilinear, BORDER_REFLECT) and validity mask
+// (nearest, BORDER_CONSTANT) in one pass, no float maps in memory.
+//
+// Replaces, per output pixel, what cv.PyRotationWarper.warp does in three passes
+// (stitching/warper.py:43-52 image, :58-68 mask): buildMaps -> remap(INTER_LINEAR, BORDER_REFLECT) and
+// buildMaps -> remap(INTER_NEAREST, BORDER_CONSTANT).
+//
+// Arithmetic contract (bit-exact with the reference's CPU path):
+//   projection  x_ = rowA[v]*colX[u], y_ = rowY[v], z_ = rowA[v]*colZ[u]      (host libm tables)
+//               (x,y,z) = k_rinv * (x_,y_,z_)  plain fp32, (a+b)+c, every op rounded, no FMA
+//               spherical/cylindrical: z > 0 ? (x/z, y/z) : (-1,-1);  plane: always divide
+//   bilinear    sx = cvRound(x*32) (half-even, INT_MIN when unrepresentable), ix = sat16(sx>>5),
+//               fx = sx&31; 4 taps with 15-bit weights (32-fy)(32-fx)*32 ..., (sum + 2^14) >> 15
+//   mask        255 iff 0 <= sat16(cvRound(x)) < W and 0 <= sat16(cvRound(y)) < H
+#include "sb_device.cuh"
+#include "sb_launch.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int WARP_BX = 32, WARP_BY = 8;
+
+__device__ __forceinline__ void project(const WarpJob &j, int u, int v, float &x, float &y)
+{
+    const float cx = __ldg(j.colX + u), cz = __ldg(j.colZ + u);
+    const float ra = __ldg(j.rowA + v), ry = __ldg(j.rowY + v);
+    const float x_ = fmul(ra, cx), y_ = ry, z_ = fmul(ra, cz);
+    x = fadd(fadd(fmul(j.k[0], x_), fmul(j.k[1], y_)), fmul(j.k[2], z_));
+    y = fadd(fadd(fmul(j.k[3], x_), fmul(j.k[4], y_)), fmul(j.k[5], z_));
+    const float z = fadd(fadd(fmul(j.k[6], x_), fmul(j.k[7], y_)), fmul(j.k[8], z_));
+    if (j.always_divide || z > 0.f) {
+        x = fdiv(x, z);
+        y = fdiv(y, z);
+    } else {
+        x = -1.f;
+        y = -1.f;
+    }
+}
+
+// simple variant: one thread per output pixel, direct (L1/L2-cached) global gathers
+__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const WarpJob *__restrict__ jobs)
+{
+    const WarpJob &j = jobs[blockIdx.z];
+    const int u = blockIdx.x * WARP_BX + threadIdx.x;
+    const int v = blockIdx.y * WARP_BY + threadIdx.y;
+    if (u >= j.dw || v >= j.dh) return;
+
+    float x, y;
+    project(j, u, v, x, y);
+
+    // validity mask: nearest neighbour into an all-255 source, constant-0 border
+    const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
+    const unsigned m = ((unsigned)nx < (unsigned)j.sw && (unsigned)ny < (unsigned)j.sh) ? 255u : 0u;
+    if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
+    if (!j.dst_rgb && !j.dst_rgbm) return;
+
+    const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
+    const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
+    const int fx = sx & 31, fy = sy & 31;
+    const int x0 = reflect(ix, j.sw), x1 = reflect(ix + 1, j.sw);
+    const int y0 = reflect(iy, j.sh), y1 = reflect(iy + 1, j.sh);
+    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32;
+    const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    const uint8_t *r0 = j.src + (long long)y0 * j.spitch, *r1 = j.src + (long long)y1 * j.spitch;
+    unsigned out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int acc = __ldg(r0 + x0 * 3 + c) * w00 + __ldg(r0 + x1 * 3 + c) * w01 + __ldg(r1 + x0 * 3 + c) * w10 +
+                  __ldg(r1 + x1 * 3 + c) * w11;
+        out[c] = (unsigned)sat_u8((acc + (1 << 14)) >> 15);
+    }
+    if (j.dst_rgb) {
+        uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + (long long)u * 3;
+        d[0] = (uint8_t)out[0];
+        d[1] = (uint8_t)out[1];
+        d[2] = (uint8_t)out[2];
+    }
+    if (j.dst_rgbm) j.dst_rgbm[(long long)v * j.rgbm_pitch + u] = out[0] | (out[1] << 8) | (out[2] << 16) | (m << 24);
+}
+
+__global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch, const uint8_t *__restrict__ mask,
+                            long long mask_pitch, uint32_t *__restrict__ dst, long long dst_pitch, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *p = rgb + (long long)y * rgb_pitch + (long long)x * 3;
+    const unsigned m = mask[(long long)y * mask_pitch + x];
+    dst[(long long)y * dst_pitch + x] = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | (m << 24);
+}
+
+}  // namespace
+
+int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_w <= 0 || max_h <= 0) return SB_OK;
+    dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), n_jobs);
+    launch(k_warp_gather, grid, block, 0, s, jobs_dev);
+    return launch_check("k_warp_gather");
+}
+
+int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
+                     long long dst_pitch, int w, int h, cudaStream_t s)
+{
+    dim3 block(32, 8), grid(div_up(w, 32), div_up(h, 8));
+    launch(k_pack_rgbm, grid, block, 0, s, rgb, rgb_pitch, mask, mask_pitch, dst, dst_pitch, w, h);
+    return launch_check("k_pack_rgbm");
+}
+
+}  // namespace sb

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY -- storage for the emulated builtin index variables.
+#include "cuda_runtime.h"
+thread_local emuIdx threadIdx, blockIdx, blockDim, gridDim;
