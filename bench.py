@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- warp + multiband-blend throughput of the B200 compositing path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = one pass of the hot path over one batch of synthetic frames for a fixed rig: fused warp of
+every image (+ validity mask), Gaussian/weight pyramids, per-band weighted accumulate + normalise + collapse,
+final uint8 panorama + mask.  At N = 1 the workload is BASELINE.json configs[1] (8 x 4000x3000 RGB, spherical
+warp, multiband blend).  With N > 1 (torchrun, one rank per GPU) every rank composites its own 8-image ring
+(weak scaling, no data-path collective in this round).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM, CUDA events on
+the launching stream); `e2e` goes through the public API with pinned HOST buffers, host<->device copies inside
+the timed region; `roofline` is the dominant kernel against the measured HBM copy bandwidth; `cpu_baseline`
+is the reference's own cv2 path (oracle/cv_path.py) timed on this box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "warp+multiband-blend input MPix/s"
+UNIT = "MPix/s"
+
+WORKLOADS = {
+    "cfg2": "8x4000x3000 RGB, spherical warp + multiband blend (BASELINE configs[1])",
+    "cfg4": "8x8000x6000 RGB, spherical warp + multiband blend (BASELINE configs[3])",
+    "cfg3": "32x4000x3000 RGB, cylindrical warp + multiband blend (BASELINE configs[2], all on one GPU)",
+    "cfg5": "16x2000x1500 RGB, affine warp + feather blend (BASELINE configs[4])",
+}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class Dist:
+    """torch.distributed (gloo) for the barrier and the max-over-ranks; only plumbing."""
+
+    def __init__(self, world):
+        self.world = world
+        self.pg = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group(backend="gloo")
+            self.pg = dist
+
+    def barrier(self):
+        if self.pg:
+            self.pg.barrier()
+
+    def max(self, v):
+        if not self.pg:
+            return v
+        import torch
+
+        t = torch.tensor([float(v)], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v):
+        if not self.pg:
+            return v
+        import torch
+
+        t = torch.tensor([float(v)], dtype=torch.float64)
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.pg:
+            self.pg.destroy_process_group()
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU sampled with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if self.ok:
+            self.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no sample landed inside the timed region")}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if one exists for this round."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+SCALE_DOWN = 1  # --scale-down (debug dry runs only; recorded in config, never a reportable number)
+
+
+def make_workload(name, rank):
+    from stitching_b200 import rigs
+
+    cfg = rigs.config(name, SCALE_DOWN)
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 100 * rank + i) for i in range(cfg["n"])]
+    return cfg, imgs
+
+
+def cpu_reference_run(cfg, imgs, n_sample, threads=None):
+    """The reference's CPU path on the first n_sample images of the ring.  Returns (MPix/s, seconds, info)."""
+    from oracle import cv_path
+
+    cams = cfg["cameras"][:n_sample]
+    sub = imgs[:n_sample]
+    mpix = sum(im.shape[0] * im.shape[1] for im in sub) / 1e6
+    if cv_path.available():
+        t0 = time.perf_counter()
+        _, _, stages = cv_path.composite(cfg, cams, sub, threads)
+        dt = time.perf_counter() - t0
+        info = cv_path.describe()
+        return mpix / dt, dt, {"backend": f"cv2 {info['cv2']}", "cores": info["threads"], "stages_s": {k: round(v, 3) for k, v in stages.items()}}
+    # cv2 missing on this box: the scalar C restatement (1 core)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import replay
+    from oracle import oracle as O
+
+    t0 = time.perf_counter()
+    replay.oracle_composite(O, cfg, cams, sub)
+    dt = time.perf_counter() - t0
+    return mpix / dt, dt, {"backend": "oracle/stitch_oracle.c (scalar)", "cores": 1, "stages_s": {}}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, imgs = make_workload(args.workload, 0)
+    n_sample = min(args.cpu_sample or 4, cfg["n"])
+    # bound the whole run to a few minutes: shrink the sample if one step is slow
+    v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+    budget = 150.0
+    while n_sample > 2 and dt * (args.steps + args.warmup) > budget:
+        n_sample = max(2, n_sample // 2)
+        v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_reference_run(cfg, imgs, n_sample)
+    times = []
+    for _ in range(args.steps):
+        _, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+        times.append(dt)
+    mpix = n_sample * cfg["w"] * cfg["h"] / 1e6
+    value = mpix * len(times) / sum(times)
+    sample = f"first {n_sample} of {cfg['n']} images of the ring at full resolution per step ({info['backend']})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample,
+                         "stages_s": info["stages_s"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    from stitching_b200 import Compositor, _lib
+
+    dist = Dist(world)
+    L = _lib.lib()
+    _lib.check(L.sb_init(local_rank), "sb_init")
+    cfg, imgs = make_workload(args.workload, rank)
+    n, w, h = cfg["n"], cfg["w"], cfg["h"]
+    sizes = [(w, h)] * n
+    t0 = time.perf_counter()
+    comp = Compositor(cfg["cameras"], sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    mpix_rank = n * w * h / 1e6
+
+    # ---- device-resident throughput (`value`) -----------------------------------------------------
+    comp.upload(imgs)
+    for _ in range(args.warmup):
+        comp.run()
+    comp.sync()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.sb_launch_count()
+    total_ms, launches = comp.time(args.steps, flush_l2=args.flush_l2)
+    launches1 = L.sb_launch_count()
+    comp.sync()
+    clocks = sampler.result()
+    dist.barrier()
+    worst_ms = dist.max(total_ms)
+    total_mpix = dist.sum(mpix_rank)
+    ms_per_step = worst_ms / args.steps
+    value = total_mpix / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    total_bytes, per_launch_bytes = comp.model_bytes()
+    k_dom = int(np.argmax([ms for _, ms in launches]))
+    dom_name, dom_ms = launches[k_dom]
+    peak, peak_src = measured_peak_gbs()
+    achieved = per_launch_bytes[k_dom] / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": ncu_traffic(dom_name), "peak_source": peak_src, "algorithmic_bytes": per_launch_bytes[k_dom],
+        "kernel_ms": dom_ms,
+        "whole_step": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                       "frac": total_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak},
+        "launches_ms": {name: round(ms, 4) for name, ms in launches},
+    }
+
+    # ---- end to end through the public API with pinned host buffers (`e2e`) --------------------------
+    src_bytes = h * w * 3
+    _, _, pw, ph = comp.roi
+    host_src = []
+    for im in imgs:
+        p = L.sb_host_alloc(src_bytes)
+        if not p:
+            _lib.check(-5, "sb_host_alloc")
+        buf = np.ctypeslib.as_array((C.c_uint8 * src_bytes).from_address(p)).reshape(h, w, 3)
+        buf[...] = im
+        host_src.append((p, buf))
+    p_pano, p_mask = L.sb_host_alloc(ph * pw * 3), L.sb_host_alloc(ph * pw)
+    pano = np.ctypeslib.as_array((C.c_uint8 * (ph * pw * 3)).from_address(p_pano)).reshape(ph, pw, 3)
+    pmask = np.ctypeslib.as_array((C.c_uint8 * (ph * pw)).from_address(p_mask)).reshape(ph, pw)
+
+    def e2e_step():
+        comp.upload([b for _, b in host_src], pinned=True)
+        comp.run()
+        comp.download(pano, pmask)  # synchronises
+
+    for _ in range(3):
+        e2e_step()
+    dist.barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = dist.max(time.perf_counter() - t0)
+    e2e = {"value": total_mpix * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * src_bytes,
+           "d2h_bytes_per_step": ph * pw * 4, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+           "api": "stitching_b200.Compositor.upload/run/download (sb_compositor_* C ABI), pinned host buffers"}
+    checksum = int(pano[::97, ::89].astype(np.uint64).sum())  # the result was really produced and read back
+
+    # ---- CPU baseline: the reference's cv2 path on this box's host cores (rank 0, N = 1 only) ------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sample = min(args.cpu_sample or 4, n)
+        v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
+               "sample": f"first {n_sample} of {n} images of the ring at full resolution, 1 cold run of {dt:.1f} s ({info['backend']})",
+               "stages_s": info["stages_s"], "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {WORKLOADS[args.workload]}" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""),
+                "images_per_gpu": n, "pano": [pw, ph],
+                "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
+                "l2": "L2 flushed between steps" if args.flush_l2 else
+                      f"no flush: a step streams {total_bytes / 1e6:.0f} MB, inputs {n * src_bytes / 1e6:.0f} MB > 126 MB L2",
+                "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent {n}-image ring per GPU (no collective)",
+                "timed": "plan (roi detection, trig tables, buffers) built once outside the timed region; a step = warp + pyramids + collapse kernels",
+            },
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "roofline": roofline,
+            "cpu_baseline": cpu, "result_checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    for p, _ in host_src:
+        L.sb_host_free(p)
+    L.sb_host_free(p_pano)
+    L.sb_host_free(p_mask)
+    comp.close()
+    dist.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--flush-l2", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring used for the CPU baseline (default 4)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale-down", type=int, default=1, help="debug: shrink the workload (not a valid measurement)")
+    args = ap.parse_args()
+    global SCALE_DOWN
+    SCALE_DOWN = args.scale_down
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,8 +118,9 @@ SB_API sb_compositor *sb_compositor_create(const sb_rig *rig);
 SB_API void sb_compositor_destroy(sb_compositor *c);
 /* geometry of the plan: per image warped rect {x,y,w,h} (== sb_warp_roi) and the pano roi {x,y,w,h} */
 SB_API int sb_compositor_geometry(const sb_compositor *c, int *rects /*[n][4]*/, int pano_roi[4], int *num_bands);
-/* bytes moved by one run according to the compulsory-traffic model, for the roofline */
-SB_API int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_stage /*[8]*/);
+/* compulsory HBM traffic of one run (DESIGN.md byte model) for the roofline: total, and per kernel launch in
+ * launch order (same order as sb_compositor_stage_times).  Returns the number of launches (or < 0). */
+SB_API int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_launch, int cap);
 /* host -> device copy of source image i (uint8 HxWx3); asynchronous on the compositor stream when
  * `pinned` != 0 (caller guarantees page-locked memory and keeps it alive until sync) */
 SB_API int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pitch, int pinned);
@@ -136,8 +137,8 @@ SB_API int sb_compositor_sync(sb_compositor *c);
 /* time `iters` back-to-back runs with CUDA events on the compositor stream; flush_l2 != 0 writes a
  * buffer larger than L2 between runs (outside the timed intervals).  ms_total = sum of the intervals. */
 SB_API int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_total);
-/* per-kernel-family device time of the last sb_compositor_time call, averaged per run:
- * names[] receives up to `cap` static strings, ms[] the matching times.  Returns count. */
+/* device time of every kernel launch of the last sb_compositor_time call, averaged per run, in launch order:
+ * names[] receives up to `cap` strings owned by the compositor, ms[] the matching times.  Returns count. */
 SB_API int sb_compositor_stage_times(sb_compositor *c, const char **names, float *ms, int cap);
 
 /* page-locked host memory for the e2e path */

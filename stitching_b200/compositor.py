@@ -94,20 +94,27 @@ class Compositor:
         return self.download()
 
     # -- measurement -------------------------------------------------------------------------------
-    def time(self, iters, flush_l2=True):
-        """Device time (ms, CUDA events on the compositor stream) of `iters` runs; returns (total_ms, {stage: ms/run})."""
+    def time(self, iters, flush_l2=False):
+        """Device time of `iters` runs, CUDA events on the compositor stream.
+
+        Returns (total_ms, [(launch name, ms per run)]) with one entry per kernel launch, in launch order."""
         ms = C.c_float()
         _lib.check(_lib.lib().sb_compositor_time(self._c, int(iters), int(flush_l2), C.byref(ms)), "sb_compositor_time")
-        names = (C.c_char_p * 8)()
-        vals = (C.c_float * 8)()
-        k = _lib.lib().sb_compositor_stage_times(self._c, names, vals, 8)
-        return ms.value, {names[i].decode(): vals[i] for i in range(k)}
+        cap = 64
+        names = (C.c_char_p * cap)()
+        vals = (C.c_float * cap)()
+        k = _lib.lib().sb_compositor_stage_times(self._c, names, vals, cap)
+        return ms.value, [(names[i].decode(), vals[i]) for i in range(k)]
 
     def model_bytes(self):
+        """Compulsory HBM traffic of one run: (total bytes, [bytes per launch, in launch order])."""
+        cap = 64
         tot = C.c_double()
-        st = (C.c_double * 8)()
-        _lib.check(_lib.lib().sb_compositor_model_bytes(self._c, C.byref(tot), st), "sb_compositor_model_bytes")
-        return tot.value, {"warp": st[0], "pyramid": st[1], "collapse": st[2]}
+        per = (C.c_double * cap)()
+        k = _lib.lib().sb_compositor_model_bytes(self._c, C.byref(tot), per, cap)
+        if k < 0:
+            _lib.check(k, "sb_compositor_model_bytes")
+        return tot.value, [per[i] for i in range(k)]
 
     def close(self):
         if getattr(self, "_c", None):

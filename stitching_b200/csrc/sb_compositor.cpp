@@ -6,6 +6,8 @@
 // storage); run() enqueues warp -> pyramids -> collapse for a batch of frames without touching the host.
 #include <algorithm>
 #include <cstring>
+#include <functional>
+#include <string>
 #include <vector>
 
 #include "sb_plan.h"
@@ -34,8 +36,9 @@ struct sb_compositor {
     PanoOut out;                       // device outputs
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, warp, pyr, collapse
-    float stage_ms[3] = {0, 0, 0};
+    std::vector<cudaEvent_t> ev;       // ev[0] = start, ev[k+1] = after launch k
+    std::vector<std::string> launch_names;
+    std::vector<float> launch_ms;      // per launch, averaged over the last sb_compositor_time call
     double warp_bytes = 0;
 };
 
@@ -74,7 +77,6 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
     SB_TRY(ensure_device());
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaStream_t s = c->stream;
-    for (auto &e : c->ev) SB_CUDA(cudaEventCreate(&e));
 
     c->src_w.assign(rig->src_w, rig->src_w + n);
     c->src_h.assign(rig->src_h, rig->src_h + n);
@@ -148,10 +150,25 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
 static int compositor_enqueue(sb_compositor *c, bool events)
 {
     cudaStream_t s = c->stream;
-    if (events) SB_CUDA(cudaEventRecord(c->ev[0], s));
+    size_t k = 0;
+    auto mark = [&](const std::string &name) -> int {
+        if (!events) return SB_OK;
+        if (c->ev.size() <= k) {
+            cudaEvent_t e;
+            SB_CUDA(cudaEventCreate(&e));
+            c->ev.push_back(e);
+        }
+        SB_CUDA(cudaEventRecord(c->ev[k], s));
+        if (k > 0) {
+            if (c->launch_names.size() < k) c->launch_names.push_back(name);
+        }
+        ++k;
+        return SB_OK;
+    };
+    SB_TRY(mark("start"));
     SB_TRY(launch_warp(c->jobs_dev, c->n, c->max_w, c->max_h, s));
-    if (events) SB_CUDA(cudaEventRecord(c->ev[1], s));
-    SB_TRY(c->plan.run(c->out, s, events ? &c->ev[2] : nullptr));
+    SB_TRY(mark("warp"));
+    SB_TRY(c->plan.run(c->out, s, events ? std::function<int(const std::string &)>(mark) : nullptr));
     return SB_OK;
 }
 
@@ -198,22 +215,21 @@ int sb_compositor_geometry(const sb_compositor *c, int *rects, int pano_roi[4], 
     return SB_OK;
 }
 
-int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_stage)
+int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes, double *per_launch, int cap)
 {
     if (!c) {
         set_error("sb_compositor_model_bytes: null handle");
         return SB_ERR_INVALID;
     }
-    double pyr = 0, col = 0;
-    c->plan.model_bytes(&pyr, &col);
-    if (total_bytes) *total_bytes = c->warp_bytes + pyr + col;
-    if (per_stage) {
-        per_stage[0] = c->warp_bytes;
-        per_stage[1] = pyr;
-        per_stage[2] = col;
-        for (int i = 3; i < 8; ++i) per_stage[i] = 0;
-    }
-    return SB_OK;
+    std::vector<double> v;
+    v.push_back(c->warp_bytes);
+    for (const auto &kv : c->plan.launch_bytes()) v.push_back(kv.second);
+    double tot = 0;
+    for (double b : v) tot += b;
+    if (total_bytes) *total_bytes = tot;
+    if (per_launch)
+        for (int i = 0; i < cap && i < (int)v.size(); ++i) per_launch[i] = v[i];
+    return (int)v.size();
 }
 
 int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pitch, int pinned)
@@ -308,23 +324,23 @@ int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_tota
         SB_TRY(dev_alloc(&c->flush_buf, c->flush_bytes, s));
     }
     float total = 0.f;
-    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.f;
+    c->launch_ms.clear();
     for (int it = 0; it < iters; ++it) {
         if (flush_l2) SB_TRY(launch_flush_l2(c->flush_buf, c->flush_bytes, s));
         SB_TRY(compositor_enqueue(c, true));
-        SB_CUDA(cudaEventSynchronize(c->ev[3]));
-        float a = 0, b = 0, d = 0;
-        SB_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
-        SB_CUDA(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
-        SB_CUDA(cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
-        c->stage_ms[0] += a;
-        c->stage_ms[1] += b;
-        c->stage_ms[2] += d;
+        const size_t nl = c->launch_names.size();
+        SB_CUDA(cudaEventSynchronize(c->ev[nl]));
+        if (c->launch_ms.size() != nl) c->launch_ms.assign(nl, 0.f);
+        for (size_t k = 0; k < nl; ++k) {
+            float t = 0;
+            SB_CUDA(cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]));
+            c->launch_ms[k] += t;
+        }
         float t = 0;
-        SB_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[3]));
+        SB_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[nl]));
         total += t;
     }
-    for (float &v : c->stage_ms) v /= (float)iters;
+    for (float &v : c->launch_ms) v /= (float)iters;
     *ms_total = total;
     return SB_OK;
 }
@@ -332,11 +348,10 @@ int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_tota
 int sb_compositor_stage_times(sb_compositor *c, const char **names, float *ms, int cap)
 {
     if (!c) return 0;
-    static const char *kNames[3] = {"warp", "pyramid", "collapse"};
-    int k = std::min(cap, 3);
+    int k = (int)std::min<size_t>((size_t)cap, c->launch_ms.size());
     for (int i = 0; i < k; ++i) {
-        if (names) names[i] = kNames[i];
-        if (ms) ms[i] = c->stage_ms[i];
+        if (names) names[i] = c->launch_names[i].c_str();
+        if (ms) ms[i] = c->launch_ms[i];
     }
     return k;
 }

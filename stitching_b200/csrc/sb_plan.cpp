@@ -220,9 +220,10 @@ void BlendPlan::release(cudaStream_t s)
     pano_dev = nullptr;
 }
 
-int BlendPlan::run(const PanoOut &out, cudaStream_t s, cudaEvent_t *ev)
+int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(const std::string &)> &mark)
 {
     const int n = (int)imgs.size();
+    auto note = [&](const std::string &name) -> int { return mark ? mark(name) : SB_OK; };
     if (kind == SB_BLEND_MULTIBAND) {
         for (int l = 0; l < nb; ++l) {
             int mw = 0, mh = 0;
@@ -231,48 +232,70 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, cudaEvent_t *ev)
                 mh = std::max(mh, im.ph >> (l + 1));
             }
             SB_TRY(launch_pyrdown(imgs_dev, 0, n, l, mw, mh, s));
+            SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
-        if (ev) SB_CUDA(cudaEventRecord(ev[0], s));
-        for (int l = nb; l >= 0; --l) SB_TRY(launch_collapse(imgs_dev, n, pano_dev, l, nb, wp >> l, hp >> l, out, s));
-        if (ev) SB_CUDA(cudaEventRecord(ev[1], s));
+        for (int l = nb; l >= 0; --l) {
+            SB_TRY(launch_collapse(imgs_dev, n, pano_dev, l, nb, wp >> l, hp >> l, out, s));
+            SB_TRY(note("collapse_l" + std::to_string(l)));
+        }
     } else {
-        if (kind == SB_BLEND_FEATHER) SB_TRY(launch_feather_weights(imgs_dev, imgs.data(), n, sharpness, s));
-        if (ev) SB_CUDA(cudaEventRecord(ev[0], s));
+        if (kind == SB_BLEND_FEATHER) {
+            SB_TRY(launch_feather_weights(imgs_dev, imgs.data(), n, sharpness, s));
+            SB_TRY(note("feather_weights"));
+        }
         SB_TRY(launch_simple_blend(imgs_dev, n, kind == SB_BLEND_FEATHER, out, s));
-        if (ev) SB_CUDA(cudaEventRecord(ev[1], s));
+        SB_TRY(note(kind == SB_BLEND_FEATHER ? "feather_blend" : "no_blend"));
     }
     return SB_OK;
 }
 
 // Compulsory HBM traffic of this plan's kernels (every input byte read once, every output byte written
-// once, no accumulator round trips): see DESIGN.md "byte model".
+// once, no accumulator round trips): see DESIGN.md "byte model".  Same order as run()'s launches.
+std::vector<std::pair<std::string, double>> BlendPlan::launch_bytes() const
+{
+    std::vector<std::pair<std::string, double>> v;
+    const double l0 = imgs.empty() ? 4.0 : (imgs[0].rgbm ? 4.0 : 7.0);  // bytes per level-0 pixel
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (int l = 0; l < nb; ++l) {
+            double b = 0;
+            for (const FeedImage &im : imgs) {
+                const double src = (double)(im.pw >> l) * (im.ph >> l);
+                b += (l == 0 ? l0 : 10.0) * src + 10.0 * src / 4;  // read level l, write level l+1
+            }
+            v.emplace_back("pyrdown_l" + std::to_string(l), b);
+        }
+        for (int l = nb; l >= 0; --l) {
+            double b = 0;
+            for (const FeedImage &im : imgs) {
+                const double a = (double)(im.pw >> l) * (im.ph >> l);
+                b += (l == 0 ? l0 : 10.0) * a;   // G_l, W_l
+                if (l < nb) b += 6.0 * a / 4;    // G_{l+1} for the pyrUp
+            }
+            const double P = (double)(wp >> l) * (hp >> l);
+            if (l < nb) b += 6.0 * P / 4;        // C_{l+1}
+            b += l > 0 ? 6.0 * P : 4.0 * (double)roi.w * roi.h;  // C_l, or the final uint8x3 + mask
+            v.emplace_back("collapse_l" + std::to_string(l), b);
+        }
+    } else {
+        double bw = 0, bb = 0;
+        for (const FeedImage &im : imgs) {
+            const double m = (double)im.w * im.h;
+            if (kind == SB_BLEND_FEATHER) bw += m * (1 + 4 + 4 + 4 + 4), bb += 4 * m;  // DT passes; weight read
+            bb += l0 * m;
+        }
+        bb += 4.0 * (double)roi.w * roi.h;
+        if (kind == SB_BLEND_FEATHER) v.emplace_back("feather_weights", bw);
+        v.emplace_back(kind == SB_BLEND_FEATHER ? "feather_blend" : "no_blend", bb);
+    }
+    return v;
+}
+
 double BlendPlan::model_bytes(double *pyr, double *collapse) const
 {
     double bp = 0, bc = 0;
-    const double l0 = imgs.empty() ? 4.0 : (imgs[0].rgbm ? 4.0 : 7.0);  // bytes per level-0 pixel
-    if (kind == SB_BLEND_MULTIBAND) {
-        for (const FeedImage &im : imgs) {
-            const double A = (double)im.pw * im.ph;
-            for (int l = 0; l < nb; ++l) {
-                const double src = A / std::pow(4.0, l), dst = src / 4;
-                bp += (l == 0 ? l0 : 10.0) * src + 10.0 * dst;  // read level l, write level l+1
-            }
-            for (int l = 0; l <= nb; ++l) {
-                const double a = A / std::pow(4.0, l);
-                bc += (l == 0 ? l0 : 10.0) * a;       // G_l, W_l
-                if (l < nb) bc += 6.0 * a / 4;        // G_{l+1} for the pyrUp
-            }
-        }
-        const double P = (double)wp * hp;
-        for (int l = 1; l <= nb; ++l) bc += 2 * 6.0 * P / std::pow(4.0, l);  // C_l written once, read once
-        bc += 4.0 * (double)roi.w * roi.h;  // final uint8x3 + mask
-    } else {
-        for (const FeedImage &im : imgs) {
-            const double m = (double)im.w * im.h;
-            if (kind == SB_BLEND_FEATHER) bp += m * (1 + 4 + 4 + 4 + 4), bc += 4 * m;  // DT passes, weight read
-            bc += l0 * m;
-        }
-        bc += 4.0 * (double)roi.w * roi.h;
+    for (const auto &kv : launch_bytes()) {
+        if (kv.first.rfind("pyrdown", 0) == 0 || kv.first == "feather_weights") bp += kv.second;
+        else bc += kv.second;
     }
     if (pyr) *pyr = bp;
     if (collapse) *collapse = bc;

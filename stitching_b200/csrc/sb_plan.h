@@ -1,5 +1,8 @@
 // sb_plan.h -- host-side plan of one blend: pano geometry, per-feed padded rects, pyramid storage in HBM.
 #pragma once
+#include <functional>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "sb_internal.h"
@@ -42,7 +45,10 @@ public:
     int add_feed(const FeedDesc &f);  // computes the padded rect; SB_ERR_INVALID if the feed leaves the roi
     // device storage for pyramid levels >= 1, feather weights, pano levels; uploads descriptors
     int allocate(cudaStream_t s);
-    int run(const PanoOut &out, cudaStream_t s, cudaEvent_t *stage_events = nullptr);  // enqueue all blend kernels
+    // enqueue all blend kernels; `mark` (optional) is called after each launch with its name (timing hooks)
+    int run(const PanoOut &out, cudaStream_t s, const std::function<int(const std::string &)> &mark = nullptr);
+    // compulsory HBM traffic per launch, in launch order: (name, bytes)
+    std::vector<std::pair<std::string, double>> launch_bytes() const;
     void release(cudaStream_t s);
     double model_bytes(double *pyr, double *collapse) const;
     size_t arena_bytes() const { return arena_bytes_; }

@@ -1,0 +1,203 @@
+"""Generate the committed golden vectors from the UNMODIFIED reference.
+
+Runs only in the build container, where /root/reference (OpenStitching/stitching v0.7.0) and its numeric
+backend cv2 4.13.0 are importable:
+
+    python tests/golden/gen_golden.py
+
+Every expected output below is produced by the reference's own classes
+(stitching.warper.Warper, stitching.blender.Blender -- reference files stitching/warper.py, stitching/blender.py)
+or, for the pyramid primitives, by the cv2 calls OpenCV's blender makes internally.  The fixtures are replayed by
+tests/test_oracle_golden.py (CPU oracle) and tests/test_gpu_parity.py (CUDA path); neither needs the reference.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, "/root/reference")
+
+import cv2 as cv  # noqa: E402
+from stitching.blender import Blender as RefBlender  # noqa: E402
+from stitching.warper import Warper as RefWarper  # noqa: E402
+
+from stitching_b200 import rigs  # noqa: E402
+
+
+def rot(rx, ry, rz):
+    cz, sz = np.cos(rz), np.sin(rz)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return (Rz @ rigs.rot_y(ry) @ rigs.rot_x(rx)).astype(np.float32)
+
+
+def gen_warp():
+    rng = np.random.default_rng(20260922)
+    cases = []
+    W, H = 96, 72
+    specs = [
+        ("spherical", rot(0.05, 0.3, 0.02), 90.0, 80.0),
+        ("spherical", rot(1.35, -2.9, 0.1), 70.0, 75.0),     # pole in view, +-pi wrap
+        ("spherical", rot(-1.5, 1.0, -0.2), 60.0, 60.0),     # other pole
+        ("spherical", rot(0.2, 3.1, 0.0), 120.0, 100.0),     # z <= 0 region / wrap
+        ("cylindrical", rot(0.1, -0.4, 0.05), 90.0, 100.0),
+        ("cylindrical", rot(-0.3, 2.8, 0.2), 75.0, 60.0),
+        ("cylindrical", rot(0.4, -3.0, -0.1), 110.0, 95.0),
+        ("plane", rot(0.05, 0.1, 0.02), 90.0, 90.0),
+        ("plane", rot(0.4, -0.7, 0.3), 80.0, 60.0),          # steep: far out-of-range coordinates
+        ("plane", rot(-0.2, 0.9, -0.1), 100.0, 140.0),
+    ]
+    for k, (wtype, R, focal, scale) in enumerate(specs):
+        cam = rigs.Camera(focal, 1.0 + 0.03 * (k % 3 - 1), W / 2 + 3.5 * (k % 2), H / 2 - 2.25, R)
+        cases.append((wtype, cam, scale, 1.0))
+    for k in range(3):
+        th, s = [0.03, -0.2, 0.11][k], [1.0, 0.9, 1.15][k]
+        Hm = np.array([[s * np.cos(th), -s * np.sin(th), [12.5, -80.25, 301.0][k]],
+                       [s * np.sin(th), s * np.cos(th), [-7.75, 40.0, -33.5][k]], [0, 0, 1]], np.float32)
+        cases.append(("affine", rigs.Camera(1.0, 1.0, 0.0, 0.0, Hm), 1.0, [1.0, 1.0, 0.75][k]))
+    out = {"n": len(cases)}
+    for i, (wtype, cam, scale, aspect) in enumerate(cases):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        wr = RefWarper(wtype)
+        wr.scale = scale
+        out[f"type_{i}"] = wtype
+        out[f"cam_{i}"] = np.array([cam.focal, cam.aspect, cam.ppx, cam.ppy], np.float64)
+        out[f"R_{i}"] = cam.R
+        out[f"scale_{i}"] = np.float64(scale)
+        out[f"aspect_{i}"] = np.float64(aspect)
+        out[f"src_{i}"] = img
+        out[f"roi_{i}"] = np.array(wr.warp_roi((W, H), cam, aspect), np.int64)
+        out[f"img_{i}"] = wr.warp_image(img, cam, aspect)
+        out[f"mask_{i}"] = wr.create_and_warp_mask((W, H), cam, aspect)
+    np.savez_compressed(os.path.join(HERE, "golden_warp.npz"), **out)
+    print("warp cases", len(cases))
+
+
+def make_mask(kind, h, w, rng):
+    if kind == "full":
+        return np.full((h, w), 255, np.uint8)
+    if kind == "box":
+        m = np.zeros((h, w), np.uint8)
+        m[h // 5: h - h // 6, w // 7: w - w // 5] = 255
+        return m
+    if kind == "speckle":
+        return (rng.random((h, w)) > 0.3).astype(np.uint8) * 255
+    if kind == "ramp":
+        return np.clip(np.add.outer(np.arange(h), np.arange(w)) * 3, 0, 255).astype(np.uint8)
+    if kind == "gray":
+        return rng.integers(0, 256, (h, w), dtype=np.uint8)
+    raise KeyError(kind)
+
+
+def gen_blend():
+    rng = np.random.default_rng(7)
+    specs = [  # (blender, strength, mask kind, n images, int16 feed)
+        ("multiband", 5, "full", 3, False),
+        ("multiband", 5, "ramp", 3, False),
+        ("multiband", 20, "gray", 2, False),
+        ("multiband", 60, "box", 3, False),
+        ("multiband", 100, "speckle", 2, False),   # nb clipped by ceil(log2(max(w,h)))
+        ("multiband", 2, "full", 2, False),        # 0 bands
+        ("multiband", 20, "ramp", 2, True),        # generic int16 input incl. negatives
+        ("feather", 5, "box", 3, False),
+        ("feather", 20, "speckle", 2, False),
+        ("feather", 5, "full", 2, True),
+        ("no", 5, "gray", 3, False),
+        ("multiband", 0.2, "box", 2, False),       # blend width < 1 -> NO blender
+    ]
+    out = {"n": len(specs)}
+    for i, (btype, strength, mk, n, s16) in enumerate(specs):
+        imgs, masks, corners = [], [], []
+        for j in range(n):
+            w, h = int(rng.integers(40, 110)), int(rng.integers(30, 90))
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if (i + j) % 2 else rigs.synth_image(h, w, 50 + 10 * i + j)
+            if s16:
+                img = img.astype(np.int16) * 3 - 150
+            imgs.append(img)
+            masks.append(make_mask(mk, h, w, rng))
+            corners.append((int(rng.integers(-60, 60)), int(rng.integers(-40, 40))))
+        sizes = [(m.shape[1], m.shape[0]) for m in masks]
+        b = RefBlender(btype, strength)
+        b.prepare(corners, sizes)
+        for img, m, c in zip(imgs, masks, corners):
+            b.feed(img, m, c)
+        pano, pmask = b.blend()
+        out[f"type_{i}"] = btype
+        out[f"strength_{i}"] = np.float64(strength)
+        out[f"count_{i}"] = n
+        for j in range(n):
+            out[f"img_{i}_{j}"] = imgs[j]
+            out[f"mask_{i}_{j}"] = masks[j]
+            out[f"corner_{i}_{j}"] = np.array(corners[j], np.int64)
+        out[f"pano_{i}"] = pano
+        out[f"pmask_{i}"] = pmask
+    np.savez_compressed(os.path.join(HERE, "golden_blend.npz"), **out)
+    print("blend cases", len(specs))
+
+
+def gen_pyr():
+    rng = np.random.default_rng(11)
+    out = {}
+    shapes = [(64, 96), (34, 50), (2, 2), (6, 4), (16, 2), (2, 8), (40, 136)]
+    out["n"] = len(shapes)
+    for i, (h, w) in enumerate(shapes):
+        a = rng.integers(-3000, 3000, (h, w, 3)).astype(np.int16)
+        f = rng.random((h, w), dtype=np.float32)
+        out[f"s16_{i}"] = a
+        out[f"f32_{i}"] = f
+        out[f"down_s16_{i}"] = cv.pyrDown(a)
+        out[f"down_f32_{i}"] = cv.pyrDown(f)
+        out[f"up_s16_{i}"] = cv.pyrUp(a)
+    v = np.array([-3, 260, -300, 100, -32768, 32767, 0, 255, -255, 256], np.int16)
+    out["csa_in"] = v
+    out["csa_out"] = cv.convertScaleAbs(v.reshape(1, -1)).reshape(-1)
+    m = (rng.random((40, 60)) > 0.2).astype(np.uint8) * 255
+    out["dt_mask"] = m
+    out["dt_l1"] = cv.distanceTransform(m, cv.DIST_L1, 3)
+    np.savez_compressed(os.path.join(HERE, "golden_pyr.npz"), **out)
+    print("pyr cases", len(shapes))
+
+
+def gen_e2e():
+    """Reference Warper + Blender driven like stitcher.py:178-189, 241-259 on scaled-down BASELINE rigs."""
+    out = {}
+    for name, sd, ncap in (("cfg2", 20, None), ("cfg3", 20, 6), ("cfg5", 10, None)):
+        cfg = rigs.config(name, sd)
+        cams = cfg["cameras"][:ncap] if ncap else cfg["cameras"]
+        imgs = [rigs.synth_image(cfg["h"], cfg["w"], i) for i in range(len(cams))]
+        wr = RefWarper(cfg["warper"])
+        wr.set_scale(cams)
+        sizes_in = [(cfg["w"], cfg["h"])] * len(cams)
+        warped = list(wr.warp_images(imgs, cams))
+        masks = list(wr.create_and_warp_masks(sizes_in, cams))
+        corners, sizes = wr.warp_rois(sizes_in, cams)
+        b = RefBlender(cfg["blender"], cfg["strength"])
+        b.prepare(corners, sizes)
+        for img, m, c in zip(warped, masks, corners):
+            b.feed(img, m, c)
+        pano, pmask = b.blend()
+        h = hashlib.sha256()
+        for im in imgs:
+            h.update(im.tobytes())
+        out[f"{name}_scale_down"] = sd
+        out[f"{name}_n"] = len(cams)
+        out[f"{name}_input_sha256"] = h.hexdigest()
+        out[f"{name}_corners"] = np.array(corners, np.int64)
+        out[f"{name}_sizes"] = np.array(sizes, np.int64)
+        out[f"{name}_pano"] = pano
+        out[f"{name}_pmask"] = pmask
+        print(name, "pano", pano.shape)
+    np.savez_compressed(os.path.join(HERE, "golden_e2e.npz"), **out)
+
+
+if __name__ == "__main__":
+    print("cv2", cv.__version__)
+    gen_warp()
+    gen_blend()
+    gen_pyr()
+    gen_e2e()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -1,0 +1,164 @@
+"""Replay of the committed golden vectors (tests/golden/*.npz) against an implementation.
+
+The same functions check the CPU oracle (tests/test_oracle_golden.py) and the CUDA path through the Python
+drop-ins (tests/test_gpu_parity.py, tests/test_host_logic.py via the emulation build).
+"""
+import hashlib
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def diff_report(got, exp, what):
+    got = np.asarray(got)
+    exp = np.asarray(exp)
+    assert got.shape == exp.shape, f"{what}: shape {got.shape} != {exp.shape}"
+    d = np.abs(got.astype(np.int64) - exp.astype(np.int64))
+    n = int((d != 0).sum())
+    return n, (int(d.max()) if n else 0), f"{what}: {n}/{d.size} values differ, max |diff| {int(d.max()) if d.size else 0}"
+
+
+def assert_exact(got, exp, what):
+    n, mx, msg = diff_report(got, exp, what)
+    assert n == 0, msg
+
+
+def warp_cases():
+    g = load("golden_warp.npz")
+    from stitching_b200 import rigs
+
+    for i in range(int(g["n"])):
+        f, a, px, py = g[f"cam_{i}"]
+        cam = rigs.Camera(f, a, px, py, g[f"R_{i}"])
+        yield dict(i=i, wtype=str(g[f"type_{i}"]), cam=cam, scale=float(g[f"scale_{i}"]), aspect=float(g[f"aspect_{i}"]),
+                   src=g[f"src_{i}"], roi=tuple(int(v) for v in g[f"roi_{i}"]), img=g[f"img_{i}"], mask=g[f"mask_{i}"])
+
+
+def blend_cases():
+    g = load("golden_blend.npz")
+    for i in range(int(g["n"])):
+        n = int(g[f"count_{i}"])
+        yield dict(i=i, btype=str(g[f"type_{i}"]), strength=float(g[f"strength_{i}"]),
+                   imgs=[g[f"img_{i}_{j}"] for j in range(n)], masks=[g[f"mask_{i}_{j}"] for j in range(n)],
+                   corners=[tuple(int(v) for v in g[f"corner_{i}_{j}"]) for j in range(n)],
+                   pano=g[f"pano_{i}"], pmask=g[f"pmask_{i}"])
+
+
+def e2e_cases():
+    g = load("golden_e2e.npz")
+    from stitching_b200 import rigs
+
+    for name in ("cfg2", "cfg3", "cfg5"):
+        cfg = rigs.config(name, int(g[f"{name}_scale_down"]))
+        n = int(g[f"{name}_n"])
+        cams = cfg["cameras"][:n]
+        imgs = [rigs.synth_image(cfg["h"], cfg["w"], i) for i in range(n)]
+        h = hashlib.sha256()
+        for im in imgs:
+            h.update(im.tobytes())
+        assert h.hexdigest() == str(g[f"{name}_input_sha256"]), "synthetic input generator drifted from the goldens"
+        yield dict(name=name, cfg=cfg, cams=cams, imgs=imgs, corners=[tuple(int(v) for v in r) for r in g[f"{name}_corners"]],
+                   sizes=[tuple(int(v) for v in r) for r in g[f"{name}_sizes"]], pano=g[f"{name}_pano"], pmask=g[f"{name}_pmask"])
+
+
+def run_warper_goldens(WarperCls):
+    """WarperCls follows stitching/warper.py's interface."""
+    for c in warp_cases():
+        w = WarperCls(c["wtype"])
+        w.scale = c["scale"]
+        size = (c["src"].shape[1], c["src"].shape[0])
+        assert tuple(w.warp_roi(size, c["cam"], c["aspect"])) == c["roi"], f"warp case {c['i']} ({c['wtype']}): roi"
+        assert_exact(w.warp_image(c["src"], c["cam"], c["aspect"]), c["img"], f"warp case {c['i']} ({c['wtype']}) image")
+        assert_exact(w.create_and_warp_mask(size, c["cam"], c["aspect"]), c["mask"], f"warp case {c['i']} ({c['wtype']}) mask")
+
+
+def run_blender_goldens(BlenderCls):
+    """BlenderCls follows stitching/blender.py's interface."""
+    for c in blend_cases():
+        b = BlenderCls(c["btype"], c["strength"])
+        sizes = [(m.shape[1], m.shape[0]) for m in c["masks"]]
+        b.prepare(c["corners"], sizes)
+        for img, m, corner in zip(c["imgs"], c["masks"], c["corners"]):
+            b.feed(img, m, corner)
+        pano, pmask = b.blend()
+        assert_exact(pano, c["pano"], f"blend case {c['i']} ({c['btype']} strength {c['strength']}) pano")
+        assert_exact(pmask, c["pmask"], f"blend case {c['i']} ({c['btype']}) mask")
+
+
+def run_e2e_goldens(WarperCls, BlenderCls):
+    for c in e2e_cases():
+        cfg = c["cfg"]
+        w = WarperCls(cfg["warper"])
+        w.set_scale(c["cams"])
+        sizes_in = [(cfg["w"], cfg["h"])] * len(c["cams"])
+        warped = list(w.warp_images(c["imgs"], c["cams"]))
+        masks = list(w.create_and_warp_masks(sizes_in, c["cams"]))
+        corners, sizes = w.warp_rois(sizes_in, c["cams"])
+        assert [tuple(x) for x in corners] == c["corners"] and [tuple(x) for x in sizes] == c["sizes"], f"{c['name']}: rois"
+        b = BlenderCls(cfg["blender"], cfg["strength"])
+        b.prepare(corners, sizes)
+        for img, m, corner in zip(warped, masks, corners):
+            b.feed(img, m, corner)
+        pano, pmask = b.blend()
+        assert_exact(pano, c["pano"], f"{c['name']} pano")
+        assert_exact(pmask, c["pmask"], f"{c['name']} mask")
+
+
+class OracleWarper:
+    """stitching/warper.py's interface on the CPU oracle (for the replay functions above)."""
+
+    def __init__(self, wtype):
+        from oracle import oracle as O
+        from stitching_b200.warper import Warper
+
+        self.O, self.wtype, self.scale, self._get_K = O, wtype, None, Warper.get_K
+
+    def set_scale(self, cameras):
+        from statistics import median
+
+        self.scale = median([c.focal for c in cameras])
+
+    def warp_roi(self, size, cam, aspect=1):
+        return self.O.warp_roi(self.wtype, self.scale * aspect, self._get_K(cam, aspect), cam.R, size)
+
+    def warp_image(self, img, cam, aspect=1):
+        return self.O.warp(self.wtype, self.scale * aspect, self._get_K(cam, aspect), cam.R, img, True, False)[1]
+
+    def create_and_warp_mask(self, size, cam, aspect=1):
+        dummy = np.zeros((size[1], size[0], 3), np.uint8)
+        return self.O.warp(self.wtype, self.scale * aspect, self._get_K(cam, aspect), cam.R, dummy, False, True)[2]
+
+    def warp_images(self, imgs, cams, aspect=1):
+        return (self.warp_image(i, c, aspect) for i, c in zip(imgs, cams))
+
+    def create_and_warp_masks(self, sizes, cams, aspect=1):
+        return (self.create_and_warp_mask(s, c, aspect) for s, c in zip(sizes, cams))
+
+    def warp_rois(self, sizes, cams, aspect=1):
+        rois = [self.warp_roi(s, c, aspect) for s, c in zip(sizes, cams)]
+        return [r[0:2] for r in rois], [r[2:4] for r in rois]
+
+
+def oracle_composite(O, cfg, cams, imgs):
+    """Warp + blend on the CPU oracle the way stitcher.py:178-189, 241-259 drive the reference classes."""
+    w = OracleWarper(cfg["warper"])
+    w.set_scale(cams)
+    warped, masks, corners, sizes = [], [], [], []
+    for img, cam in zip(imgs, cams):
+        rect, wi, wm = O.warp(cfg["warper"], w.scale, w._get_K(cam, 1), cam.R, img)
+        warped.append(wi)
+        masks.append(wm)
+        corners.append(rect[:2])
+        sizes.append(rect[2:])
+    b = O.Blender(cfg["blender"], cfg["strength"])
+    b.prepare(corners, sizes)
+    for wi, wm, c in zip(warped, masks, corners):
+        b.feed(wi, wm, c)
+    pano, pmask = b.blend()
+    return dict(warped=warped, masks=masks, corners=corners, sizes=sizes, pano=pano, pmask=pmask, num_bands=b.num_bands)

@@ -1,0 +1,148 @@
+"""Host logic of the product (plans, geometry, error behaviour, Python drop-ins) on a GPU-less box.
+
+These tests compile the PRODUCT sources against tests/emu's serial CUDA stand-in -- test infrastructure
+that lets the plan / index arithmetic run without a device.  The CUDA build itself is covered by
+tests/test_gpu_parity.py (-m gpu).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import replay
+from stitching_b200 import Blender, Compositor, StitchingError, Warper, rigs
+
+
+def test_interface_constants_match_the_reference_boundary():
+    # warper.py:10-29, blender.py:8-14 (what stitcher.py / cli/stitch.py read)
+    assert Warper.DEFAULT_WARP_TYPE == "spherical"
+    assert len(Warper.WARP_TYPE_CHOICES) == 16 and Warper.WARP_TYPE_CHOICES[:4] == ("spherical", "plane", "affine", "cylindrical")
+    assert Blender.BLENDER_CHOICES == ("multiband", "feather", "no")
+    assert Blender.DEFAULT_BLENDER == "multiband" and Blender.DEFAULT_BLEND_STRENGTH == 5
+
+
+def test_warper_goldens_through_emulated_library(use_emu):
+    replay.run_warper_goldens(Warper)
+
+
+def test_blender_goldens_through_emulated_library(use_emu):
+    replay.run_blender_goldens(Blender)
+
+
+def test_e2e_goldens_through_emulated_library(use_emu):
+    replay.run_e2e_goldens(Warper, Blender)
+
+
+def test_compositor_matches_oracle(use_emu, oracle):
+    for name, sd, ncap in (("cfg2", 25, None), ("cfg3", 25, 5), ("cfg5", 12, None)):
+        cfg = rigs.config(name, sd)
+        cams = cfg["cameras"][:ncap] if ncap else cfg["cameras"]
+        imgs = [rigs.noise_image(cfg["h"], cfg["w"], 1000 + i) for i in range(len(cams))]
+        ref = replay.oracle_composite(oracle, cfg, cams, imgs)
+        c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+        assert [r[:2] for r in c.rects] == [tuple(x) for x in ref["corners"]]
+        assert [r[2:] for r in c.rects] == [tuple(x) for x in ref["sizes"]]
+        if cfg["blender"] == "multiband":
+            assert c.num_bands == ref["num_bands"]
+        pano, mask = c.composite(imgs)
+        replay.assert_exact(pano, ref["pano"], f"{name} pano")
+        replay.assert_exact(mask, ref["pmask"], f"{name} mask")
+        wi, wm = c.download_warped(1)
+        replay.assert_exact(wi, ref["warped"][1], f"{name} warped image 1")
+        replay.assert_exact(wm, ref["masks"][1], f"{name} warped mask 1")
+        total, per_launch = c.model_bytes()
+        assert total > 0 and abs(sum(per_launch) - total) < 1e-6 * total
+        ms, launches = c.time(1)
+        assert len(launches) == len(per_launch) and launches[0][0] == "warp"
+        c.close()
+
+
+def test_band_clipping_matches_oracle(use_emu, oracle):
+    """MultiBandBlender::prepare's band clipping -- product plan vs oracle restatement."""
+    rng = np.random.default_rng(3)
+    L = oracle.lib()
+    for _ in range(200):
+        n = int(rng.integers(1, 5))
+        sizes = [(int(rng.integers(5, 400)), int(rng.integers(5, 300))) for _ in range(n)]
+        corners = [(int(rng.integers(-500, 500)), int(rng.integers(-300, 300))) for _ in range(n)]
+        roi = oracle.result_roi(corners, sizes)
+        nbr = int(rng.integers(0, 12))
+        h = L.so_mb_create(nbr, *roi)
+        b = use_emu.sb_blender_create(2, nbr, C.c_float(0))
+        assert use_emu.sb_blender_prepare(b, *roi) == 0
+        assert use_emu.sb_blender_num_bands(b) == L.so_mb_num_bands(h)
+        use_emu.sb_blender_destroy(b)
+        L.so_mb_destroy(h)
+
+
+def test_generators_and_fused_extension(use_emu):
+    cams = rigs.yaw_ring(3, 80, 60, 90, 25)
+    w = Warper("cylindrical")
+    w.set_scale(cams)
+    imgs = [rigs.noise_image(60, 80, i) for i in range(3)]
+    gen = w.warp_images(imgs, cams)
+    assert hasattr(gen, "__next__")  # stitcher.py:185-189 relies on laziness
+    first = next(gen)
+    both = w.warp_image_and_mask(imgs[0], cams[0])
+    assert np.array_equal(first, both[0])
+    assert np.array_equal(w.create_and_warp_mask((80, 60), cams[0]), both[1])
+    corners, sizes = w.warp_rois([(80, 60)] * 3, cams)
+    assert len(corners) == 3 and all(len(c) == 2 for c in corners) and first.shape[:2] == (sizes[0][1], sizes[0][0])
+    # a cropped (non-contiguous) view is accepted, like the reference after cropper.py:150-151
+    big = rigs.noise_image(70, 100, 9)
+    view = big[5:65, 10:90]
+    assert np.array_equal(w.warp_image(view, cams[0]), w.warp_image(np.ascontiguousarray(view), cams[0]))
+
+
+def test_error_behaviour(use_emu):
+    cams = rigs.yaw_ring(2, 64, 48, 70, 20)
+    w = Warper()
+    with pytest.raises(TypeError):  # scale is None until set_scale (warper.py:44)
+        w.warp_roi((64, 48), cams[0])
+    w.set_scale(cams)
+    bad = rigs.Camera(70, 1, 32, 24, np.eye(3))
+    bad.R = np.eye(3, dtype=np.float64)  # cv2 asserts CV_32F
+    with pytest.raises(StitchingError):
+        w.warp_roi((64, 48), bad)
+    f = Warper("fisheye")  # the constructor accepts every reference choice; using an unported one raises
+    f.scale = 1.0
+    with pytest.raises(StitchingError):
+        f.warp_roi((64, 48), cams[0])
+    b = Blender("multiband", 5)
+    with pytest.raises(AttributeError):  # blender.py:41 before prepare: self.blender is None
+        b.feed(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4), np.uint8), (0, 0))
+    b.prepare([(0, 0), (30, 0)], [(40, 30), (40, 30)])
+    with pytest.raises(StitchingError):  # leaves the prepared roi
+        b.feed(np.zeros((30, 40, 3), np.uint8), np.full((30, 40), 255, np.uint8), (500, 0))
+    with pytest.raises(StitchingError):  # mask / image size mismatch
+        b.feed(np.zeros((30, 40, 3), np.uint8), np.full((30, 41), 255, np.uint8), (0, 0))
+    b.feed(np.zeros((30, 40, 3), np.uint8), np.full((30, 40), 255, np.uint8), (0, 0))
+    pano, mask = b.blend()
+    assert pano.shape == (30, 70, 3) and mask.shape == (30, 70) and pano.dtype == np.uint8
+    with pytest.raises(StitchingError):  # blend() consumed the state, like OpenCV
+        b.blender.blend()
+    # blend width < 1 silently selects the NO blender (blender.py:27)
+    tiny = Blender("multiband", 0.1)
+    tiny.prepare([(0, 0)], [(8, 8)])
+    assert tiny.blender.kind == "no"
+
+
+def test_umat_like_mask_and_create_panorama(use_emu, oracle):
+    class FakeUMat:  # cv.UMat exposes .get() -> ndarray (seam_finder.py:38-43 hands UMats to Blender.feed)
+        def __init__(self, a):
+            self._a = a
+
+        def get(self):
+            return self._a
+
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (20, 30, 3), dtype=np.uint8) for _ in range(2)]
+    masks = [rng.integers(0, 2, (20, 30), dtype=np.uint8) * 255 for _ in range(2)]
+    corners, sizes = [(0, 0), (12, 5)], [(30, 20), (30, 20)]
+    pano, pmask = Blender.create_panorama(imgs, [FakeUMat(m) for m in masks], corners, sizes)
+    o = oracle.Blender("no")
+    o.prepare(corners, sizes)
+    for i, m, c in zip(imgs, masks, corners):
+        o.feed(i, m, c)
+    ep, em = o.blend()
+    assert np.array_equal(pano, ep) and np.array_equal(pmask, em)

@@ -1,0 +1,28 @@
+"""The CPU oracle against the golden vectors produced by the unmodified reference (bit-exact)."""
+import numpy as np
+
+import replay
+
+
+def test_oracle_warp_goldens(oracle):
+    replay.run_warper_goldens(replay.OracleWarper)
+
+
+def test_oracle_blend_goldens(oracle):
+    replay.run_blender_goldens(oracle.Blender)
+
+
+def test_oracle_e2e_goldens(oracle):
+    replay.run_e2e_goldens(replay.OracleWarper, oracle.Blender)
+
+
+def test_oracle_pyramid_goldens(oracle):
+    g = replay.load("golden_pyr.npz")
+    for i in range(int(g["n"])):
+        replay.assert_exact(oracle.pyrdown_s16(g[f"s16_{i}"]), g[f"down_s16_{i}"], f"pyrDown s16 case {i}")
+        replay.assert_exact(oracle.pyrup_s16(g[f"s16_{i}"]), g[f"up_s16_{i}"], f"pyrUp s16 case {i}")
+        got = oracle.pyrdown_f32(g[f"f32_{i}"])
+        assert np.array_equal(got.view(np.uint32), g[f"down_f32_{i}"].view(np.uint32)), f"pyrDown f32 case {i} not bit-exact"
+    replay.assert_exact(oracle.convert_scale_abs(g["csa_in"]), g["csa_out"], "convertScaleAbs")
+    d = oracle.dist_l1(g["dt_mask"])
+    assert np.array_equal(d, g["dt_l1"]), "distanceTransform L1"
