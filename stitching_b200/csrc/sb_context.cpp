@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 
 #include "sb_internal.h"
 
@@ -138,3 +139,14 @@ void sb_host_free(void *p)
 }
 
 }  // extern "C"
+
+namespace sb {
+bool use_simple_kernels()
+{
+    static const bool simple = [] {
+        const char *e = getenv("SB_KERNELS");
+        return e && std::string(e) == "simple";
+    }();
+    return simple;
+}
+}  // namespace sb

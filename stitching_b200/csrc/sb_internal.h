@@ -118,7 +118,10 @@ int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaS
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)
-int launch_pyrdown(const FeedImage *imgs_dev, int first, int count, int l, int max_w, int max_h, cudaStream_t s);
+int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, int first, int count, int l, int max_w, int max_h,
+                   cudaStream_t s);
+// SB_KERNELS=simple selects the one-thread-per-pixel gather kernels everywhere (debugging / A-B parity)
+bool use_simple_kernels();
 // multiband: accumulate + normalise + collapse level l (top-down); at l == 0 writes the final outputs
 int launch_collapse(const FeedImage *imgs_dev, int n, const PanoLevel *pano_dev, int l, int nb, int lw, int lh,
                     PanoOut out, cudaStream_t s);

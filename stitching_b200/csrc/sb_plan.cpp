@@ -231,7 +231,7 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
                 mw = std::max(mw, im.pw >> (l + 1));
                 mh = std::max(mh, im.ph >> (l + 1));
             }
-            SB_TRY(launch_pyrdown(imgs_dev, 0, n, l, mw, mh, s));
+            SB_TRY(launch_pyrdown(imgs_dev, imgs.data(), 0, n, l, mw, mh, s));
             SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
         for (int l = nb; l >= 0; --l) {
