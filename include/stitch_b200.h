@@ -130,6 +130,13 @@ SB_API int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, 
 SB_API int sb_compositor_run(sb_compositor *c);
 /* device -> host copy of the panorama (uint8 HxWx3 + uint8 mask); synchronises */
 SB_API int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch);
+/* Pipelined end-to-end step (throughput path): enqueue H2D of the n sources, warp + blend, and D2H of the
+ * panorama on separate streams chained by events, and return a ticket.  Two buffer sets are kept, so at most
+ * two tickets may be in flight: the copies of one step overlap the kernels of its neighbours.  Host buffers
+ * should be page-locked (sb_host_alloc) and must stay valid until sb_compositor_wait(ticket) returns. */
+SB_API int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const size_t *pitches, uint8_t *dst,
+                                size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, unsigned long long *ticket);
+SB_API int sb_compositor_wait(sb_compositor *c, unsigned long long ticket);
 /* device -> host copy of warped image i / its mask (for parity tests of the fused path) */
 SB_API int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask,
                                          size_t mask_pitch);

@@ -64,6 +64,9 @@ SIGNATURES = [
     ("sb_compositor_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     ("sb_compositor_download_warped", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     ("sb_compositor_sync", C.c_int, [C.c_void_p]),
+    ("sb_compositor_submit", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_ulonglong)]),
+    ("sb_compositor_wait", C.c_int, [C.c_void_p, C.c_ulonglong]),
     ("sb_compositor_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     ("sb_compositor_stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), c_float_p, C.c_int]),
     ("sb_host_alloc", C.c_void_p, [C.c_size_t]),

@@ -87,6 +87,36 @@ class Compositor:
                    "sb_compositor_download_warped")
         return img, mask
 
+    def submit(self, images, out, out_mask):
+        """Pipelined step: enqueue upload of `images`, warp + blend, download into `out` / `out_mask`; returns a
+        ticket for wait().  At most two tickets in flight; host arrays should live in pinned memory
+        (`pinned_empty`) and must stay untouched until wait(ticket) returns."""
+        n = self.n
+        ptrs = (C.c_void_p * n)()
+        pitches = (C.c_size_t * n)()
+        for i, img in enumerate(images):
+            if img.dtype != np.uint8 or img.shape != (self.sizes[i][1], self.sizes[i][0], 3) or img.strides[1:] != (3, 1):
+                raise StitchingError(f"image {i}: expected a uint8 {self.sizes[i][1]}x{self.sizes[i][0]}x3 array with packed pixels")
+            ptrs[i] = img.ctypes.data
+            pitches[i] = img.strides[0]
+        ticket = C.c_ulonglong()
+        _lib.check(_lib.lib().sb_compositor_submit(self._c, ptrs, pitches, out.ctypes.data_as(C.c_void_p), out.strides[0],
+                                                   out_mask.ctypes.data_as(C.c_void_p), out_mask.strides[0], C.byref(ticket)),
+                   "sb_compositor_submit")
+        return ticket.value
+
+    def wait(self, ticket):
+        _lib.check(_lib.lib().sb_compositor_wait(self._c, C.c_ulonglong(ticket)), "sb_compositor_wait")
+
+    def pinned_empty(self, shape):
+        """uint8 ndarray in page-locked host memory (freed with the compositor)."""
+        nbytes = int(np.prod(shape))
+        p = _lib.lib().sb_host_alloc(nbytes)
+        if not p:
+            _lib.check(-5, "sb_host_alloc")
+        self._pinned.append(p)
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p)).reshape(shape)
+
     def composite(self, images):
         """One call: upload, warp + blend, download.  Returns (uint8 pano, uint8 mask) like Blender.blend()."""
         self.upload(images)
@@ -118,8 +148,11 @@ class Compositor:
 
     def close(self):
         if getattr(self, "_c", None):
-            _lib.lib().sb_compositor_destroy(self._c)
+            _lib.lib().sb_compositor_destroy(self._c)  # synchronises all its streams first
             self._c = None
+            for p in self._pinned:
+                _lib.lib().sb_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:

@@ -108,7 +108,7 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
     WarpJob job;
     SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));
     if (dst_img) {
-        SB_TRY(tmp.get(&d_src, (size_t)src_w * 3 * src_h));
+        SB_TRY(tmp.get(&d_src, (size_t)src_w * 3 * src_h + SB_SRC_PAD));
         SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
         SB_CUDA(cudaMemcpy2DAsync(d_src, (size_t)src_w * 3, src, src_pitch, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, s));
         job.src = d_src;

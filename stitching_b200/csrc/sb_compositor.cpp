@@ -40,6 +40,14 @@ struct sb_compositor {
     std::vector<std::string> launch_names;
     std::vector<float> launch_ms;      // per launch, averaged over the last sb_compositor_time call
     double warp_bytes = 0;
+    // pipelined submit / wait: a second set of source + output buffers, copy streams, per-slot events
+    bool pipe_ready = false;
+    std::vector<uint8_t *> src_dev2;
+    WarpJob *jobs_dev2 = nullptr;
+    PanoOut out2;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+    unsigned long long submitted = 0;
 };
 
 static void compositor_free(sb_compositor *c)
@@ -55,6 +63,21 @@ static void compositor_free(sb_compositor *c)
     dev_free(c->out.rgb, s);
     dev_free(c->out.mask, s);
     dev_free(c->flush_buf, s);
+    if (c->h2d) (void)cudaStreamSynchronize(c->h2d);
+    if (c->d2h) (void)cudaStreamSynchronize(c->d2h);
+    for (auto p : c->src_dev2) dev_free(p, s);
+    dev_free(c->jobs_dev2, s);
+    if (c->pipe_ready) {
+        dev_free(c->out2.rgb, s);
+        dev_free(c->out2.mask, s);
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (c->e_h2d[k]) (void)cudaEventDestroy(c->e_h2d[k]);
+        if (c->e_comp[k]) (void)cudaEventDestroy(c->e_comp[k]);
+        if (c->e_d2h[k]) (void)cudaEventDestroy(c->e_d2h[k]);
+    }
+    if (c->h2d) (void)cudaStreamDestroy(c->h2d);
+    if (c->d2h) (void)cudaStreamDestroy(c->d2h);
     c->plan.release(s);
     for (auto &e : c->ev)
         if (e) (void)cudaEventDestroy(e);
@@ -104,7 +127,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
         sizes[2 * i + 1] = rect[3];
         c->max_w = std::max(c->max_w, rect[2]);
         c->max_h = std::max(c->max_h, rect[3]);
-        SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i], s));
+        SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
         SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rect[2] * rect[3] * 4, s));
         SB_TRY(dev_alloc((void **)&c->tab_dev[i], ((size_t)2 * rect[2] + 2 * rect[3]) * sizeof(float), s));
         SB_TRY(make_warp_job(p, rect, c->src_w[i], c->src_h[i], c->tab_dev[i], &c->jobs[i], s, host_tab));
@@ -147,7 +170,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
     return SB_OK;
 }
 
-static int compositor_enqueue(sb_compositor *c, bool events)
+static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
 {
     cudaStream_t s = c->stream;
     size_t k = 0;
@@ -166,9 +189,40 @@ static int compositor_enqueue(sb_compositor *c, bool events)
         return SB_OK;
     };
     SB_TRY(mark("start"));
-    SB_TRY(launch_warp(c->jobs_dev, c->n, c->max_w, c->max_h, s));
+    SB_TRY(launch_warp(slot ? c->jobs_dev2 : c->jobs_dev, c->n, c->max_w, c->max_h, s));
     SB_TRY(mark("warp"));
-    SB_TRY(c->plan.run(c->out, s, events ? std::function<int(const std::string &)>(mark) : nullptr));
+    SB_TRY(c->plan.run(slot ? c->out2 : c->out, s, events ? std::function<int(const std::string &)>(mark) : nullptr));
+    return SB_OK;
+}
+
+// second buffer set + copy streams for sb_compositor_submit / _wait
+static int compositor_pipe_init(sb_compositor *c)
+{
+    if (c->pipe_ready) return SB_OK;
+    cudaStream_t s = c->stream;
+    c->src_dev2.assign(c->n, nullptr);
+    std::vector<WarpJob> jobs2 = c->jobs;
+    for (int i = 0; i < c->n; ++i) {
+        SB_TRY(dev_alloc((void **)&c->src_dev2[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
+        jobs2[i].src = c->src_dev2[i];
+    }
+    SB_TRY(dev_alloc((void **)&c->jobs_dev2, sizeof(WarpJob) * c->n, s));
+    SB_CUDA(cudaMemcpyAsync(c->jobs_dev2, jobs2.data(), sizeof(WarpJob) * c->n, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));  // jobs2 is a local
+    c->out2 = c->out;
+    c->out2.rgb = nullptr;
+    c->out2.mask = nullptr;
+    SB_TRY(dev_alloc((void **)&c->out2.rgb, (size_t)c->out.w * 3 * c->out.h, s));
+    SB_TRY(dev_alloc((void **)&c->out2.mask, (size_t)c->out.w * c->out.h, s));
+    SB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        SB_CUDA(cudaEventCreateWithFlags(&c->e_h2d[k], cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&c->e_comp[k], cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&c->e_d2h[k], cudaEventDisableTiming));
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+    c->pipe_ready = true;
     return SB_OK;
 }
 
@@ -285,6 +339,57 @@ int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uin
         SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, c->out.mask, (size_t)c->out.mask_pitch, c->out.w, c->out.h,
                                   cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+// Pipelined end-to-end step: H2D of this batch, warp + blend, D2H of the panorama are enqueued on three
+// streams and chained with events; with two buffer sets the copies of step k overlap the kernels of step k+-1.
+int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const size_t *pitches, uint8_t *dst, size_t dst_pitch,
+                         uint8_t *dst_mask, size_t mask_pitch, unsigned long long *ticket)
+{
+    if (!c || !srcs || !pitches || (dst && dst_pitch < (size_t)c->out.w * 3) || (dst_mask && mask_pitch < (size_t)c->out.w)) {
+        set_error("sb_compositor_submit: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    for (int i = 0; i < c->n; ++i)
+        if (!srcs[i] || pitches[i] < (size_t)c->src_w[i] * 3) {
+            set_error("sb_compositor_submit: invalid source %d", i);
+            return SB_ERR_INVALID;
+        }
+    SB_TRY(compositor_pipe_init(c));
+    const unsigned long long t = c->submitted;
+    const int slot = (int)(t & 1);
+    const std::vector<uint8_t *> &sdev = slot ? c->src_dev2 : c->src_dev;
+    const PanoOut &o = slot ? c->out2 : c->out;
+    // sources of this slot are free once the previous compute that read them has finished
+    if (t >= 2) SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
+    for (int i = 0; i < c->n; ++i)
+        SB_CUDA(cudaMemcpy2DAsync(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
+                                  cudaMemcpyHostToDevice, c->h2d));
+    SB_CUDA(cudaEventRecord(c->e_h2d[slot], c->h2d));
+    SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_h2d[slot], 0));
+    // the output buffers of this slot are free once their previous download has finished
+    if (t >= 2) SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_d2h[slot], 0));
+    SB_TRY(compositor_enqueue(c, false, slot));
+    SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
+    SB_CUDA(cudaStreamWaitEvent(c->d2h, c->e_comp[slot], 0));
+    if (dst)
+        SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, o.rgb, (size_t)o.rgb_pitch, (size_t)o.w * 3, o.h, cudaMemcpyDeviceToHost, c->d2h));
+    if (dst_mask)
+        SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, o.mask, (size_t)o.mask_pitch, o.w, o.h, cudaMemcpyDeviceToHost, c->d2h));
+    SB_CUDA(cudaEventRecord(c->e_d2h[slot], c->d2h));
+    c->submitted = t + 1;
+    if (ticket) *ticket = t;
+    return SB_OK;
+}
+
+int sb_compositor_wait(sb_compositor *c, unsigned long long ticket)
+{
+    if (!c || !c->pipe_ready || ticket >= c->submitted || ticket + 2 < c->submitted) {
+        set_error("sb_compositor_wait: ticket %llu is not in flight", ticket);
+        return SB_ERR_STATE;
+    }
+    SB_CUDA(cudaEventSynchronize(c->e_d2h[ticket & 1]));
     return SB_OK;
 }
 

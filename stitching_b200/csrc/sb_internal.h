@@ -10,6 +10,7 @@
 
 #define SB_MAX_BANDS 16
 #define SB_MAX_IMAGES 256
+#define SB_SRC_PAD 16  // spare bytes after a source image: the warp kernel reads aligned 8-byte words
 
 namespace sb {
 

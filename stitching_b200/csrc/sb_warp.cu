@@ -79,6 +79,68 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const WarpJob 
     if (j.dst_rgbm) j.dst_rgbm[(long long)v * j.rgbm_pitch + u] = out[0] | (out[1] << 8) | (out[2] << 16) | (m << 24);
 }
 
+#ifndef SB_EMU
+// Fast variant: the two horizontally adjacent source pixels of a bilinear footprint are 6 contiguous bytes;
+// fetch them with one (or two) aligned 8-byte loads instead of six byte loads.  Callers allocate the source
+// with SB_SRC_PAD spare bytes so that the second aligned word may straddle the end of the image.
+__device__ __forceinline__ void fetch_pair(const uint8_t *__restrict__ rowp, int x0, int x1, unsigned &p0, unsigned &p1)
+{
+    if (x1 == x0 + 1) {
+        const unsigned long long addr = (unsigned long long)(rowp + 3 * x0);
+        const unsigned o = (unsigned)addr & 7u;
+        const unsigned long long *q = reinterpret_cast<const unsigned long long *>(addr - o);
+        unsigned long long v = __ldg(q) >> (8 * o);
+        if (o > 2) v |= __ldg(q + 1) << (64 - 8 * o);
+        p0 = (unsigned)v & 0xffffffu;
+        p1 = (unsigned)(v >> 24) & 0xffffffu;
+    } else {  // the footprint straddles a reflected border
+        const uint8_t *a = rowp + 3 * x0, *b = rowp + 3 * x1;
+        p0 = (unsigned)__ldg(a) | ((unsigned)__ldg(a + 1) << 8) | ((unsigned)__ldg(a + 2) << 16);
+        p1 = (unsigned)__ldg(b) | ((unsigned)__ldg(b + 1) << 8) | ((unsigned)__ldg(b + 2) << 16);
+    }
+}
+
+__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const WarpJob *__restrict__ jobs)
+{
+    const WarpJob &j = jobs[blockIdx.z];
+    const int u = blockIdx.x * WARP_BX + threadIdx.x;
+    const int v = blockIdx.y * WARP_BY + threadIdx.y;
+    if (u >= j.dw || v >= j.dh) return;
+
+    float x, y;
+    project(j, u, v, x, y);
+    const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
+    const unsigned m = ((unsigned)nx < (unsigned)j.sw && (unsigned)ny < (unsigned)j.sh) ? 255u : 0u;
+    if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
+    if (!j.dst_rgb && !j.dst_rgbm) return;
+
+    const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
+    const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
+    const int fx = sx & 31, fy = sy & 31;
+    const int x0 = reflect(ix, j.sw), x1 = reflect(ix + 1, j.sw);
+    const int y0 = reflect(iy, j.sh), y1 = reflect(iy + 1, j.sh);
+    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32;
+    const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    unsigned a0, a1, b0, b1;
+    fetch_pair(j.src + (long long)y0 * j.spitch, x0, x1, a0, a1);
+    fetch_pair(j.src + (long long)y1 * j.spitch, x0, x1, b0, b1);
+    unsigned out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int acc = (int)((a0 >> (8 * c)) & 255u) * w00 + (int)((a1 >> (8 * c)) & 255u) * w01 +
+                        (int)((b0 >> (8 * c)) & 255u) * w10 + (int)((b1 >> (8 * c)) & 255u) * w11;
+        out[c] = (unsigned)sat_u8((acc + (1 << 14)) >> 15);
+    }
+    if (j.dst_rgb) {
+        uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + (long long)u * 3;
+        d[0] = (uint8_t)out[0];
+        d[1] = (uint8_t)out[1];
+        d[2] = (uint8_t)out[2];
+    }
+    if (j.dst_rgbm) j.dst_rgbm[(long long)v * j.rgbm_pitch + u] = out[0] | (out[1] << 8) | (out[2] << 16) | (m << 24);
+}
+#endif  // SB_EMU
+
 __global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch, const uint8_t *__restrict__ mask,
                             long long mask_pitch, uint32_t *__restrict__ dst, long long dst_pitch, int w, int h)
 {
@@ -96,6 +158,12 @@ int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaS
 {
     if (n_jobs <= 0 || max_w <= 0 || max_h <= 0) return SB_OK;
     dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), n_jobs);
+#ifndef SB_EMU
+    if (!use_simple_kernels()) {
+        launch(k_warp_wide, grid, block, 0, s, jobs_dev);
+        return launch_check("k_warp_wide");
+    }
+#endif
     launch(k_warp_gather, grid, block, 0, s, jobs_dev);
     return launch_check("k_warp_gather");
 }

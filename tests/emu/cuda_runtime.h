@@ -45,6 +45,9 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
     return cudaSuccess;
 }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -175,6 +175,62 @@ def test_drop_in_classes_equal_compositor(cuda_lib):
     assert np.array_equal(pano, p2) and np.array_equal(mask, m2)
 
 
+def test_pipelined_submit_wait(cuda_lib):
+    """The 2-deep pipelined end-to-end path returns exactly what the synchronous path returns, batch by batch."""
+    cfg = rigs.config("cfg2", 4)
+    cams = cfg["cameras"]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    c = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    batches = []
+    for b in range(6):
+        pinned = [c.pinned_empty((cfg["h"], cfg["w"], 3)) for _ in cams]
+        for i, p in enumerate(pinned):
+            p[...] = rigs.noise_image(cfg["h"], cfg["w"], 10 * b + i)
+        batches.append(pinned)
+    expected = [tuple(a.copy() for a in c.composite(b)) for b in batches]
+    _, _, pw, ph = c.roi
+    outs = [(c.pinned_empty((ph, pw, 3)), c.pinned_empty((ph, pw))) for _ in range(2)]
+    tickets = []
+    for k, b in enumerate(batches):
+        if k >= 2:
+            c.wait(tickets[k - 2])
+            assert np.array_equal(outs[k & 1][0], expected[k - 2][0]) and np.array_equal(outs[k & 1][1], expected[k - 2][1])
+        tickets.append(c.submit(b, *outs[k & 1]))
+    for k in (4, 5):
+        c.wait(tickets[k])
+        assert np.array_equal(outs[k & 1][0], expected[k][0]) and np.array_equal(outs[k & 1][1], expected[k][1])
+    c.close()
+
+
+def test_simple_and_fast_kernels_agree(cuda_lib):
+    """A/B inside one process is not possible (the variant is chosen once per process): run the other variant in
+    a child process and compare panoramas byte for byte."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, sys.argv[1]);"
+        "from stitching_b200 import Compositor, rigs;"
+        "cfg = rigs.config('cfg2', 4); cams = cfg['cameras'];"
+        "imgs = [rigs.noise_image(cfg['h'], cfg['w'], 300 + i) for i in range(len(cams))];"
+        "c = Compositor(cams, [(cfg['w'], cfg['h'])] * len(cams), cfg['warper'], cfg['blender'], cfg['strength']);"
+        "p, m = c.composite(imgs); np.savez(sys.argv[2], p=p, m=m)"
+    )
+    from conftest import ROOT
+
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for variant in ("simple", "fast"):
+            env = dict(os.environ)
+            env["SB_KERNELS"] = variant
+            out = os.path.join(d, variant + ".npz")
+            subprocess.check_call([sys.executable, "-c", code, ROOT, out], env=env)
+            z = np.load(out)
+            res[variant] = (z["p"], z["m"])
+    assert np.array_equal(res["simple"][0], res["fast"][0]) and np.array_equal(res["simple"][1], res["fast"][1])
+
+
 def test_full_size_properties(cuda_lib, oracle):
     """BASELINE cfg 2 at full size (8 x 4000x3000, spherical, multiband): size-independent properties."""
     cfg = rigs.config("cfg2", 1)

@@ -57,6 +57,29 @@ def test_compositor_matches_oracle(use_emu, oracle):
         c.close()
 
 
+def test_pipelined_submit_wait_equals_composite(use_emu):
+    cfg = rigs.config("cfg2", 25)
+    cams = cfg["cameras"]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    c = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    batches = [[rigs.noise_image(cfg["h"], cfg["w"], 10 * b + i) for i in range(len(cams))] for b in range(5)]
+    expected = [c.composite(b) for b in batches]
+    _, _, pw, ph = c.roi
+    outs = [(c.pinned_empty((ph, pw, 3)), c.pinned_empty((ph, pw))) for _ in range(2)]
+    tickets = []
+    for k, b in enumerate(batches):
+        if k >= 2:
+            c.wait(tickets[k - 2])
+            assert np.array_equal(outs[k & 1][0], expected[k - 2][0]) and np.array_equal(outs[k & 1][1], expected[k - 2][1])
+        tickets.append(c.submit(b, *outs[k & 1]))
+    for k in (3, 4):
+        c.wait(tickets[k])
+        assert np.array_equal(outs[k & 1][0], expected[k][0])
+    with pytest.raises(StitchingError):
+        c.wait(tickets[0])  # long gone
+    c.close()
+
+
 def test_band_clipping_matches_oracle(use_emu, oracle):
     """MultiBandBlender::prepare's band clipping -- product plan vs oracle restatement."""
     rng = np.random.default_rng(3)
