@@ -101,9 +101,7 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
     Scratch tmp(s);
     float *tab = nullptr;
     uint8_t *d_src = nullptr, *d_img = nullptr, *d_mask = nullptr;
-    WarpJob *d_job = nullptr;
     SB_TRY(tmp.get(&tab, (size_t)2 * w + 2 * h));
-    SB_TRY(tmp.get(&d_job, 1));
     std::vector<float> host_tab;
     WarpJob job;
     SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));
@@ -121,8 +119,7 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
         job.dst_mask = d_mask;
         job.mask_pitch = w;
     }
-    SB_CUDA(cudaMemcpyAsync(d_job, &job, sizeof job, cudaMemcpyHostToDevice, s));
-    SB_TRY(launch_warp(d_job, 1, w, h, s));
+    SB_TRY(launch_warp(&job, 1, s));
     if (dst_img) SB_CUDA(cudaMemcpy2DAsync(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));
     if (dst_mask) SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));

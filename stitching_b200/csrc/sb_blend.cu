@@ -190,147 +190,25 @@ __global__ void k_dt_cols(const FeedImage *__restrict__ imgs, int i, float sharp
     }
 }
 
-#ifndef SB_EMU
-// ---------------------------------------------------------------------------------------------------
-// Fast variant for levels l < nb: one thread per 2x2 quad of level l.  The four pixels of a quad share the
-// same 3x3 neighbourhood of the coarser level, so each pyrUp (of the image's G_{l+1} and of the collapsed
-// C_{l+1}) costs 9 loads per channel per quad instead of 9 per pixel; fine-level rows are read as pairs.
-// A block covers a 64x16 tile and first marks which fed images touch it (feed order is kept).
-// ---------------------------------------------------------------------------------------------------
-constexpr int CQ_BX = 32, CQ_BY = 8;
-
-__device__ __forceinline__ void load3x3(const int16_t *__restrict__ S, int pitch, int sw, int sh, int ci, int cj, int a[3][3])
-{
-    const int xp = ci > 0 ? ci - 1 : (sw > 1 ? 1 : 0), xn = ci + 1 < sw ? ci + 1 : sw - 1;
-    const int yp = cj > 0 ? cj - 1 : (sh > 1 ? 1 : 0), yn = cj + 1 < sh ? cj + 1 : sh - 1;
-    const int16_t *rp = S + (long long)yp * pitch, *rc = S + (long long)cj * pitch, *rn = S + (long long)yn * pitch;
-    a[0][0] = rp[xp]; a[0][1] = rp[ci]; a[0][2] = rp[xn];
-    a[1][0] = rc[xp]; a[1][1] = rc[ci]; a[1][2] = rc[xn];
-    a[2][0] = rn[xp]; a[2][1] = rn[ci]; a[2][2] = rn[xn];
-}
-// pyrUp of the 3x3 neighbourhood at the four pixels (2ci+dx, 2cj+dy): u[dy][dx]
-__device__ __forceinline__ void up_quad(const int a[3][3], int u[2][2])
-{
-    u[0][0] = (a[0][0] + a[0][2] + a[2][0] + a[2][2] + 6 * (a[0][1] + a[1][0] + a[1][2] + a[2][1]) + 36 * a[1][1] + 32) >> 6;
-    u[0][1] = (4 * (a[0][1] + a[0][2] + a[2][1] + a[2][2]) + 24 * (a[1][1] + a[1][2]) + 32) >> 6;
-    u[1][0] = (4 * (a[1][0] + a[1][2] + a[2][0] + a[2][2]) + 24 * (a[1][1] + a[2][1]) + 32) >> 6;
-    u[1][1] = (16 * (a[1][1] + a[1][2] + a[2][1] + a[2][2]) + 32) >> 6;
-}
-
-__global__ void __launch_bounds__(CQ_BX *CQ_BY)
-    k_collapse_quad(const FeedImage *__restrict__ imgs, int n, const PanoLevel *__restrict__ pano, int l, int nb, int lw, int lh,
-                    PanoOut out)
-{
-    __shared__ unsigned char cover[SB_MAX_IMAGES];
-    const int tile_x = blockIdx.x * (2 * CQ_BX), tile_y = blockIdx.y * (2 * CQ_BY);
-    for (int i = threadIdx.y * CQ_BX + threadIdx.x; i < n; i += CQ_BX * CQ_BY) {
-        const FeedImage &im = imgs[i];
-        const int ox = im.px >> l, oy = im.py >> l, w_l = im.pw >> l, h_l = im.ph >> l;
-        cover[i] = tile_x < ox + w_l && tile_x + 2 * CQ_BX > ox && tile_y < oy + h_l && tile_y + 2 * CQ_BY > oy;
-    }
-    __syncthreads();
-    const int x = tile_x + 2 * threadIdx.x, y = tile_y + 2 * threadIdx.y;  // top-left pixel of the quad (even, even)
-    if (x >= lw || y >= lh) return;
-    if (l == 0 && (x >= out.w || y >= out.h)) return;
-
-    int acc[2][2][3] = {};
-    float wsum[2][2] = {};
-    for (int i = 0; i < n; ++i) {
-        if (!cover[i]) continue;
-        const FeedImage &im = imgs[i];
-        const int X = x - (im.px >> l), Y = y - (im.py >> l);
-        const int w_l = im.pw >> l, h_l = im.ph >> l;  // even; the rect origin is even too, so a quad is in or out as a whole
-        if ((unsigned)X >= (unsigned)w_l || (unsigned)Y >= (unsigned)h_l) continue;
-        int g[2][2][3];
-        float wt[2][2];
-        if (l == 0) {
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) load_level0(im, X + dx, Y + dy, g[dy][dx], wt[dy][dx]);
-        } else {
-            const Level &L = im.lv[l];
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-                const long long o = (long long)(Y + dy) * L.pitch + X;  // X even: 4-byte aligned pairs
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const unsigned pr = *reinterpret_cast<const unsigned *>(L.g + c * L.plane + o);
-                    g[dy][0][c] = (short)(pr & 0xffffu);
-                    g[dy][1][c] = (short)(pr >> 16);
-                }
-                const float2 wp = *reinterpret_cast<const float2 *>(L.w + o);
-                wt[dy][0] = wp.x;
-                wt[dy][1] = wp.y;
-            }
-        }
-        const Level &U = im.lv[l + 1];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int a[3][3], u[2][2];
-            load3x3(U.g + c * U.plane, U.pitch, w_l >> 1, h_l >> 1, X >> 1, Y >> 1, a);
-            up_quad(a, u);
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx)
-                    acc[dy][dx][c] += f2s_wrap(fmul((float)sat_s16(g[dy][dx][c] - u[dy][dx]), wt[dy][dx]));
-        }
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) wsum[dy][dx] = fadd(wsum[dy][dx], wt[dy][dx]);
-    }
-
-    int v[2][2][3];
-    const PanoLevel &P = pano[l + 1];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        int a[3][3], u[2][2];
-        load3x3(P.c + c * P.plane, P.pitch, P.w_px, P.h_px, x >> 1, y >> 1, a);
-        up_quad(a, u);
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx)
-                v[dy][dx][c] = sat_s16(u[dy][dx] + f2s_wrap(fdiv((float)(short)acc[dy][dx][c], fadd(wsum[dy][dx], SB_WEIGHT_EPS))));
-    }
-    if (l > 0) {
-        const PanoLevel &Q = pano[l];
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            const long long o = (long long)(y + dy) * Q.pitch + x;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                *reinterpret_cast<unsigned *>(Q.c + c * Q.plane + o) =
-                    ((unsigned)v[dy][0][c] & 0xffffu) | ((unsigned)v[dy][1][c] << 16);
-        }
-    } else {
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                if (x + dx >= out.w || y + dy >= out.h) continue;
-                const bool on = wsum[dy][dx] > SB_WEIGHT_EPS;
-                store_final(out, x + dx, y + dy, v[dy][dx], on, on ? 255u : 0u);
-            }
-    }
-}
-#endif  // SB_EMU
 
 }  // namespace
 
-int launch_collapse(const FeedImage *imgs_dev, int n, const PanoLevel *pano_dev, int l, int nb, int lw, int lh, PanoOut out,
-                    cudaStream_t s)
+int launch_collapse_fast(const ColDesc *col, int n, const PanoLevel &up, const PanoLevel &cur, int l, int lw, int lh, PanoOut out,
+                         cudaStream_t s);  // sb_collapse_fast.cu
+
+int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
+                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s)
 {
     int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
     if (gw <= 0 || gh <= 0) return SB_OK;
 #ifndef SB_EMU
-    if (!use_simple_kernels() && l < nb) {
-        dim3 block(CQ_BX, CQ_BY), grid(div_up(gw, 2 * CQ_BX), div_up(gh, 2 * CQ_BY));
-        launch(k_collapse_quad, grid, block, 0, s, imgs_dev, n, pano_dev, l, nb, lw, lh, out);
-        return launch_check("k_collapse_quad");
-    }
+    // the fast kernel handles levels below the top and reads level 0 through the packed RGBM layout
+    bool packed = true;
+    for (int i = 0; i < n; ++i) packed = packed && imgs_host[i].rgbm != nullptr;
+    if (!use_simple_kernels() && l < nb && (l > 0 || packed))
+        return launch_collapse_fast(col, n, pano_host[l + 1], pano_host[l], l, lw, lh, out, s);
+#else
+    (void)imgs_host; (void)col; (void)pano_host;
 #endif
     dim3 block(CL_BX, CL_BY), grid(div_up(gw, CL_BX), div_up(gh, CL_BY));
     launch(k_collapse_gather, grid, block, 0, s, imgs_dev, n, pano_dev, l, nb, lw, lh, out);

@@ -26,7 +26,7 @@ struct sb_compositor {
     std::vector<int> src_w, src_h;
     std::vector<Rect> rects;           // warped rects (pano-absolute)
     std::vector<WarpJob> jobs;         // host copy
-    WarpJob *jobs_dev = nullptr;
+    std::vector<WarpJob> jobs2;        // the same jobs reading the second source buffer set (pipelined path)
     std::vector<uint8_t *> src_dev;    // u8x3 sources
     std::vector<uint32_t *> rgbm_dev;  // warped, packed
     std::vector<float *> tab_dev;
@@ -43,7 +43,6 @@ struct sb_compositor {
     // pipelined submit / wait: a second set of source + output buffers, copy streams, per-slot events
     bool pipe_ready = false;
     std::vector<uint8_t *> src_dev2;
-    WarpJob *jobs_dev2 = nullptr;
     PanoOut out2;
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
@@ -59,14 +58,12 @@ static void compositor_free(sb_compositor *c)
     for (auto p : c->rgbm_dev) dev_free(p, s);
     for (auto p : c->tab_dev) dev_free(p, s);
     for (auto p : c->usermask_dev) dev_free(p, s);
-    dev_free(c->jobs_dev, s);
     dev_free(c->out.rgb, s);
     dev_free(c->out.mask, s);
     dev_free(c->flush_buf, s);
     if (c->h2d) (void)cudaStreamSynchronize(c->h2d);
     if (c->d2h) (void)cudaStreamSynchronize(c->d2h);
     for (auto p : c->src_dev2) dev_free(p, s);
-    dev_free(c->jobs_dev2, s);
     if (c->pipe_ready) {
         dev_free(c->out2.rgb, s);
         dev_free(c->out2.mask, s);
@@ -138,8 +135,6 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
         c->jobs[i].rgbm_pitch = rect[2];
         c->warp_bytes += 3.0 * c->src_w[i] * c->src_h[i] + 4.0 * rect[2] * rect[3];
     }
-    SB_TRY(dev_alloc((void **)&c->jobs_dev, sizeof(WarpJob) * n, s));
-    SB_CUDA(cudaMemcpyAsync(c->jobs_dev, c->jobs.data(), sizeof(WarpJob) * n, cudaMemcpyHostToDevice, s));
 
     // Blender.prepare (blender.py:23-38)
     const Rect roi = result_roi(corners.data(), sizes.data(), n);
@@ -189,7 +184,7 @@ static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
         return SB_OK;
     };
     SB_TRY(mark("start"));
-    SB_TRY(launch_warp(slot ? c->jobs_dev2 : c->jobs_dev, c->n, c->max_w, c->max_h, s));
+    SB_TRY(launch_warp(slot ? c->jobs2.data() : c->jobs.data(), c->n, s));
     SB_TRY(mark("warp"));
     SB_TRY(c->plan.run(slot ? c->out2 : c->out, s, events ? std::function<int(const std::string &)>(mark) : nullptr));
     return SB_OK;
@@ -201,14 +196,11 @@ static int compositor_pipe_init(sb_compositor *c)
     if (c->pipe_ready) return SB_OK;
     cudaStream_t s = c->stream;
     c->src_dev2.assign(c->n, nullptr);
-    std::vector<WarpJob> jobs2 = c->jobs;
+    c->jobs2 = c->jobs;
     for (int i = 0; i < c->n; ++i) {
         SB_TRY(dev_alloc((void **)&c->src_dev2[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
-        jobs2[i].src = c->src_dev2[i];
+        c->jobs2[i].src = c->src_dev2[i];
     }
-    SB_TRY(dev_alloc((void **)&c->jobs_dev2, sizeof(WarpJob) * c->n, s));
-    SB_CUDA(cudaMemcpyAsync(c->jobs_dev2, jobs2.data(), sizeof(WarpJob) * c->n, cudaMemcpyHostToDevice, s));
-    SB_CUDA(cudaStreamSynchronize(s));  // jobs2 is a local
     c->out2 = c->out;
     c->out2.rgb = nullptr;
     c->out2.mask = nullptr;

@@ -99,6 +99,30 @@ struct FeedImage {
     Level lv[SB_MAX_BANDS + 1];  // lv[0] unused
 };
 
+// Compact per-(image, level) descriptors for the fast kernels: everything a kernel needs for one level in a
+// few 16-byte words, prebuilt on the host (the generic FeedImage stays the source of truth for the simple ones).
+struct alignas(16) ColDesc {       // collapse of level l
+    int ox, oy, w_l, h_l;          // padded rect of the image at level l, pano level coordinates
+    const uint32_t *rgbm;          // level 0: packed fed image
+    const int16_t *g;              // level l >= 1: colour planes
+    const float *w;                //              weights
+    const int16_t *ug;             // level l+1 colour planes (null at the top level)
+    int rgbm_pitch, iw, ih, left;  // level 0: image size and origin inside the padded rect
+    int top, pitch, plane, upitch; // level l / l+1 pitches and plane strides, in elements
+    int uplane, pad0, pad1, pad2;
+};
+struct alignas(16) PyrDesc {       // pyrDown of level l -> l+1
+    int sw, sh, dpitch, dplane;    // source level size; destination pitch / plane stride (elements)
+    const uint32_t *rgbm;          // level 0 source
+    const int16_t *sg;             // level >= 1 source planes
+    const float *swt;
+    int16_t *dg;
+    float *dwt;
+    int rgbm_pitch, iw;
+    int ih, left, top, spitch;
+    int splane, pad0, pad1, pad2;
+};
+
 struct PanoLevel {
     int16_t *c;  // collapsed planar int16 x3 [3][h][pitch]
     int w_px, h_px, pitch;
@@ -115,17 +139,20 @@ struct PanoOut {
 // ---------------------------------------------------------------------------------------------
 // kernel launchers
 // ---------------------------------------------------------------------------------------------
-int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaStream_t s);
+// jobs are HOST structs: they are passed by value in the kernel parameter block, SB_WARP_BATCH images per launch
+#define SB_WARP_BATCH 32
+int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s);
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)
-int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, int first, int count, int l, int max_w, int max_h,
-                   cudaStream_t s);
+// `pyr` / `col`: the compact descriptors of level l for the same images (device pointers, `count` / `n` entries)
+int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const PyrDesc *pyr, int first, int count, int l,
+                   int max_w, int max_h, cudaStream_t s);
 // SB_KERNELS=simple selects the one-thread-per-pixel gather kernels everywhere (debugging / A-B parity)
 bool use_simple_kernels();
 // multiband: accumulate + normalise + collapse level l (top-down); at l == 0 writes the final outputs
-int launch_collapse(const FeedImage *imgs_dev, int n, const PanoLevel *pano_dev, int l, int nb, int lw, int lh,
-                    PanoOut out, cudaStream_t s);
+int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
+                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s);
 // feather: distance-transform weight maps, then one fused accumulate/normalise pass; NO blender
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);

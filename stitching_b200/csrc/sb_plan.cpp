@@ -176,6 +176,8 @@ int BlendPlan::allocate(cudaStream_t s)
     }
     const size_t imgs_off = carve(sizeof(FeedImage) * (size_t)std::max(n, 1));
     const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
+    const size_t col_off = carve(sizeof(ColDesc) * (size_t)std::max(n, 1) * (nb + 1));
+    const size_t pyr_off = carve(sizeof(PyrDesc) * (size_t)std::max(n, 1) * (nb + 1));
     arena_bytes_ = off;
     SB_TRY(dev_alloc(&arena_, arena_bytes_, s));
     char *base = (char *)arena_;
@@ -204,6 +206,66 @@ int BlendPlan::allocate(cudaStream_t s)
     }
     imgs_dev = (FeedImage *)(base + imgs_off);
     pano_dev = (PanoLevel *)(base + panod_off);
+    col_dev = (ColDesc *)(base + col_off);
+    pyr_dev = (PyrDesc *)(base + pyr_off);
+    // compact per-(level, image) descriptors for the fast kernels: [l * n + i]
+    std::vector<ColDesc> col((size_t)n * (nb + 1));
+    std::vector<PyrDesc> pyr((size_t)n * (nb + 1));
+    if (kind == SB_BLEND_MULTIBAND) {
+        for (int l = 0; l <= nb; ++l)
+            for (int i = 0; i < n; ++i) {
+                const FeedImage &im = imgs[i];
+                ColDesc &c = col[(size_t)l * n + i];
+                std::memset(&c, 0, sizeof c);
+                c.ox = im.px >> l;
+                c.oy = im.py >> l;
+                c.w_l = im.pw >> l;
+                c.h_l = im.ph >> l;
+                c.rgbm = im.rgbm;
+                c.rgbm_pitch = (int)im.rgbm_pitch;
+                c.iw = im.w;
+                c.ih = im.h;
+                c.left = im.left;
+                c.top = im.top;
+                if (l >= 1) {
+                    c.g = im.lv[l].g;
+                    c.w = im.lv[l].w;
+                    c.pitch = im.lv[l].pitch;
+                    c.plane = (int)im.lv[l].plane;
+                }
+                if (l < nb) {
+                    c.ug = im.lv[l + 1].g;
+                    c.upitch = im.lv[l + 1].pitch;
+                    c.uplane = (int)im.lv[l + 1].plane;
+                }
+                PyrDesc &p = pyr[(size_t)l * n + i];
+                std::memset(&p, 0, sizeof p);
+                if (l < nb) {
+                    p.sw = im.pw >> l;
+                    p.sh = im.ph >> l;
+                    p.rgbm = im.rgbm;
+                    p.rgbm_pitch = (int)im.rgbm_pitch;
+                    p.iw = im.w;
+                    p.ih = im.h;
+                    p.left = im.left;
+                    p.top = im.top;
+                    if (l >= 1) {
+                        p.sg = im.lv[l].g;
+                        p.swt = im.lv[l].w;
+                        p.spitch = im.lv[l].pitch;
+                        p.splane = (int)im.lv[l].plane;
+                    }
+                    p.dg = im.lv[l + 1].g;
+                    p.dwt = im.lv[l + 1].w;
+                    p.dpitch = im.lv[l + 1].pitch;
+                    p.dplane = (int)im.lv[l + 1].plane;
+                }
+            }
+        if (n) {
+            SB_CUDA(cudaMemcpyAsync(col_dev, col.data(), sizeof(ColDesc) * col.size(), cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaMemcpyAsync(pyr_dev, pyr.data(), sizeof(PyrDesc) * pyr.size(), cudaMemcpyHostToDevice, s));
+        }
+    }
     if (n) SB_CUDA(cudaMemcpyAsync(imgs_dev, imgs.data(), sizeof(FeedImage) * n, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(pano_dev, pano, sizeof pano, cudaMemcpyHostToDevice, s));
     // the descriptor copies read pageable host memory owned by this object: make them complete now
@@ -218,6 +280,8 @@ void BlendPlan::release(cudaStream_t s)
     arena_bytes_ = 0;
     imgs_dev = nullptr;
     pano_dev = nullptr;
+    col_dev = nullptr;
+    pyr_dev = nullptr;
 }
 
 int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(const std::string &)> &mark)
@@ -231,11 +295,11 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
                 mw = std::max(mw, im.pw >> (l + 1));
                 mh = std::max(mh, im.ph >> (l + 1));
             }
-            SB_TRY(launch_pyrdown(imgs_dev, imgs.data(), 0, n, l, mw, mh, s));
+            SB_TRY(launch_pyrdown(imgs_dev, imgs.data(), pyr_dev + (size_t)l * n, 0, n, l, mw, mh, s));
             SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
         for (int l = nb; l >= 0; --l) {
-            SB_TRY(launch_collapse(imgs_dev, n, pano_dev, l, nb, wp >> l, hp >> l, out, s));
+            SB_TRY(launch_collapse(imgs_dev, imgs.data(), col_dev + (size_t)l * n, n, pano_dev, pano, l, nb, wp >> l, hp >> l, out, s));
             SB_TRY(note("collapse_l" + std::to_string(l)));
         }
     } else {

@@ -39,6 +39,8 @@ public:
     PanoLevel pano[SB_MAX_BANDS + 1];
     FeedImage *imgs_dev = nullptr;
     PanoLevel *pano_dev = nullptr;
+    ColDesc *col_dev = nullptr;  // [(nb+1)][n] compact descriptors for the fast kernels
+    PyrDesc *pyr_dev = nullptr;
 
     // geometry only (no device work): usable without a GPU for tests of the host logic
     int set_geometry(int kind, int num_bands_requested, float sharpness, const Rect &roi);

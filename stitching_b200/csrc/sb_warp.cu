@@ -12,6 +12,9 @@
 //   bilinear    sx = cvRound(x*32) (half-even, INT_MIN when unrepresentable), ix = sat16(sx>>5),
 //               fx = sx&31; 4 taps with 15-bit weights (32-fy)(32-fx)*32 ..., (sum + 2^14) >> 15
 //   mask        255 iff 0 <= sat16(cvRound(x)) < W and 0 <= sat16(cvRound(y)) < H
+//
+// The job descriptors travel BY VALUE in the kernel parameter block (constant bank, up to SB_WARP_BATCH images
+// per launch): the profile of the first version showed 20 of 31 loads per pixel re-reading them from global memory.
 #include "sb_device.cuh"
 #include "sb_launch.h"
 
@@ -20,6 +23,10 @@ namespace sb {
 namespace {
 
 constexpr int WARP_BX = 32, WARP_BY = 8;
+
+struct WarpBatch {
+    WarpJob j[SB_WARP_BATCH];
+};
 
 __device__ __forceinline__ void project(const WarpJob &j, int u, int v, float &x, float &y)
 {
@@ -38,10 +45,21 @@ __device__ __forceinline__ void project(const WarpJob &j, int u, int v, float &x
     }
 }
 
-// simple variant: one thread per output pixel, direct (L1/L2-cached) global gathers
-__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const WarpJob *__restrict__ jobs)
+__device__ __forceinline__ void store_pixel(const WarpJob &j, int u, int v, unsigned r, unsigned g, unsigned b, unsigned m)
 {
-    const WarpJob &j = jobs[blockIdx.z];
+    if (j.dst_rgb) {
+        uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + 3 * u;
+        d[0] = (uint8_t)r;
+        d[1] = (uint8_t)g;
+        d[2] = (uint8_t)b;
+    }
+    if (j.dst_rgbm) j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
+}
+
+// simple variant: one thread per output pixel, byte gathers
+__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const __grid_constant__ WarpBatch B)
+{
+    const WarpJob &j = B.j[blockIdx.z];
     const int u = blockIdx.x * WARP_BX + threadIdx.x;
     const int v = blockIdx.y * WARP_BY + threadIdx.y;
     if (u >= j.dw || v >= j.dh) return;
@@ -70,39 +88,52 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const WarpJob 
                   __ldg(r1 + x1 * 3 + c) * w11;
         out[c] = (unsigned)sat_u8((acc + (1 << 14)) >> 15);
     }
-    if (j.dst_rgb) {
-        uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + (long long)u * 3;
-        d[0] = (uint8_t)out[0];
-        d[1] = (uint8_t)out[1];
-        d[2] = (uint8_t)out[2];
-    }
-    if (j.dst_rgbm) j.dst_rgbm[(long long)v * j.rgbm_pitch + u] = out[0] | (out[1] << 8) | (out[2] << 16) | (m << 24);
+    store_pixel(j, u, v, out[0], out[1], out[2], m);
 }
 
 #ifndef SB_EMU
 // Fast variant: the two horizontally adjacent source pixels of a bilinear footprint are 6 contiguous bytes;
 // fetch them with one (or two) aligned 8-byte loads instead of six byte loads.  Callers allocate the source
 // with SB_SRC_PAD spare bytes so that the second aligned word may straddle the end of the image.
-__device__ __forceinline__ void fetch_pair(const uint8_t *__restrict__ rowp, int x0, int x1, unsigned &p0, unsigned &p1)
+__device__ __forceinline__ void fetch_pair(const uint8_t *__restrict__ src, unsigned row_off, int x0, int x1, unsigned &p0, unsigned &p1)
 {
     if (x1 == x0 + 1) {
-        const unsigned long long addr = (unsigned long long)(rowp + 3 * x0);
+        const unsigned long long addr = (unsigned long long)src + row_off + 3u * (unsigned)x0;
         const unsigned o = (unsigned)addr & 7u;
-        const unsigned long long *q = reinterpret_cast<const unsigned long long *>(addr - o);
-        unsigned long long v = __ldg(q) >> (8 * o);
-        if (o > 2) v |= __ldg(q + 1) << (64 - 8 * o);
-        p0 = (unsigned)v & 0xffffffu;
-        p1 = (unsigned)(v >> 24) & 0xffffffu;
+        const uint2 *q = reinterpret_cast<const uint2 *>(addr - o);
+        const uint2 lo = __ldg(q);
+        // bytes o .. o+5 of the 16-byte window (lo, hi): shift the 32-bit words with funnel shifts
+        const unsigned sh = 8u * (o & 3u);
+        unsigned w0 = lo.x, w1 = lo.y, w2 = 0u;
+        if (o > 2) {
+            const uint2 hi = __ldg(q + 1);
+            w2 = hi.x;
+            if (o >= 4) {
+                w0 = lo.y;
+                w1 = hi.x;
+                w2 = hi.y;
+            }
+        }
+        const unsigned a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh);  // bytes 0-3 and 4-7 from the start
+        p0 = a & 0xffffffu;
+        p1 = __funnelshift_r(a, b, 24) & 0xffffffu;
     } else {  // the footprint straddles a reflected border
-        const uint8_t *a = rowp + 3 * x0, *b = rowp + 3 * x1;
+        const uint8_t *a = src + row_off + 3 * x0, *b = src + row_off + 3 * x1;
         p0 = (unsigned)__ldg(a) | ((unsigned)__ldg(a + 1) << 8) | ((unsigned)__ldg(a + 2) << 16);
         p1 = (unsigned)__ldg(b) | ((unsigned)__ldg(b + 1) << 8) | ((unsigned)__ldg(b + 2) << 16);
     }
 }
 
-__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const WarpJob *__restrict__ jobs)
+// reflect() with a branch-free single-bounce path; the modulo form only when the coordinate is far outside
+__device__ __forceinline__ int reflect_near(int p, int n)
 {
-    const WarpJob &j = jobs[blockIdx.z];
+    const int q = p < 0 ? -p - 1 : (p >= n ? 2 * n - 1 - p : p);
+    return (unsigned)q < (unsigned)n ? q : reflect(p, n);
+}
+
+__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_constant__ WarpBatch B)
+{
+    const WarpJob &j = B.j[blockIdx.z];
     const int u = blockIdx.x * WARP_BX + threadIdx.x;
     const int v = blockIdx.y * WARP_BY + threadIdx.y;
     if (u >= j.dw || v >= j.dh) return;
@@ -117,27 +148,24 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const WarpJob *_
     const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
     const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
     const int fx = sx & 31, fy = sy & 31;
-    const int x0 = reflect(ix, j.sw), x1 = reflect(ix + 1, j.sw);
-    const int y0 = reflect(iy, j.sh), y1 = reflect(iy + 1, j.sh);
-    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32;
-    const int w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    const int x0 = reflect_near(ix, j.sw), x1 = reflect_near(ix + 1, j.sw);
+    const int y0 = reflect_near(iy, j.sh), y1 = reflect_near(iy + 1, j.sh);
     unsigned a0, a1, b0, b1;
-    fetch_pair(j.src + (long long)y0 * j.spitch, x0, x1, a0, a1);
-    fetch_pair(j.src + (long long)y1 * j.spitch, x0, x1, b0, b1);
-    unsigned out[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int acc = (int)((a0 >> (8 * c)) & 255u) * w00 + (int)((a1 >> (8 * c)) & 255u) * w01 +
-                        (int)((b0 >> (8 * c)) & 255u) * w10 + (int)((b1 >> (8 * c)) & 255u) * w11;
-        out[c] = (unsigned)sat_u8((acc + (1 << 14)) >> 15);
-    }
-    if (j.dst_rgb) {
-        uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + (long long)u * 3;
-        d[0] = (uint8_t)out[0];
-        d[1] = (uint8_t)out[1];
-        d[2] = (uint8_t)out[2];
-    }
-    if (j.dst_rgbm) j.dst_rgbm[(long long)v * j.rgbm_pitch + u] = out[0] | (out[1] << 8) | (out[2] << 16) | (m << 24);
+    const unsigned pitch = (unsigned)j.spitch;  // coordinates are int16-saturated: offsets stay below 2^32
+    fetch_pair(j.src, (unsigned)y0 * pitch, x0, x1, a0, a1);
+    fetch_pair(j.src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    // (sum_k w_k p_k + 2^14) >> 15 with w = 32 (32-fy|fy)(32-fx|fx), evaluated as two exact lerps:
+    //   h = (32-fx) a + fx b  (<= 8160),  s = (32-fy) h0 + fy h1  (<= 261120),  out = (s + 512) >> 10
+    // red and blue share a register as two 16-bit lanes through the horizontal lerp
+    const unsigned M = 0x00ff00ffu;
+    const unsigned gx = (unsigned)fx, hx = 32u - gx;
+    const unsigned h0rb = (a0 & M) * hx + (a1 & M) * gx, h1rb = (b0 & M) * hx + (b1 & M) * gx;
+    const unsigned h0g = ((a0 >> 8) & 255u) * hx + ((a1 >> 8) & 255u) * gx, h1g = ((b0 >> 8) & 255u) * hx + ((b1 >> 8) & 255u) * gx;
+    const unsigned gy = (unsigned)fy, hy = 32u - gy;
+    const unsigned r = ((h0rb & 0xffffu) * hy + (h1rb & 0xffffu) * gy + 512u) >> 10;
+    const unsigned b = ((h0rb >> 16) * hy + (h1rb >> 16) * gy + 512u) >> 10;
+    const unsigned g = (h0g * hy + h1g * gy + 512u) >> 10;
+    store_pixel(j, u, v, r, g, b, m);
 }
 #endif  // SB_EMU
 
@@ -154,18 +182,31 @@ __global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch
 
 }  // namespace
 
-int launch_warp(const WarpJob *jobs_dev, int n_jobs, int max_w, int max_h, cudaStream_t s)
+int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
 {
-    if (n_jobs <= 0 || max_w <= 0 || max_h <= 0) return SB_OK;
-    dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), n_jobs);
+    for (int first = 0; first < n_jobs; first += SB_WARP_BATCH) {
+        const int cnt = n_jobs - first < SB_WARP_BATCH ? n_jobs - first : SB_WARP_BATCH;
+        WarpBatch B;
+        int max_w = 0, max_h = 0;
+        for (int i = 0; i < cnt; ++i) {
+            B.j[i] = jobs_host[first + i];
+            max_w = max_w > B.j[i].dw ? max_w : B.j[i].dw;
+            max_h = max_h > B.j[i].dh ? max_h : B.j[i].dh;
+        }
+        for (int i = cnt; i < SB_WARP_BATCH; ++i) B.j[i] = B.j[0];
+        if (max_w <= 0 || max_h <= 0) continue;
+        dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), cnt);
 #ifndef SB_EMU
-    if (!use_simple_kernels()) {
-        launch(k_warp_wide, grid, block, 0, s, jobs_dev);
-        return launch_check("k_warp_wide");
-    }
+        if (!use_simple_kernels()) {
+            launch(k_warp_wide, grid, block, 0, s, B);
+            SB_TRY(launch_check("k_warp_wide"));
+            continue;
+        }
 #endif
-    launch(k_warp_gather, grid, block, 0, s, jobs_dev);
-    return launch_check("k_warp_gather");
+        launch(k_warp_gather, grid, block, 0, s, B);
+        SB_TRY(launch_check("k_warp_gather"));
+    }
+    return SB_OK;
 }
 
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,

@@ -59,6 +59,7 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 struct emuIdx { unsigned x, y, z; };
 extern thread_local emuIdx threadIdx, blockIdx, blockDim, gridDim;
 template <typename T> static inline T __ldg(const T *p) { return *p; }
