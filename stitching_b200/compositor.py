@@ -63,6 +63,17 @@ class Compositor:
             _lib.check(L.sb_compositor_upload(self._c, i, img.ctypes.data_as(C.c_void_p), img.strides[0], int(pinned)),
                        "sb_compositor_upload")
 
+    def set_mask(self, i, mask):
+        """Blend mask of image i in warped coordinates (uint8 h' x w', e.g. SeamFinder.resize's output); replaces the
+        warped validity mask as blend weight from the next run on."""
+        if hasattr(mask, "get") and not isinstance(mask, np.ndarray):
+            mask = mask.get()
+        mask = np.ascontiguousarray(mask, np.uint8)
+        if mask.shape != (self.rects[i][3], self.rects[i][2]):
+            raise StitchingError(f"mask {i}: expected {self.rects[i][3]}x{self.rects[i][2]}")
+        _lib.check(_lib.lib().sb_compositor_set_mask(self._c, i, mask.ctypes.data_as(C.c_void_p), mask.strides[0]),
+                   "sb_compositor_set_mask")
+
     def run(self):
         _lib.check(_lib.lib().sb_compositor_run(self._c), "sb_compositor_run")
 

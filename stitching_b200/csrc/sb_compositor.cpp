@@ -47,6 +47,11 @@ struct sb_compositor {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
     unsigned long long submitted = 0;
+#ifndef SB_EMU
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // one captured step per buffer slot
+#endif
+    unsigned graph_kernels = 0;
+    std::vector<cudaEvent_t> tev;  // step start / end events of sb_compositor_time
 };
 
 static void compositor_free(sb_compositor *c)
@@ -75,6 +80,11 @@ static void compositor_free(sb_compositor *c)
     }
     if (c->h2d) (void)cudaStreamDestroy(c->h2d);
     if (c->d2h) (void)cudaStreamDestroy(c->d2h);
+#ifndef SB_EMU
+    for (auto &g : c->graph_exec)
+        if (g) (void)cudaGraphExecDestroy(g);
+#endif
+    for (auto &e : c->tev) (void)cudaEventDestroy(e);
     c->plan.release(s);
     for (auto &e : c->ev)
         if (e) (void)cudaEventDestroy(e);
@@ -165,7 +175,45 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
     return SB_OK;
 }
 
+static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot);
+
+// One step = one CUDA graph launch: the plan is static, so the ~2(nb+1) kernel launches are captured once per
+// buffer slot and replayed (the coarse levels are launch-latency bound).  SB_GRAPH=0 launches them one by one.
 static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
+{
+#ifndef SB_EMU
+    static const bool use_graph = [] {
+        const char *e = getenv("SB_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    if (!events && use_graph) {
+        cudaStream_t s = c->stream;
+        if (!c->graph_exec[slot]) {
+            const unsigned long long before = sb_launch_count();
+            SB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = compositor_enqueue_kernels(c, false, slot);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(s, &g);
+            c->graph_kernels = (unsigned)(sb_launch_count() - before);
+            adjust_launch_count(-(long long)c->graph_kernels);  // captured, not executed
+            if (rc != SB_OK) {
+                if (g) (void)cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            const cudaError_t ei = cudaGraphInstantiate(&c->graph_exec[slot], g, 0);
+            (void)cudaGraphDestroy(g);
+            if (ei != cudaSuccess) return cuda_fail(ei, "cudaGraphInstantiate", __FILE__, __LINE__);
+        }
+        SB_CUDA(cudaGraphLaunch(c->graph_exec[slot], s));
+        adjust_launch_count((long long)c->graph_kernels);
+        return SB_OK;
+    }
+#endif
+    return compositor_enqueue_kernels(c, events, slot);
+}
+
+static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
 {
     cudaStream_t s = c->stream;
     size_t k = 0;
@@ -292,14 +340,30 @@ int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pit
 
 int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t pitch)
 {
-    (void)mask;
-    (void)pitch;
-    if (!c || i < 0 || i >= c->n) {
+    if (!c || i < 0 || i >= c->n || !mask || pitch < (size_t)c->rects[i].w) {
         set_error("sb_compositor_set_mask: invalid argument");
         return SB_ERR_INVALID;
     }
-    set_error("sb_compositor_set_mask: mask_mode 1 is not implemented yet");
-    return SB_ERR_INVALID;
+    // the blend mask of image i in warped coordinates (what stitcher.py:223-239 hands to Blender.feed); it replaces
+    // the validity mask in the weight byte of the packed warped image from the next run on
+    const int w = c->rects[i].w, h = c->rects[i].h;
+    if (!c->usermask_dev[i]) SB_TRY(dev_alloc((void **)&c->usermask_dev[i], (size_t)w * h, c->stream));
+    SB_CUDA(cudaMemcpy2DAsync(c->usermask_dev[i], w, mask, pitch, w, h, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    c->jobs[i].blend_mask = c->usermask_dev[i];
+    c->jobs[i].blend_mask_pitch = w;
+    if (!c->jobs2.empty()) {
+        c->jobs2[i].blend_mask = c->usermask_dev[i];
+        c->jobs2[i].blend_mask_pitch = w;
+    }
+#ifndef SB_EMU
+    for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture
+        if (g) {
+            (void)cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+#endif
+    return SB_OK;
 }
 
 int sb_compositor_run(sb_compositor *c)
@@ -421,6 +485,34 @@ int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_tota
         SB_TRY(dev_alloc(&c->flush_buf, c->flush_bytes, s));
     }
     float total = 0.f;
+    // pass 1: whole steps exactly as sb_compositor_run issues them (one graph launch), one event pair per step
+    // (the host enqueues ahead of the device: no host synchronisation between steps; with flush_l2 the flush
+    // kernel runs between a step's end event and the next step's start event)
+    while ((int)c->tev.size() < 2 * iters) {
+        cudaEvent_t e;
+        SB_CUDA(cudaEventCreate(&e));
+        c->tev.push_back(e);
+    }
+    for (int it = 0; it < iters; ++it) {
+        if (flush_l2) SB_TRY(launch_flush_l2(c->flush_buf, c->flush_bytes, s));
+        if (flush_l2 || it == 0) SB_CUDA(cudaEventRecord(c->tev[2 * it], s));
+        SB_TRY(compositor_enqueue(c, false));
+        if (flush_l2 || it == iters - 1) SB_CUDA(cudaEventRecord(c->tev[2 * it + 1], s));
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (flush_l2) {
+        for (int it = 0; it < iters; ++it) {
+            float t = 0;
+            SB_CUDA(cudaEventElapsedTime(&t, c->tev[2 * it], c->tev[2 * it + 1]));
+            total += t;
+        }
+    } else {
+        SB_CUDA(cudaEventElapsedTime(&total, c->tev[0], c->tev[2 * (iters - 1) + 1]));
+    }
+    *ms_total = total;
+    // pass 2: per-kernel breakdown (individual launches with an event after each), a few iterations
+    iters = iters < 5 ? iters : 5;
+    total = 0.f;
     c->launch_ms.clear();
     for (int it = 0; it < iters; ++it) {
         if (flush_l2) SB_TRY(launch_flush_l2(c->flush_buf, c->flush_bytes, s));
@@ -438,7 +530,6 @@ int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_tota
         total += t;
     }
     for (float &v : c->launch_ms) v /= (float)iters;
-    *ms_total = total;
     return SB_OK;
 }
 

@@ -36,6 +36,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void adjust_launch_count(long long delta) { g_launches.fetch_add((unsigned long long)delta, std::memory_order_relaxed); }
 int sm_count() { return g_sm; }
 cudaStream_t default_stream() { return g_stream; }
 

@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int ensure_device();  // SB_OK when sb_init succeeded (or lazily selects device 0)
 int sm_count();
 void count_launch(unsigned n = 1);
+void adjust_launch_count(long long delta);  // graph capture records launches that do not execute; replays execute them
 cudaStream_t default_stream();
 
 // stream-ordered device allocation (cudaMallocAsync pool with a high release threshold)
@@ -67,6 +68,8 @@ struct WarpJob {
     long long mask_pitch;
     uint32_t *dst_rgbm;  // packed r | g<<8 | b<<16 | mask<<24, or null
     long long rgbm_pitch;  // elements
+    const uint8_t *blend_mask;  // optional blend mask (seam mask AND validity, stitcher.py:223-239) stored in the
+    long long blend_mask_pitch; // mask byte of dst_rgbm instead of the validity mask
     int dw, dh;
     const float *colX, *colZ, *rowA, *rowY;
     float k[9];

@@ -53,7 +53,10 @@ __device__ __forceinline__ void store_pixel(const WarpJob &j, int u, int v, unsi
         d[1] = (uint8_t)g;
         d[2] = (uint8_t)b;
     }
-    if (j.dst_rgbm) j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
+    if (j.dst_rgbm) {
+        if (j.blend_mask) m = j.blend_mask[(long long)v * j.blend_mask_pitch + u];
+        j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
+    }
 }
 
 // simple variant: one thread per output pixel, byte gathers

@@ -145,7 +145,19 @@ class OracleWarper:
         return [r[0:2] for r in rois], [r[2:4] for r in rois]
 
 
-def oracle_composite(O, cfg, cams, imgs):
+def ramp_masks(masks, ramp=64):
+    """Mask set B of SURVEY 8(d): the validity mask with a linear gray ramp toward the left/right neighbours
+    (mimics SeamFinder.resize's 256-level output)."""
+    out = []
+    for m in masks:
+        h, w = m.shape
+        x = np.arange(w)
+        r = np.minimum(np.minimum(x, w - 1 - x) * 255 // max(ramp, 1), 255).astype(np.uint8)
+        out.append(np.minimum(m, r[None, :]))
+    return out
+
+
+def oracle_composite(O, cfg, cams, imgs, mask_fn=None):
     """Warp + blend on the CPU oracle the way stitcher.py:178-189, 241-259 drive the reference classes."""
     w = OracleWarper(cfg["warper"])
     w.set_scale(cams)
@@ -156,6 +168,8 @@ def oracle_composite(O, cfg, cams, imgs):
         masks.append(wm)
         corners.append(rect[:2])
         sizes.append(rect[2:])
+    if mask_fn is not None:
+        masks = mask_fn(masks)
     b = O.Blender(cfg["blender"], cfg["strength"])
     b.prepare(corners, sizes)
     for wi, wm, c in zip(warped, masks, corners):

@@ -175,6 +175,22 @@ def test_drop_in_classes_equal_compositor(cuda_lib):
     assert np.array_equal(pano, p2) and np.array_equal(mask, m2)
 
 
+@pytest.mark.parametrize("name,scale_down", [("cfg2", 4), ("cfg5", 2)])
+def test_compositor_with_seam_like_blend_masks(cuda_lib, oracle, name, scale_down):
+    """Mask set B of SURVEY 8(d): gray-ramp blend masks (what SeamFinder.resize produces) instead of validity masks."""
+    cfg = rigs.config(name, scale_down)
+    cams = cfg["cameras"]
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 40 + i) for i in range(len(cams))]
+    ref = replay.oracle_composite(oracle, cfg, cams, imgs, mask_fn=lambda ms: replay.ramp_masks(ms, 64))
+    c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+    for i, m in enumerate(ref["masks"]):
+        c.set_mask(i, m)
+    pano, mask = c.composite(imgs)
+    assert_parity(pano, ref["pano"], f"{name} pano with ramp masks")
+    assert np.array_equal(mask, ref["pmask"])
+    c.close()
+
+
 def test_pipelined_submit_wait(cuda_lib):
     """The 2-deep pipelined end-to-end path returns exactly what the synchronous path returns, batch by batch."""
     cfg = rigs.config("cfg2", 4)

@@ -57,6 +57,22 @@ def test_compositor_matches_oracle(use_emu, oracle):
         c.close()
 
 
+def test_compositor_with_seam_like_blend_masks(use_emu, oracle):
+    """Mask set B (gray ramps, 256 levels) through Compositor.set_mask == oracle fed with the same masks."""
+    for name, sd in (("cfg2", 25), ("cfg5", 12)):
+        cfg = rigs.config(name, sd)
+        cams = cfg["cameras"]
+        imgs = [rigs.synth_image(cfg["h"], cfg["w"], 40 + i) for i in range(len(cams))]
+        ref = replay.oracle_composite(oracle, cfg, cams, imgs, mask_fn=lambda ms: replay.ramp_masks(ms, 16))
+        c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+        for i, m in enumerate(ref["masks"]):
+            c.set_mask(i, m)
+        pano, mask = c.composite(imgs)
+        replay.assert_exact(pano, ref["pano"], f"{name} pano with ramp masks")
+        replay.assert_exact(mask, ref["pmask"], f"{name} mask with ramp masks")
+        c.close()
+
+
 def test_pipelined_submit_wait_equals_composite(use_emu):
     cfg = rigs.config("cfg2", 25)
     cams = cfg["cameras"]
