@@ -194,7 +194,15 @@ def cpu_reference_run(cfg, imgs, n_sample, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cfg, imgs = make_workload(args.workload, 0)
+    if world > 1:  # the sharded arm's workload (run_sharded): 4 images per GPU on a cylindrical ring
+        from stitching_b200 import rigs
+
+        n, w, h = 4 * world, 4000 // SCALE_DOWN, 3000 // SCALE_DOWN
+        cfg = dict(n=n, w=w, h=h, warper="cylindrical", cameras=rigs.yaw_ring(n, w, h, 8000 / SCALE_DOWN, 10), blender="multiband", strength=5)
+        imgs = [rigs.synth_image(h, w, i) for i in range(min(args.cpu_sample or 4, n))]
+        args.workload = "cfg3"
+    else:
+        cfg, imgs = make_workload(args.workload, 0)
     n_sample = min(args.cpu_sample or 4, cfg["n"])
     # bound the whole run to a few minutes: shrink the sample if one step is slow
     v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
@@ -302,25 +310,27 @@ def run_ours(args, rank, local_rank, world):
     latency_ms = 1e3 * (time.perf_counter() - t0) / 3
     # throughput: every step still uploads its inputs and downloads its result, but consecutive steps are
     # pipelined (two buffer sets, copy streams): sb_compositor_submit / sb_compositor_wait
-    pano2, pmask2 = comp.pinned_empty((ph, pw, 3)), comp.pinned_empty((ph, pw))
-    outs = [(pano, pmask), (pano2, pmask2)]
+    depth = 3  # buffer sets inside the compositor = results that may be in flight
+    outs = [(pano, pmask)] + [(comp.pinned_empty((ph, pw, 3)), comp.pinned_empty((ph, pw))) for _ in range(depth - 1)]
+    pano2 = outs[1][0]
     srcs = [b for _, b in host_src]
-    for k in range(2):
+    for k in range(depth):
         comp.wait(comp.submit(srcs, *outs[k]))
     dist.barrier()
     t0 = time.perf_counter()
     tickets = []
     for k in range(e2e_steps):
-        tickets.append(comp.submit(srcs, *outs[k & 1]))
-        if k >= 1:
-            comp.wait(tickets[k - 1])
-    comp.wait(tickets[-1])
+        if k >= depth:
+            comp.wait(tickets[k - depth])  # the host buffer of this slot has been delivered: it may be reused
+        tickets.append(comp.submit(srcs, *outs[k % depth]))
+    for t in tickets[-depth:]:
+        comp.wait(t)
     e2e_s = dist.max(time.perf_counter() - t0)
     e2e = {"value": total_mpix * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * src_bytes,
            "d2h_bytes_per_step": ph * pw * 4, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
            "unpipelined_ms_per_step": latency_ms,
            "api": "stitching_b200.Compositor.submit/wait (sb_compositor_submit/_wait C ABI): per step H2D of the sources "
-                  "from pinned host memory + warp/blend + D2H of panorama and mask; consecutive steps pipelined 2 deep"}
+                  "from pinned host memory + warp/blend + D2H of panorama and mask; consecutive steps pipelined 3 deep"}
     assert np.array_equal(pano, pano2), "pipelined slots disagree"
     checksum = int(pano[::97, ::89].astype(np.uint64).sum())  # the result was really produced and read back
 
@@ -359,6 +369,108 @@ def run_ours(args, rank, local_rank, world):
     dist.close()
 
 
+def run_sharded(args, rank, local_rank, world):
+    """N > 1: ONE panorama over N GPUs (BASELINE configs[2] family): 4 images of 4000x3000 per GPU on a cylindrical
+    ring (f = 8000, 10 degree step; N = 8 is configs[2] itself), each rank warps + pyramids its block and the per-band
+    partial sums where footprints cross strip boundaries travel over NVLink (NCCL send/recv), then every rank
+    collapses its own column strip.  Weak scaling: per-GPU work is fixed."""
+    from stitching_b200 import Compositor, _lib, rigs
+    from stitching_b200 import dist as sbdist
+
+    dist = Dist(world)
+    L = _lib.lib()
+
+    def bcast(payload):
+        box = [payload]
+        dist.pg.broadcast_object_list(box, src=0)
+        return box[0]
+
+    sbdist.init_comm(rank, world, bcast, device=local_rank)
+    per_gpu, w, h = 4, 4000 // SCALE_DOWN, 3000 // SCALE_DOWN
+    n = per_gpu * world
+    cams = rigs.yaw_ring(n, w, h, 8000 / SCALE_DOWN, 10)
+    t0 = time.perf_counter()
+    comp = Compositor(cams, [(w, h)] * n, "cylindrical", "multiband", 5, rank=rank, world=world)
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    imgs = [rigs.synth_image(h, w, i) for i in range(comp.first, comp.first + comp.count)]
+    comp.upload(imgs)
+    for _ in range(args.warmup):
+        comp.run()
+    comp.sync()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.sb_launch_count()
+    total_ms, launches = comp.time(args.steps)
+    launches1 = L.sb_launch_count()
+    comp.sync()
+    clocks = sampler.result()
+    dist.barrier()
+    worst_ms = dist.max(total_ms)
+    total_mpix = n * w * h / 1e6
+    ms_per_step = worst_ms / args.steps
+    value = total_mpix / (ms_per_step * 1e-3)
+    slab_bytes = sum(comp.shard_slab(p, True)[1] for p in range(world) if p != rank)
+    slab_total = dist.sum(slab_bytes)
+
+    # end to end: every rank uploads its block from pinned host memory and reads its strip back, every step
+    src_bytes = h * w * 3
+    host = [comp.pinned_empty((h, w, 3)) for _ in imgs]
+    for b, im in zip(host, imgs):
+        b[...] = im
+    sw = comp.strip[1] - comp.strip[0]
+    ph = comp.roi[3]
+    pano, pmask = comp.pinned_empty((ph, max(sw, 1), 3)), comp.pinned_empty((ph, max(sw, 1)))
+
+    def e2e_step():
+        comp.upload(host, pinned=True)
+        comp.run()
+        if sw > 0:
+            comp.download(pano, pmask)  # synchronises
+        else:
+            comp.sync()
+
+    for _ in range(3):
+        e2e_step()
+    dist.barrier()
+    e2e_steps = max(4, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    dist.barrier()
+    e2e_s = dist.max(time.perf_counter() - t0)
+    h2d = dist.sum(len(imgs) * src_bytes)
+    d2h = dist.sum(ph * sw * 4)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
+            "config": {
+                "workload": f"cfg3 family: {n}x{w}x{h} RGB, cylindrical warp + multiband blend, ONE panorama sharded over {world} GPUs "
+                            f"({per_gpu} images per GPU; N=8 is BASELINE configs[2])" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""),
+                "images_per_gpu": per_gpu, "pano": [comp.roi[2], comp.roi[3]], "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
+                "parallelism": f"{world} GPUs: image blocks per rank, pano column strips per rank, one grouped NCCL send/recv of "
+                               f"the per-band partial sums ({slab_total / 1e6:.1f} MB per step in total)",
+                "l2": f"no flush: each rank streams its {per_gpu * src_bytes / 1e6:.0f} MB of sources every step (> 126 MB L2)",
+                "timed": "plan built once; a step = warp + pyramids + partial sums + NCCL exchange + collapse of the own strip",
+            },
+            "clocks": clocks,
+            "e2e": {"value": total_mpix * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "api": "stitching_b200.Compositor(rank, world).upload/run/download per rank, pinned host buffers"},
+            "gpu_launches": int(launches1 - launches0),
+            "roofline": {"bound": "hbm", "kernel": None, "achieved": None, "peak": measured_peak_gbs()[0], "unit": "GB/s", "frac": None,
+                         "traffic": None, "note": "per-kernel roofline is reported at N = 1", "launches_ms_rank0": {k: round(v, 4) for k, v in launches}},
+            "cpu_baseline": None,
+            "result_checksum": int(pano[::97, ::89].astype(np.uint64).sum()),
+        }
+        print(json.dumps(line), flush=True)
+    comp.close()
+    sbdist.shutdown()
+    dist.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,6 +481,7 @@ def main():
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring used for the CPU baseline (default 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: one independent panorama per GPU instead of one sharded panorama")
     ap.add_argument("--scale-down", type=int, default=1, help="debug: shrink the workload (not a valid measurement)")
     args = ap.parse_args()
     global SCALE_DOWN
@@ -377,6 +490,8 @@ def main():
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif world > 1 and not args.replicas:
+        run_sharded(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -131,8 +131,8 @@ SB_API int sb_compositor_run(sb_compositor *c);
 /* device -> host copy of the panorama (uint8 HxWx3 + uint8 mask); synchronises */
 SB_API int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch);
 /* Pipelined end-to-end step (throughput path): enqueue H2D of the n sources, warp + blend, and D2H of the
- * panorama on separate streams chained by events, and return a ticket.  Two buffer sets are kept, so at most
- * two tickets may be in flight: the copies of one step overlap the kernels of its neighbours.  Host buffers
+ * panorama on separate streams chained by events, and return a ticket.  Three buffer sets are kept, so at most
+ * three tickets may be in flight: the copies of one step overlap the kernels of its neighbours.  Host buffers
  * should be page-locked (sb_host_alloc) and must stay valid until sb_compositor_wait(ticket) returns. */
 SB_API int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const size_t *pitches, uint8_t *dst,
                                 size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, unsigned long long *ticket);
@@ -156,6 +156,21 @@ SB_API void sb_host_free(void *p);
  * Multi-GPU (one process per GPU): images are sharded over ranks, each rank composites its shard
  * and the per-band accumulators of overlapping footprints are exchanged with NCCL.
  * ------------------------------------------------------------------------------------------- */
+/* One panorama over `world` GPUs.  Every rank passes the SAME rig (all n images); rank r warps and builds pyramids
+ * for images [r*n/world, (r+1)*n/world) only (upload just those) and owns one column strip of the panorama.
+ * sb_compositor_run = local kernels + one grouped NCCL send/recv of the per-band partial sums where padded
+ * footprints cross strip boundaries + normalise/collapse of the own strip.  Requires sb_comm_init, the
+ * multiband blender with >= 1 band and image blocks ordered left to right.  download() returns the strip. */
+SB_API sb_compositor *sb_compositor_create_sharded(const sb_rig *rig, int rank, int world);
+/* first image / number of images of this rank and its output columns [strip[0], strip[1]) in pano-roi coordinates */
+SB_API int sb_compositor_shard_info(const sb_compositor *c, int *first_image, int *n_local, int strip[2]);
+/* transport hooks: phase 0 = local kernels up to the filled send slabs, phase 1 = finish after the receive slabs
+ * were filled; sb_compositor_shard_slab exposes the device buffers (outgoing != 0: send slab to `peer`) */
+SB_API int sb_compositor_shard_phase(sb_compositor *c, int phase);
+SB_API int sb_compositor_shard_slab(sb_compositor *c, int peer, int outgoing, void **dev_ptr, size_t *bytes);
+/* plain device-to-device copy on the library's default stream, synchronous (utility for the hooks above) */
+SB_API int sb_device_copy(void *dst, const void *src, size_t bytes);
+
 #define SB_COMM_ID_BYTES 128
 SB_API int sb_comm_unique_id(uint8_t id[SB_COMM_ID_BYTES]);
 SB_API int sb_comm_init(const uint8_t id[SB_COMM_ID_BYTES], int rank, int world);

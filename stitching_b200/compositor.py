@@ -17,8 +17,12 @@ from .warper import Warper
 
 class Compositor:
     def __init__(self, cameras, sizes, warper_type="spherical", blender_type="multiband", blend_strength=5, scale=None,
-                 aspect=1):
-        """cameras: objects with .focal, .K(), .R (cv.detail.CameraParams or rigs.Camera); sizes: [(w, h)]."""
+                 aspect=1, rank=0, world=1):
+        """cameras: objects with .focal, .K(), .R (cv.detail.CameraParams or rigs.Camera); sizes: [(w, h)].
+
+        world > 1: one panorama over `world` GPUs, one process per GPU.  Every rank passes ALL cameras; rank r owns
+        images [r*n/world, (r+1)*n/world) -- `self.first`, `self.count` -- uploads only those and gets the column
+        strip `self.strip` = (lo, hi) of the panorama back (stitching_b200.dist.init_comm must have run)."""
         n = len(cameras)
         if n == 0 or len(sizes) != n:
             raise StitchingError("Compositor needs one size per camera")
@@ -39,7 +43,11 @@ class Compositor:
                        np.float32(blend_strength), self._w, self._h, self._K.ctypes.data_as(_lib.c_float_p),
                        self._R.ctypes.data_as(_lib.c_float_p), 0)
         L = _lib.lib()
-        self._c = L.sb_compositor_create(C.byref(rig))
+        self.rank, self.world = int(rank), int(world)
+        if self.world > 1:
+            self._c = L.sb_compositor_create_sharded(C.byref(rig), self.rank, self.world)
+        else:
+            self._c = L.sb_compositor_create(C.byref(rig))
         if not self._c:
             _lib.check(-1, "sb_compositor_create")
         rects = (C.c_int * (4 * n))()
@@ -50,11 +58,17 @@ class Compositor:
         self.roi = tuple(roi)
         self.num_bands = nb.value
         self._pinned = []
+        first, count, strip = C.c_int(), C.c_int(), (C.c_int * 2)()
+        _lib.check(L.sb_compositor_shard_info(self._c, C.byref(first), C.byref(count), strip), "sb_compositor_shard_info")
+        self.first, self.count, self.strip = first.value, count.value, (strip[0], strip[1])
 
     # -- data movement ---------------------------------------------------------------------------
     def upload(self, images, pinned=False):
+        """images: the frames of THIS rank's block, in order (all n frames when world == 1)."""
         L = _lib.lib()
-        for i, img in enumerate(images):
+        if len(images) != self.count:
+            raise StitchingError(f"expected {self.count} images (block {self.first}..{self.first + self.count - 1}), got {len(images)}")
+        for i, img in enumerate(images, start=self.first):
             img = np.asarray(img)
             if img.dtype != np.uint8 or img.shape != (self.sizes[i][1], self.sizes[i][0], 3):
                 raise StitchingError(f"image {i}: expected uint8 {self.sizes[i][1]}x{self.sizes[i][0]}x3")
@@ -81,7 +95,9 @@ class Compositor:
         _lib.check(_lib.lib().sb_compositor_sync(self._c), "sb_compositor_sync")
 
     def download(self, out=None, out_mask=None):
-        _, _, w, h = self.roi
+        """(pano, mask); with world > 1 the columns self.strip[0]:self.strip[1] of the panorama."""
+        h = self.roi[3]
+        w = self.strip[1] - self.strip[0]
         pano = np.empty((h, w, 3), np.uint8) if out is None else out
         mask = np.empty((h, w), np.uint8) if out_mask is None else out_mask
         _lib.check(_lib.lib().sb_compositor_download(self._c, pano.ctypes.data_as(C.c_void_p), pano.strides[0],
@@ -98,9 +114,21 @@ class Compositor:
                    "sb_compositor_download_warped")
         return img, mask
 
+    # -- sharded composite: transport hooks (sb_compositor_run moves the slabs with NCCL itself) ---------
+    def shard_phase(self, phase):
+        """0: local kernels up to the filled send slabs; 1: finish after the receive slabs were filled."""
+        _lib.check(_lib.lib().sb_compositor_shard_phase(self._c, int(phase)), "sb_compositor_shard_phase")
+
+    def shard_slab(self, peer, outgoing):
+        """(device pointer, bytes) of the slab sent to (outgoing=True) or received from `peer`; bytes may be 0."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _lib.check(_lib.lib().sb_compositor_shard_slab(self._c, int(peer), int(bool(outgoing)), C.byref(p), C.byref(n)),
+                   "sb_compositor_shard_slab")
+        return p.value, n.value
+
     def submit(self, images, out, out_mask):
         """Pipelined step: enqueue upload of `images`, warp + blend, download into `out` / `out_mask`; returns a
-        ticket for wait().  At most two tickets in flight; host arrays should live in pinned memory
+        ticket for wait().  At most three tickets in flight; host arrays should live in pinned memory
         (`pinned_empty`) and must stay untouched until wait(ticket) returns."""
         n = self.n
         ptrs = (C.c_void_p * n)()

@@ -12,6 +12,8 @@
 //   unpadded roi and fuses cv.convertScaleAbs (blender.py:47).
 //
 // feather / no (blender.py:27-28, 34-36 -> cv.detail_FeatherBlender, cv.detail.Blender): single level.
+#include <cstring>
+
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -193,23 +195,27 @@ __global__ void k_dt_cols(const FeedImage *__restrict__ imgs, int i, float sharp
 
 }  // namespace
 
-int launch_collapse_fast(const ColDesc *col, int n, const PanoLevel &up, const PanoLevel &cur, int l, int lw, int lh, PanoOut out,
-                         cudaStream_t s);  // sb_collapse_fast.cu
-
 int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
                     const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s)
 {
     int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
     if (gw <= 0 || gh <= 0) return SB_OK;
-#ifndef SB_EMU
-    // the fast kernel handles levels below the top and reads level 0 through the packed RGBM layout
+    // the fast kernel reads level 0 through the packed RGBM layout and needs at least one band
     bool packed = true;
     for (int i = 0; i < n; ++i) packed = packed && imgs_host[i].rgbm != nullptr;
-    if (!use_simple_kernels() && l < nb && (l > 0 || packed))
-        return launch_collapse_fast(col, n, pano_host[l + 1], pano_host[l], l, lw, lh, out, s);
-#else
-    (void)imgs_host; (void)col; (void)pano_host;
-#endif
+    if (!use_simple_kernels() && nb >= 1 && (l > 0 || packed)) {
+        CollapseArgs A;
+        std::memset(&A, 0, sizeof A);
+        A.col = col;
+        A.n = n;
+        if (l < nb) A.up = pano_host[l + 1];
+        A.cur = pano_host[l];
+        A.rw = l == 0 ? (out.w + 1) / 2 * 2 : lw;
+        A.rh = l == 0 ? (out.h + 1) / 2 * 2 : lh;
+        A.out = out;
+        A.out_hi = out.w;
+        return launch_collapse_fast(A, l, nb, s);
+    }
     dim3 block(CL_BX, CL_BY), grid(div_up(gw, CL_BX), div_up(gh, CL_BY));
     launch(k_collapse_gather, grid, block, 0, s, imgs_dev, n, pano_dev, l, nb, lw, lh, out);
     return launch_check("k_collapse_gather");

@@ -1,4 +1,4 @@
-// sb_collapse_fast.cu -- instruction-lean version of the per-level multiband kernel (levels below the top).
+// sb_collapse_fast.cu -- instruction-lean version of the per-level multiband kernel, all levels.
 //
 // Same arithmetic as k_collapse_gather (sb_blend.cu; see there for the reference call chain
 // stitching/blender.py:41,46 -> MultiBandBlender::feed / ::blend), reorganised for the B200 SM, where the
@@ -11,13 +11,18 @@
 //     (short)trunc(L * 0) = 0 and wsum + 0 = wsum, i.e. nothing -- at level 0 this is the whole padding ring
 //     (constant-0 border of the weight map) and everything outside the warped footprint (mask byte 0);
 //   * level 0 reads the packed RGBM layout; its colours are bytes, so the Laplacian cannot saturate there.
-// A block covers a 64x16 tile and first marks which fed images touch it; images are visited in feed order.
+// A block covers a 64x16 tile and first marks which items touch it; items are visited in feed order.
+//
+// Multi-GPU (one rank per GPU, images sharded over ranks): the same kernel runs in two more roles.  An item can
+// be a SLAB -- the partial sums (acc int16x3 wrap-around, wsum float32) another rank computed for its own images
+// over a rectangle -- which is simply added; and with `partial` set the kernel stops after the accumulation and
+// writes such a slab for a neighbour instead of normalising.  A launch covers a REGION of the level (a rank's
+// pano strip plus a 2-pixel margin per level, enough for the pyrUp of the next finer level).
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
 namespace sb {
 
-#ifndef SB_EMU
 namespace {
 
 constexpr int CF_BX = 32, CF_BY = 8;
@@ -59,33 +64,75 @@ __device__ __forceinline__ void up_quad(const int16_t *__restrict__ S, const Nbr
 
 __device__ __forceinline__ int trunc16(float v) { return (int)(short)__float2int_rz(v); }  // |v| < 2^31 here
 
-template <bool L0>
-__global__ void __launch_bounds__(CF_BX *CF_BY)
-    k_collapse_fast(const ColDesc *__restrict__ col, int n, PanoLevel up, PanoLevel cur, int lw, int lh, PanoOut out)
+// LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
+template <int LV>
+__global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
-    __shared__ unsigned char cover[SB_MAX_IMAGES];
-    const int tile_x = blockIdx.x * (2 * CF_BX), tile_y = blockIdx.y * (2 * CF_BY);
+    const ColDesc *__restrict__ col = A.col;
+    const int n = A.n;
+    const int tile_x = A.rx0 + blockIdx.x * (2 * CF_BX), tile_y = A.ry0 + blockIdx.y * (2 * CF_BY);
+#ifndef SB_EMU
+    __shared__ unsigned char cover[SB_MAX_ITEMS];
     for (int i = threadIdx.y * CF_BX + threadIdx.x; i < n; i += CF_BX * CF_BY) {
         const int4 r = __ldg(reinterpret_cast<const int4 *>(&col[i].ox));
         cover[i] = tile_x < r.x + r.z && tile_x + 2 * CF_BX > r.x && tile_y < r.y + r.w && tile_y + 2 * CF_BY > r.y;
     }
     __syncthreads();
-    const int x = tile_x + 2 * threadIdx.x, y = tile_y + 2 * threadIdx.y;  // top-left pixel of the quad (even, even)
-    if (x >= lw || y >= lh) return;
-    if (L0 && (x >= out.w || y >= out.h)) return;
+#endif
+    const int x = tile_x + 2 * threadIdx.x, y = tile_y + 2 * threadIdx.y;  // top-left pixel of the quad
+    if (x >= A.rx0 + A.rw || y >= A.ry0 + A.rh) return;
+    // pixel (dx, dy) of the quad exists?  (only the top level has odd extents)
+    bool pv[2][2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) pv[dy][dx] = LV != 2 || (x + dx < A.rx0 + A.rw && y + dy < A.ry0 + A.rh);
 
     int acc[2][2][3] = {};
     float wsum[2][2] = {};
     for (int i = 0; i < n; ++i) {
+#ifndef SB_EMU
         if (!cover[i]) continue;
+#endif
         const ColDesc &d = col[i];
         const int4 r = __ldg(reinterpret_cast<const int4 *>(&d.ox));
-        const int X = x - r.x, Y = y - r.y;  // the rect origin and size are even: a quad is in or out as a whole
-        if ((unsigned)X >= (unsigned)r.z || (unsigned)Y >= (unsigned)r.w) continue;
-        const int4 s1 = __ldg(reinterpret_cast<const int4 *>(&d.top));  // top, pitch, plane, upitch
+        const int X = x - r.x, Y = y - r.y;
+        bool in[2][2];
+        if (LV != 2) {
+            // below the top level rect origins and sizes are even: a quad is in or out as a whole
+            if ((unsigned)X >= (unsigned)r.z || (unsigned)Y >= (unsigned)r.w) continue;
+            in[0][0] = in[0][1] = in[1][0] = in[1][1] = true;
+        } else {
+            bool any = false;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    in[dy][dx] = pv[dy][dx] && (unsigned)(X + dx) < (unsigned)r.z && (unsigned)(Y + dy) < (unsigned)r.w;
+                    any = any || in[dy][dx];
+                }
+            if (!any) continue;
+        }
+        const int4 s1 = __ldg(reinterpret_cast<const int4 *>(&d.top));      // top, pitch, plane, upitch
+        const int4 s2 = __ldg(reinterpret_cast<const int4 *>(&d.uplane));   // uplane, kind, -, -
+        if (s2.y == 1) {
+            // a slab of partial sums from another rank: add (int16 wrap-around, float in rank order)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    if (!in[dy][dx]) continue;
+                    const int o = (Y + dy) * s1.y + X + dx;
+                    acc[dy][dx][0] += d.g[o];
+                    acc[dy][dx][1] += d.g[s1.z + o];
+                    acc[dy][dx][2] += d.g[2 * s1.z + o];
+                    wsum[dy][dx] = fadd(wsum[dy][dx], d.w[o]);
+                }
+            continue;
+        }
         int g[2][2][3];
         float wt[2][2];
-        if (L0) {
+        if (LV == 0) {
             const int4 s0 = __ldg(reinterpret_cast<const int4 *>(&d.rgbm_pitch));  // rgbm_pitch, iw, ih, left
             const int ix = X - s0.w, iy = Y - s1.x;
             if (ix + 1 < 0 || ix >= s0.y || iy + 1 < 0 || iy >= s0.z) continue;  // whole quad in the zero-weight padding
@@ -95,8 +142,8 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    const bool in = (unsigned)(ix + dx) < (unsigned)s0.y && (unsigned)(iy + dy) < (unsigned)s0.z;
-                    p[dy][dx] = in ? __ldg(base + (iy + dy) * s0.x + ix + dx) : 0u;
+                    const bool inside = (unsigned)(ix + dx) < (unsigned)s0.y && (unsigned)(iy + dy) < (unsigned)s0.z;
+                    p[dy][dx] = inside ? __ldg(base + (iy + dy) * s0.x + ix + dx) : 0u;
                 }
             if (((p[0][0] | p[0][1] | p[1][0] | p[1][1]) >> 24) == 0u) continue;  // all four weights are exactly 0
 #pragma unroll
@@ -108,7 +155,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
                     g[dy][dx][2] = (p[dy][dx] >> 16) & 255u;
                     wt[dy][dx] = fmul((float)(p[dy][dx] >> 24), SB_INV255);
                 }
-        } else {
+        } else if (LV == 1) {
             const int o0 = Y * s1.y + X;  // X even: the pairs are 4- / 8-byte aligned
             const float2 w0 = __ldg(reinterpret_cast<const float2 *>(d.w + o0));
             const float2 w1 = __ldg(reinterpret_cast<const float2 *>(d.w + o0 + s1.y));
@@ -118,30 +165,68 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
             for (int c = 0; c < 3; ++c) {
                 const unsigned a = __ldg(reinterpret_cast<const unsigned *>(d.g + c * s1.z + o0));
                 const unsigned b = __ldg(reinterpret_cast<const unsigned *>(d.g + c * s1.z + o0 + s1.y));
-                g[0][0][c] = (short)(a & 0xffffu); g[0][1][c] = (short)(a >> 16);
-                g[1][0][c] = (short)(b & 0xffffu); g[1][1][c] = (short)(b >> 16);
+                g[0][0][c] = (short)(a & 0xffffu); g[0][1][c] = (int)a >> 16;
+                g[1][0][c] = (short)(b & 0xffffu); g[1][1][c] = (int)b >> 16;
             }
-        }
-        const int uplane = __ldg(&d.uplane);
-        const Nbr q = neighbours(X >> 1, Y >> 1, r.z >> 1, r.w >> 1, s1.w);
-        const int16_t *ug = d.ug;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int u[2][2];
-            up_quad(ug + c * uplane, q, u);
+        } else {
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    int lap = g[dy][dx][c] - u[dy][dx];
-                    if (!L0) lap = sat_s16(lap);  // bytes minus an average of bytes cannot leave int16
-                    acc[dy][dx][c] += trunc16(fmul((float)lap, wt[dy][dx]));
+                    wt[dy][dx] = 0.f;
+                    g[dy][dx][0] = g[dy][dx][1] = g[dy][dx][2] = 0;
+                    if (!in[dy][dx]) continue;
+                    const int o = (Y + dy) * s1.y + X + dx;
+                    wt[dy][dx] = d.w[o];
+                    g[dy][dx][0] = d.g[o];
+                    g[dy][dx][1] = d.g[s1.z + o];
+                    g[dy][dx][2] = d.g[2 * s1.z + o];
                 }
+        }
+        if (LV != 2) {
+            const Nbr q = neighbours(X >> 1, Y >> 1, r.z >> 1, r.w >> 1, s1.w);
+            const int16_t *ug = d.ug;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                int u[2][2];
+                up_quad(ug + c * s2.x, q, u);
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        int lap = g[dy][dx][c] - u[dy][dx];
+                        if (LV != 0) lap = sat_s16(lap);  // bytes minus an average of bytes cannot leave int16
+                        acc[dy][dx][c] += trunc16(fmul((float)lap, wt[dy][dx]));
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += trunc16(fmul((float)g[dy][dx][c], wt[dy][dx]));
         }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) wsum[dy][dx] = fadd(wsum[dy][dx], wt[dy][dx]);
+    }
+
+    if (A.partial) {
+        // hand the partial sums of this rank's items to the rank that owns the region
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                if (!pv[dy][dx]) continue;
+                const int o = (y + dy - A.ry0) * A.slab_pitch + (x + dx - A.rx0);
+                A.slab_acc[o] = (int16_t)acc[dy][dx][0];
+                A.slab_acc[A.slab_plane + o] = (int16_t)acc[dy][dx][1];
+                A.slab_acc[2 * A.slab_plane + o] = (int16_t)acc[dy][dx][2];
+                A.slab_w[o] = wsum[dy][dx];
+            }
+        return;
     }
 
     // blend step + collapse: v = sat16(pyrUp(C_{l+1}) + (short)trunc(acc / (wsum + eps)))
@@ -151,33 +236,56 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) den[dy][dx] = fadd(wsum[dy][dx], SB_WEIGHT_EPS);
-    const Nbr q = neighbours(x >> 1, y >> 1, up.w_px, up.h_px, up.pitch);
+    if (LV != 2) {
+        const Nbr q = neighbours(x >> 1, y >> 1, A.up.w_px, A.up.h_px, A.up.pitch);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        int u[2][2];
-        up_quad(up.c + c * up.plane, q, u);
+        for (int c = 0; c < 3; ++c) {
+            int u[2][2];
+            up_quad(A.up.c + c * A.up.plane, q, u);
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx)
-                v[dy][dx][c] = sat_s16(u[dy][dx] + f2s_wrap(fdiv((float)(short)acc[dy][dx][c], den[dy][dx])));
+                for (int dx = 0; dx < 2; ++dx)
+                    v[dy][dx][c] = sat_s16(u[dy][dx] + f2s_wrap(fdiv((float)(short)acc[dy][dx][c], den[dy][dx])));
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = f2s_wrap(fdiv((float)(short)acc[dy][dx][c], den[dy][dx]));
     }
-    if (!L0) {
+    if (LV == 1) {
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            const int o = (y + dy) * cur.pitch + x;
+            const int o = (y + dy) * A.cur.pitch + x;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                *reinterpret_cast<unsigned *>(cur.c + c * cur.plane + o) = ((unsigned)v[dy][0][c] & 0xffffu) | ((unsigned)v[dy][1][c] << 16);
+                *reinterpret_cast<unsigned *>(A.cur.c + c * A.cur.plane + o) = ((unsigned)v[dy][0][c] & 0xffffu) | ((unsigned)v[dy][1][c] << 16);
         }
         return;
     }
-    // level 0: mask, zero outside it, crop to the roi, |v| saturated to uint8 (convertScaleAbs)
+    if (LV == 2) {  // the launcher never uses this kernel for a 0-band blend, so the top level is never level 0
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                if (!pv[dy][dx]) continue;
+                const int o = (y + dy) * A.cur.pitch + x + dx;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) A.cur.c[c * A.cur.plane + o] = (int16_t)v[dy][dx][c];
+            }
+        return;
+    }
+    // level 0: mask, zero outside it, crop to the roi / the rank's strip, |v| saturated to uint8 (convertScaleAbs)
+    const PanoOut &out = A.out;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
         if (y + dy >= out.h) continue;
+        const bool s0 = x >= A.out_lo && x < A.out_hi, s1 = x + 1 >= A.out_lo && x + 1 < A.out_hi;  // column is stored?
         const bool on0 = wsum[dy][0] > SB_WEIGHT_EPS, on1 = wsum[dy][1] > SB_WEIGHT_EPS;
-        const bool two = x + 1 < out.w;
+        const int xo = x - A.out_x0;  // column inside the output buffer
         if (out.rgb) {
             unsigned b[6];
 #pragma unroll
@@ -185,32 +293,32 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
                 b[c] = on0 ? (unsigned)min(abs(v[dy][0][c]), 255) : 0u;
                 b[3 + c] = on1 ? (unsigned)min(abs(v[dy][1][c]), 255) : 0u;
             }
-            uint8_t *p = out.rgb + (long long)(y + dy) * out.rgb_pitch + 3 * x;  // x even: 2-byte aligned when the pitch is even
-            if (two && ((out.rgb_pitch & 1) == 0)) {
+            uint8_t *p = out.rgb + (long long)(y + dy) * out.rgb_pitch + 3 * xo;
+            if (s0 && s1 && ((out.rgb_pitch | xo) & 1) == 0) {  // 2-byte aligned
                 unsigned short *p2 = reinterpret_cast<unsigned short *>(p);
                 p2[0] = (unsigned short)(b[0] | (b[1] << 8));
                 p2[1] = (unsigned short)(b[2] | (b[3] << 8));
                 p2[2] = (unsigned short)(b[4] | (b[5] << 8));
             } else {
-                p[0] = (uint8_t)b[0]; p[1] = (uint8_t)b[1]; p[2] = (uint8_t)b[2];
-                if (two) { p[3] = (uint8_t)b[3]; p[4] = (uint8_t)b[4]; p[5] = (uint8_t)b[5]; }
+                if (s0) { p[0] = (uint8_t)b[0]; p[1] = (uint8_t)b[1]; p[2] = (uint8_t)b[2]; }
+                if (s1) { p[3] = (uint8_t)b[3]; p[4] = (uint8_t)b[4]; p[5] = (uint8_t)b[5]; }
             }
         }
         if (out.mask) {
-            uint8_t *m = out.mask + (long long)(y + dy) * out.mask_pitch + x;
-            if (two && ((out.mask_pitch & 1) == 0)) {
+            uint8_t *m = out.mask + (long long)(y + dy) * out.mask_pitch + xo;
+            if (s0 && s1 && ((out.mask_pitch | xo) & 1) == 0) {
                 *reinterpret_cast<unsigned short *>(m) = (unsigned short)((on0 ? 255u : 0u) | (on1 ? 0xff00u : 0u));
             } else {
-                m[0] = on0 ? 255 : 0;
-                if (two) m[1] = on1 ? 255 : 0;
+                if (s0) m[0] = on0 ? 255 : 0;
+                if (s1) m[1] = on1 ? 255 : 0;
             }
         }
         if (out.s16) {
-            int16_t *d = out.s16 + (long long)(y + dy) * out.s16_pitch + 3 * x;
+            int16_t *d = out.s16 + (long long)(y + dy) * out.s16_pitch + 3 * xo;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                d[c] = (int16_t)(on0 ? v[dy][0][c] : 0);
-                if (two) d[3 + c] = (int16_t)(on1 ? v[dy][1][c] : 0);
+                if (s0) d[c] = (int16_t)(on0 ? v[dy][0][c] : 0);
+                if (s1) d[3 + c] = (int16_t)(on1 ? v[dy][1][c] : 0);
             }
         }
     }
@@ -218,22 +326,21 @@ __global__ void __launch_bounds__(CF_BX *CF_BY)
 
 }  // namespace
 
-int launch_collapse_fast(const ColDesc *col, int n, const PanoLevel &up, const PanoLevel &cur, int l, int lw, int lh, PanoOut out,
-                         cudaStream_t s)
+int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s)
 {
-    const int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
-    dim3 block(CF_BX, CF_BY), grid(div_up(gw, 2 * CF_BX), div_up(gh, 2 * CF_BY));
-    if (l == 0)
-        launch(k_collapse_fast<true>, grid, block, 0, s, col, n, up, cur, lw, lh, out);
+    if (A.rw <= 0 || A.rh <= 0) return SB_OK;
+    if (A.n > SB_MAX_ITEMS) {
+        set_error("collapse: %d items exceed SB_MAX_ITEMS=%d", A.n, SB_MAX_ITEMS);
+        return SB_ERR_INVALID;
+    }
+    dim3 block(CF_BX, CF_BY), grid(div_up(A.rw, 2 * CF_BX), div_up(A.rh, 2 * CF_BY));
+    if (l == nb)
+        launch(k_collapse_fast<2>, grid, block, 0, s, A);
+    else if (l == 0)
+        launch(k_collapse_fast<0>, grid, block, 0, s, A);
     else
-        launch(k_collapse_fast<false>, grid, block, 0, s, col, n, up, cur, lw, lh, out);
+        launch(k_collapse_fast<1>, grid, block, 0, s, A);
     return launch_check("k_collapse_fast");
 }
-#else
-int launch_collapse_fast(const ColDesc *, int, const PanoLevel &, const PanoLevel &, int, int, int, PanoOut, cudaStream_t)
-{
-    return SB_ERR_INVALID;  // never called in the emulation build
-}
-#endif
 
 }  // namespace sb

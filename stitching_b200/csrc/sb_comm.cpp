@@ -51,11 +51,58 @@ int nccl_fail(int rc, const char *what)
 }
 }  // namespace
 
+namespace {
+typedef int (*fn_send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_group)(void);
+fn_send p_send = nullptr;
+fn_recv p_recv = nullptr;
+fn_group p_group_start = nullptr, p_group_end = nullptr;
+}  // namespace
+
 namespace sb {
-void *comm_handle() { return g_comm; }
-void *comm_library() { return g_nccl; }
 int comm_rank() { return g_rank; }
 int comm_world() { return g_world; }
+bool comm_ready() { return g_comm != nullptr; }
+
+// One grouped point-to-point exchange on stream `s`: for every peer k, send sendb[k] bytes and receive recvb[k] bytes
+// (either may be 0).  This is the overlap exchange of the sharded composite: only the slabs where footprints cross a
+// strip boundary travel over NVLink, not pano-sized buffers (NCCL has no int16 reduction: the add happens in the
+// consumer kernel, in rank order).
+int comm_exchange(int n, const int *peers, void *const *sendp, const size_t *sendb, void *const *recvp, const size_t *recvb,
+                  cudaStream_t s)
+{
+    if (!g_comm) {
+        set_error("sharded composite: sb_comm_init has not been called");
+        return SB_ERR_STATE;
+    }
+    if (!p_send) {
+        p_send = (fn_send)dlsym(g_nccl, "ncclSend");
+        p_recv = (fn_recv)dlsym(g_nccl, "ncclRecv");
+        p_group_start = (fn_group)dlsym(g_nccl, "ncclGroupStart");
+        p_group_end = (fn_group)dlsym(g_nccl, "ncclGroupEnd");
+        if (!p_send || !p_recv || !p_group_start || !p_group_end) {
+            set_error("NCCL library lacks ncclSend / ncclRecv / ncclGroupStart / ncclGroupEnd");
+            return SB_ERR_COMM;
+        }
+    }
+    const int ncclChar = 0;  // ncclInt8 / ncclChar
+    int rc = p_group_start();
+    if (rc) return nccl_fail(rc, "ncclGroupStart");
+    for (int k = 0; k < n; ++k) {
+        if (sendb[k]) {
+            rc = p_send(sendp[k], sendb[k], ncclChar, peers[k], g_comm, s);
+            if (rc) return nccl_fail(rc, "ncclSend");
+        }
+        if (recvb[k]) {
+            rc = p_recv(recvp[k], recvb[k], ncclChar, peers[k], g_comm, s);
+            if (rc) return nccl_fail(rc, "ncclRecv");
+        }
+    }
+    rc = p_group_end();
+    if (rc) return nccl_fail(rc, "ncclGroupEnd");
+    return SB_OK;
+}
 }  // namespace sb
 
 extern "C" {

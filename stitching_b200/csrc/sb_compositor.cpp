@@ -11,12 +11,15 @@
 #include <vector>
 
 #include "sb_plan.h"
+#include "sb_shard.h"
 
 namespace sb {
 int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, float *tab_dev, WarpJob *job, cudaStream_t s,
                   std::vector<float> &host_tab);
 }
 using namespace sb;
+
+#define SB_PIPE_DEPTH 3  // buffer sets of the pipelined submit / wait path
 
 struct sb_compositor {
     int n = 0;
@@ -26,14 +29,14 @@ struct sb_compositor {
     std::vector<int> src_w, src_h;
     std::vector<Rect> rects;           // warped rects (pano-absolute)
     std::vector<WarpJob> jobs;         // host copy
-    std::vector<WarpJob> jobs2;        // the same jobs reading the second source buffer set (pipelined path)
+    std::vector<WarpJob> jobsx[SB_PIPE_DEPTH - 1];  // the same jobs reading the extra source buffer sets (pipelined path)
     std::vector<uint8_t *> src_dev;    // u8x3 sources
     std::vector<uint32_t *> rgbm_dev;  // warped, packed
     std::vector<float *> tab_dev;
     std::vector<uint8_t *> usermask_dev;
     int max_w = 0, max_h = 0;
     BlendPlan plan;
-    PanoOut out;                       // device outputs
+    PanoOut out{};                     // device outputs
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
     std::vector<cudaEvent_t> ev;       // ev[0] = start, ev[k+1] = after launch k
@@ -42,16 +45,20 @@ struct sb_compositor {
     double warp_bytes = 0;
     // pipelined submit / wait: a second set of source + output buffers, copy streams, per-slot events
     bool pipe_ready = false;
-    std::vector<uint8_t *> src_dev2;
-    PanoOut out2;
+    std::vector<uint8_t *> src_devx[SB_PIPE_DEPTH - 1];
+    PanoOut outx[SB_PIPE_DEPTH - 1] = {};
     cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t e_h2d[SB_PIPE_DEPTH] = {}, e_comp[SB_PIPE_DEPTH] = {}, e_d2h[SB_PIPE_DEPTH] = {};
     unsigned long long submitted = 0;
 #ifndef SB_EMU
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // one captured step per buffer slot
+    cudaGraphExec_t graph_exec[SB_PIPE_DEPTH] = {};  // one captured step per buffer slot
 #endif
     unsigned graph_kernels = 0;
     std::vector<cudaEvent_t> tev;  // step start / end events of sb_compositor_time
+    // multi-GPU: this process composites images [first, first + count) and one column strip of the panorama
+    bool sharded = false;
+    int first = 0, count = 0;
+    ShardPlan shard;
 };
 
 static void compositor_free(sb_compositor *c)
@@ -68,12 +75,15 @@ static void compositor_free(sb_compositor *c)
     dev_free(c->flush_buf, s);
     if (c->h2d) (void)cudaStreamSynchronize(c->h2d);
     if (c->d2h) (void)cudaStreamSynchronize(c->d2h);
-    for (auto p : c->src_dev2) dev_free(p, s);
+    for (auto &v : c->src_devx)
+        for (auto p : v) dev_free(p, s);
     if (c->pipe_ready) {
-        dev_free(c->out2.rgb, s);
-        dev_free(c->out2.mask, s);
+        for (auto &o : c->outx) {
+            dev_free(o.rgb, s);
+            dev_free(o.mask, s);
+        }
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < SB_PIPE_DEPTH; ++k) {
         if (c->e_h2d[k]) (void)cudaEventDestroy(c->e_h2d[k]);
         if (c->e_comp[k]) (void)cudaEventDestroy(c->e_comp[k]);
         if (c->e_d2h[k]) (void)cudaEventDestroy(c->e_d2h[k]);
@@ -85,6 +95,7 @@ static void compositor_free(sb_compositor *c)
         if (g) (void)cudaGraphExecDestroy(g);
 #endif
     for (auto &e : c->tev) (void)cudaEventDestroy(e);
+    c->shard.release(s);
     c->plan.release(s);
     for (auto &e : c->ev)
         if (e) (void)cudaEventDestroy(e);
@@ -95,10 +106,15 @@ static void compositor_free(sb_compositor *c)
     delete c;
 }
 
-static int compositor_build(sb_compositor *c, const sb_rig *rig)
+static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int world)
 {
     const int n = rig->n_images;
     c->n = n;
+    c->sharded = world > 1;
+    c->first = 0;
+    c->count = n;
+    if (c->sharded) ShardPlan::block_of(n, world, rank, &c->first, &c->count);
+    auto mine = [&](int i) { return i >= c->first && i < c->first + c->count; };
     c->warp_type = rig->warp_type;
     c->scale = rig->scale;
     c->blend_kind_requested = rig->blend_kind;
@@ -134,6 +150,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
         sizes[2 * i + 1] = rect[3];
         c->max_w = std::max(c->max_w, rect[2]);
         c->max_h = std::max(c->max_h, rect[3]);
+        if (!mine(i)) continue;  // another rank warps this image: only its geometry is needed here
         SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
         SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rect[2] * rect[3] * 4, s));
         SB_TRY(dev_alloc((void **)&c->tab_dev[i], ((size_t)2 * rect[2] + 2 * rect[3]) * sizeof(float), s));
@@ -163,14 +180,24 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig)
         f.rgbm_pitch = c->rects[i].w;
         SB_TRY(c->plan.add_feed(f));
     }
+    int out_w = roi.w;
+    if (c->sharded) {
+        c->plan.active_first = c->first;
+        c->plan.active_count = c->count;
+        SB_TRY(c->shard.build(c->plan, rank, world));
+        int lo, hi;
+        c->shard.strip(c->plan, &lo, &hi);
+        out_w = hi - lo;
+    }
     SB_TRY(c->plan.allocate(s));
+    if (c->sharded) SB_TRY(c->shard.allocate(c->plan, s));
     std::memset(&c->out, 0, sizeof c->out);
-    c->out.w = roi.w;
+    c->out.w = out_w;
     c->out.h = roi.h;
-    c->out.rgb_pitch = (long long)roi.w * 3;
-    c->out.mask_pitch = roi.w;
-    SB_TRY(dev_alloc((void **)&c->out.rgb, (size_t)roi.w * 3 * roi.h, s));
-    SB_TRY(dev_alloc((void **)&c->out.mask, (size_t)roi.w * roi.h, s));
+    c->out.rgb_pitch = (long long)out_w * 3;
+    c->out.mask_pitch = out_w;
+    SB_TRY(dev_alloc((void **)&c->out.rgb, (size_t)std::max(out_w, 1) * 3 * roi.h, s));
+    SB_TRY(dev_alloc((void **)&c->out.mask, (size_t)std::max(out_w, 1) * roi.h, s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }
@@ -186,7 +213,7 @@ static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
         const char *e = getenv("SB_GRAPH");
         return !(e && e[0] == '0');
     }();
-    if (!events && use_graph) {
+    if (!events && use_graph && !c->sharded) {  // (the sharded step contains the NCCL exchange: launched directly)
         cudaStream_t s = c->stream;
         if (!c->graph_exec[slot]) {
             const unsigned long long before = sb_launch_count();
@@ -213,6 +240,25 @@ static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
     return compositor_enqueue_kernels(c, events, slot);
 }
 
+// sharded step, local part: pyramids of the own images, then the partial sums every neighbour needs
+static int shard_local(sb_compositor *c, cudaStream_t s, const std::function<int(const std::string &)> &mark)
+{
+    BlendPlan &P = c->plan;
+    const int n = (int)P.imgs.size();
+    for (int l = 0; l < P.nb; ++l) {
+        int mw = 0, mh = 0;
+        for (int i = c->first; i < c->first + c->count; ++i) {
+            mw = std::max(mw, P.imgs[i].pw >> (l + 1));
+            mh = std::max(mh, P.imgs[i].ph >> (l + 1));
+        }
+        SB_TRY(launch_pyrdown(P.imgs_dev, P.imgs.data(), P.pyr_dev + (size_t)l * n, c->first, c->count, l, mw, mh, s));
+        SB_TRY(mark("pyrdown_l" + std::to_string(l)));
+    }
+    SB_TRY(c->shard.partial_out(P, s));
+    SB_TRY(mark("partial_out"));
+    return SB_OK;
+}
+
 static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
 {
     cudaStream_t s = c->stream;
@@ -232,9 +278,16 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
         return SB_OK;
     };
     SB_TRY(mark("start"));
-    SB_TRY(launch_warp(slot ? c->jobs2.data() : c->jobs.data(), c->n, s));
+    const WarpJob *jobs = slot ? c->jobsx[slot - 1].data() : c->jobs.data();
+    SB_TRY(launch_warp(jobs + c->first, c->count, s));
     SB_TRY(mark("warp"));
-    SB_TRY(c->plan.run(slot ? c->out2 : c->out, s, events ? std::function<int(const std::string &)>(mark) : nullptr));
+    const PanoOut &out = slot ? c->outx[slot - 1] : c->out;
+    if (!c->sharded) return c->plan.run(out, s, events ? std::function<int(const std::string &)>(mark) : nullptr);
+    SB_TRY(shard_local(c, s, std::function<int(const std::string &)>(mark)));
+    SB_TRY(c->shard.exchange(s));
+    SB_TRY(mark("exchange"));
+    SB_TRY(c->shard.finish(c->plan, out, s));
+    SB_TRY(mark("finish"));
     return SB_OK;
 }
 
@@ -243,20 +296,22 @@ static int compositor_pipe_init(sb_compositor *c)
 {
     if (c->pipe_ready) return SB_OK;
     cudaStream_t s = c->stream;
-    c->src_dev2.assign(c->n, nullptr);
-    c->jobs2 = c->jobs;
-    for (int i = 0; i < c->n; ++i) {
-        SB_TRY(dev_alloc((void **)&c->src_dev2[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
-        c->jobs2[i].src = c->src_dev2[i];
+    for (int k = 0; k < SB_PIPE_DEPTH - 1; ++k) {
+        c->src_devx[k].assign(c->n, nullptr);
+        c->jobsx[k] = c->jobs;
+        for (int i = 0; i < c->n; ++i) {
+            SB_TRY(dev_alloc((void **)&c->src_devx[k][i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
+            c->jobsx[k][i].src = c->src_devx[k][i];
+        }
+        c->outx[k] = c->out;
+        c->outx[k].rgb = nullptr;
+        c->outx[k].mask = nullptr;
+        SB_TRY(dev_alloc((void **)&c->outx[k].rgb, (size_t)c->out.w * 3 * c->out.h, s));
+        SB_TRY(dev_alloc((void **)&c->outx[k].mask, (size_t)c->out.w * c->out.h, s));
     }
-    c->out2 = c->out;
-    c->out2.rgb = nullptr;
-    c->out2.mask = nullptr;
-    SB_TRY(dev_alloc((void **)&c->out2.rgb, (size_t)c->out.w * 3 * c->out.h, s));
-    SB_TRY(dev_alloc((void **)&c->out2.mask, (size_t)c->out.w * c->out.h, s));
     SB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     SB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < SB_PIPE_DEPTH; ++k) {
         SB_CUDA(cudaEventCreateWithFlags(&c->e_h2d[k], cudaEventDisableTiming));
         SB_CUDA(cudaEventCreateWithFlags(&c->e_comp[k], cudaEventDisableTiming));
         SB_CUDA(cudaEventCreateWithFlags(&c->e_d2h[k], cudaEventDisableTiming));
@@ -277,11 +332,76 @@ sb_compositor *sb_compositor_create(const sb_rig *rig)
         return nullptr;
     }
     sb_compositor *c = new sb_compositor;
-    if (compositor_build(c, rig) != SB_OK) {
+    if (compositor_build(c, rig, 0, 1) != SB_OK) {
         compositor_free(c);
         return nullptr;
     }
     return c;
+}
+
+// One panorama over `world` GPUs (one process each): this rank warps and pyramids images
+// [rank*n/world, (rank+1)*n/world) and owns one column strip of the panorama (sb_shard.h).
+sb_compositor *sb_compositor_create_sharded(const sb_rig *rig, int rank, int world)
+{
+    if (!rig || rig->n_images <= 0 || rig->n_images > SB_MAX_IMAGES || !rig->src_w || !rig->src_h || !rig->K || !rig->R ||
+        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_AFFINE || world < 1 || rank < 0 || rank >= world) {
+        set_error("sb_compositor_create_sharded: invalid argument");
+        return nullptr;
+    }
+    sb_compositor *c = new sb_compositor;
+    if (compositor_build(c, rig, rank, world) != SB_OK) {
+        compositor_free(c);
+        return nullptr;
+    }
+    return c;
+}
+
+int sb_compositor_shard_info(const sb_compositor *c, int *first_image, int *n_local, int strip[2])
+{
+    if (!c) {
+        set_error("sb_compositor_shard_info: null handle");
+        return SB_ERR_INVALID;
+    }
+    if (first_image) *first_image = c->first;
+    if (n_local) *n_local = c->count;
+    if (strip) {
+        strip[0] = 0;
+        strip[1] = c->plan.roi.w;
+        if (c->sharded) c->shard.strip(c->plan, &strip[0], &strip[1]);
+    }
+    return SB_OK;
+}
+
+// Transport hooks: run the two halves of a sharded step separately and reach the slab buffers, so that a caller can
+// move the slabs itself (tests do, with plain copies; sb_compositor_run uses NCCL).
+int sb_compositor_shard_phase(sb_compositor *c, int phase)
+{
+    if (!c || !c->sharded || phase < 0 || phase > 1) {
+        set_error("sb_compositor_shard_phase: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    cudaStream_t s = c->stream;
+    auto nomark = [](const std::string &) -> int { return SB_OK; };
+    if (phase == 0) {
+        SB_TRY(launch_warp(c->jobs.data() + c->first, c->count, s));
+        SB_TRY(shard_local(c, s, std::function<int(const std::string &)>(nomark)));
+    } else {
+        SB_TRY(c->shard.finish(c->plan, c->out, s));
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
+int sb_compositor_shard_slab(sb_compositor *c, int peer, int outgoing, void **dev_ptr, size_t *bytes)
+{
+    if (!c || !c->sharded || peer < 0 || peer >= c->shard.world || peer == c->shard.rank || !dev_ptr || !bytes) {
+        set_error("sb_compositor_shard_slab: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    const PeerSlab &p = outgoing ? c->shard.send[peer] : c->shard.recv[peer];
+    *dev_ptr = p.buf;
+    *bytes = p.bytes;
+    return SB_OK;
 }
 
 void sb_compositor_destroy(sb_compositor *c) { compositor_free(c); }
@@ -332,6 +452,10 @@ int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pit
         set_error("sb_compositor_upload: invalid argument");
         return SB_ERR_INVALID;
     }
+    if (!c->src_dev[i]) {
+        set_error("sb_compositor_upload: image %d belongs to another rank (this rank owns %d..%d)", i, c->first, c->first + c->count - 1);
+        return SB_ERR_INVALID;
+    }
     SB_CUDA(cudaMemcpy2DAsync(c->src_dev[i], (size_t)c->src_w[i] * 3, src, pitch, (size_t)c->src_w[i] * 3, c->src_h[i],
                               cudaMemcpyHostToDevice, c->stream));
     if (!pinned) SB_CUDA(cudaStreamSynchronize(c->stream));
@@ -340,8 +464,8 @@ int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pit
 
 int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t pitch)
 {
-    if (!c || i < 0 || i >= c->n || !mask || pitch < (size_t)c->rects[i].w) {
-        set_error("sb_compositor_set_mask: invalid argument");
+    if (!c || i < 0 || i >= c->n || !mask || pitch < (size_t)c->rects[i].w || !c->rgbm_dev[i]) {
+        set_error("sb_compositor_set_mask: invalid argument (or an image of another rank)");
         return SB_ERR_INVALID;
     }
     // the blend mask of image i in warped coordinates (what stitcher.py:223-239 hands to Blender.feed); it replaces
@@ -352,10 +476,11 @@ int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t 
     SB_CUDA(cudaStreamSynchronize(c->stream));
     c->jobs[i].blend_mask = c->usermask_dev[i];
     c->jobs[i].blend_mask_pitch = w;
-    if (!c->jobs2.empty()) {
-        c->jobs2[i].blend_mask = c->usermask_dev[i];
-        c->jobs2[i].blend_mask_pitch = w;
-    }
+    for (auto &jx : c->jobsx)
+        if (!jx.empty()) {
+            jx[i].blend_mask = c->usermask_dev[i];
+            jx[i].blend_mask_pitch = w;
+        }
 #ifndef SB_EMU
     for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture
         if (g) {
@@ -399,13 +524,17 @@ int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uin
 }
 
 // Pipelined end-to-end step: H2D of this batch, warp + blend, D2H of the panorama are enqueued on three
-// streams and chained with events; with two buffer sets the copies of step k overlap the kernels of step k+-1.
+// streams and chained with events; with three buffer sets the copies of a step overlap the kernels and copies of its neighbours.
 int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const size_t *pitches, uint8_t *dst, size_t dst_pitch,
                          uint8_t *dst_mask, size_t mask_pitch, unsigned long long *ticket)
 {
     if (!c || !srcs || !pitches || (dst && dst_pitch < (size_t)c->out.w * 3) || (dst_mask && mask_pitch < (size_t)c->out.w)) {
         set_error("sb_compositor_submit: invalid argument");
         return SB_ERR_INVALID;
+    }
+    if (c->sharded) {
+        set_error("sb_compositor_submit: the pipelined path is single-GPU; use upload / run / download on a sharded compositor");
+        return SB_ERR_STATE;
     }
     for (int i = 0; i < c->n; ++i)
         if (!srcs[i] || pitches[i] < (size_t)c->src_w[i] * 3) {
@@ -414,18 +543,18 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
         }
     SB_TRY(compositor_pipe_init(c));
     const unsigned long long t = c->submitted;
-    const int slot = (int)(t & 1);
-    const std::vector<uint8_t *> &sdev = slot ? c->src_dev2 : c->src_dev;
-    const PanoOut &o = slot ? c->out2 : c->out;
+    const int slot = (int)(t % SB_PIPE_DEPTH);
+    const std::vector<uint8_t *> &sdev = slot ? c->src_devx[slot - 1] : c->src_dev;
+    const PanoOut &o = slot ? c->outx[slot - 1] : c->out;
     // sources of this slot are free once the previous compute that read them has finished
-    if (t >= 2) SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
+    if (t >= SB_PIPE_DEPTH) SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
     for (int i = 0; i < c->n; ++i)
         SB_CUDA(cudaMemcpy2DAsync(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
                                   cudaMemcpyHostToDevice, c->h2d));
     SB_CUDA(cudaEventRecord(c->e_h2d[slot], c->h2d));
     SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_h2d[slot], 0));
     // the output buffers of this slot are free once their previous download has finished
-    if (t >= 2) SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_d2h[slot], 0));
+    if (t >= SB_PIPE_DEPTH) SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_d2h[slot], 0));
     SB_TRY(compositor_enqueue(c, false, slot));
     SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
     SB_CUDA(cudaStreamWaitEvent(c->d2h, c->e_comp[slot], 0));
@@ -441,18 +570,18 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
 
 int sb_compositor_wait(sb_compositor *c, unsigned long long ticket)
 {
-    if (!c || !c->pipe_ready || ticket >= c->submitted || ticket + 2 < c->submitted) {
+    if (!c || !c->pipe_ready || ticket >= c->submitted || ticket + SB_PIPE_DEPTH < c->submitted) {
         set_error("sb_compositor_wait: ticket %llu is not in flight", ticket);
         return SB_ERR_STATE;
     }
-    SB_CUDA(cudaEventSynchronize(c->e_d2h[ticket & 1]));
+    SB_CUDA(cudaEventSynchronize(c->e_d2h[ticket % SB_PIPE_DEPTH]));
     return SB_OK;
 }
 
 int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch)
 {
-    if (!c || i < 0 || i >= c->n) {
-        set_error("sb_compositor_download_warped: invalid argument");
+    if (!c || i < 0 || i >= c->n || !c->rgbm_dev[i]) {
+        set_error("sb_compositor_download_warped: invalid argument (or an image of another rank)");
         return SB_ERR_INVALID;
     }
     const int w = c->rects[i].w, h = c->rects[i].h;

@@ -123,6 +123,19 @@ int sb_device_info(char *name, size_t name_len, int *sm_count, int *cc_major, in
 
 unsigned long long sb_launch_count(void) { return sb::g_launches.load(); }
 
+int sb_device_copy(void *dst, const void *src, size_t bytes)
+{
+    SB_TRY(sb::ensure_device());
+    if (!bytes) return SB_OK;
+    if (!dst || !src) {
+        sb::set_error("sb_device_copy: null pointer");
+        return SB_ERR_INVALID;
+    }
+    SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, sb::g_stream));
+    SB_CUDA(cudaStreamSynchronize(sb::g_stream));
+    return SB_OK;
+}
+
 void *sb_host_alloc(size_t bytes)
 {
     if (sb::ensure_device() != SB_OK) return nullptr;

@@ -112,7 +112,7 @@ struct alignas(16) ColDesc {       // collapse of level l
     const int16_t *ug;             // level l+1 colour planes (null at the top level)
     int rgbm_pitch, iw, ih, left;  // level 0: image size and origin inside the padded rect
     int top, pitch, plane, upitch; // level l / l+1 pitches and plane strides, in elements
-    int uplane, pad0, pad1, pad2;
+    int uplane, kind, pad1, pad2;  // kind 0: a fed image; 1: a slab of partial sums (g = acc planes, w = weight sums)
 };
 struct alignas(16) PyrDesc {       // pyrDown of level l -> l+1
     int sw, sh, dpitch, dplane;    // source level size; destination pitch / plane stride (elements)
@@ -138,6 +138,22 @@ struct PanoOut {
     int16_t *s16; long long s16_pitch;     // final int16 HxWx3 before convertScaleAbs (nullable); pitch in elements
     int w, h;                              // unpadded roi size
 };
+
+// one launch of the fast per-level multiband kernel (sb_collapse_fast.cu), passed by value
+#define SB_MAX_ITEMS 320  // fed images + slabs of other ranks
+struct CollapseArgs {
+    const ColDesc *col;       // items of this level in feed order (device)
+    int n;
+    PanoLevel up, cur;        // C_{l+1} (source of the pyrUp) and C_l (destination)
+    int rx0, ry0, rw, rh;     // region of the level covered by this launch (even-aligned below the top level)
+    int partial;              // 1: write the partial sums (acc, wsum) of the items to the slab below instead of finishing
+    int16_t *slab_acc;        //    int16 x3 planes, origin = (rx0, ry0)
+    float *slab_w;
+    int slab_pitch, slab_plane;
+    PanoOut out;              // level 0: final outputs; the buffer covers pano columns [out_x0, out_x0 + out.w)
+    int out_x0, out_lo, out_hi;  // only columns [out_lo, out_hi) are stored (a strip's margin is not output)
+};
+int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // kernel launchers

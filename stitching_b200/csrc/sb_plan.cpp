@@ -158,9 +158,11 @@ int BlendPlan::allocate(cudaStream_t s)
     std::vector<std::vector<Slot>> slots(n);
     std::vector<size_t> fw_off(n, 0);
     size_t pano_off[SB_MAX_BANDS + 1] = {0};
+    auto active = [&](int i) { return active_count < 0 || (i >= active_first && i < active_first + active_count); };
     if (kind == SB_BLEND_MULTIBAND) {
         for (int i = 0; i < n; ++i) {
             slots[i].resize(nb + 1);
+            if (!active(i)) continue;  // another rank owns this image: geometry only
             for (int l = 1; l <= nb; ++l) {
                 const int w = imgs[i].pw >> l, h = imgs[i].ph >> l, pitch = level_pitch(w);
                 slots[i][l].g = carve((size_t)3 * h * pitch * sizeof(int16_t));
@@ -190,8 +192,8 @@ int BlendPlan::allocate(cudaStream_t s)
                 L.h_px = imgs[i].ph >> l;
                 L.pitch = level_pitch(L.w_px);
                 L.plane = (long long)L.h_px * L.pitch;
-                L.g = (int16_t *)(base + slots[i][l].g);
-                L.w = (float *)(base + slots[i][l].w);
+                L.g = active(i) ? (int16_t *)(base + slots[i][l].g) : nullptr;
+                L.w = active(i) ? (float *)(base + slots[i][l].w) : nullptr;
             }
         for (int l = 1; l <= nb; ++l) {
             PanoLevel &P = pano[l];
@@ -209,8 +211,10 @@ int BlendPlan::allocate(cudaStream_t s)
     col_dev = (ColDesc *)(base + col_off);
     pyr_dev = (PyrDesc *)(base + pyr_off);
     // compact per-(level, image) descriptors for the fast kernels: [l * n + i]
-    std::vector<ColDesc> col((size_t)n * (nb + 1));
-    std::vector<PyrDesc> pyr((size_t)n * (nb + 1));
+    std::vector<ColDesc> &col = col_host;
+    std::vector<PyrDesc> &pyr = pyr_host;
+    col.assign((size_t)n * (nb + 1), ColDesc{});
+    pyr.assign((size_t)n * (nb + 1), PyrDesc{});
     if (kind == SB_BLEND_MULTIBAND) {
         for (int l = 0; l <= nb; ++l)
             for (int i = 0; i < n; ++i) {

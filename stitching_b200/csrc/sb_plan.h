@@ -41,6 +41,11 @@ public:
     PanoLevel *pano_dev = nullptr;
     ColDesc *col_dev = nullptr;  // [(nb+1)][n] compact descriptors for the fast kernels
     PyrDesc *pyr_dev = nullptr;
+    std::vector<ColDesc> col_host;  // host copies (the sharded compositor builds its item lists from them)
+    std::vector<PyrDesc> pyr_host;
+    // images [active_first, active_first + active_count) get pyramid storage; the others (owned by other ranks of
+    // a sharded composite) only take part in the geometry.  active_count < 0: all images.
+    int active_first = 0, active_count = -1;
 
     // geometry only (no device work): usable without a GPU for tests of the host logic
     int set_geometry(int kind, int num_bands_requested, float sharpness, const Rect &roi);

@@ -1,0 +1,59 @@
+// sb_shard.h -- one panorama composited by several GPUs (one process per GPU): image blocks per rank, pano column
+// strips per rank, exchange of the per-band partial sums where footprints cross a strip boundary.
+#pragma once
+#include <vector>
+
+#include "sb_plan.h"
+
+namespace sb {
+
+struct SlabLevel {
+    int x0, y0, w, h;       // rectangle at this level, pano level coordinates (w == 0: nothing at this level)
+    int pitch, plane;       // elements
+    size_t acc_off, w_off;  // byte offsets inside the slab buffer
+};
+struct PeerSlab {
+    SlabLevel lv[SB_MAX_BANDS + 1];
+    size_t bytes = 0;       // 0: no exchange with this peer in this direction
+    void *buf = nullptr;    // device
+};
+
+class ShardPlan {
+public:
+    int rank = 0, world = 1;
+    int first = 0, count = 0;        // this rank's image block [first, first + count)
+    std::vector<int> bounds;         // strip boundaries in padded-pano columns, world + 1 entries, multiples of 2^nb
+    std::vector<PeerSlab> send, recv;  // indexed by peer rank
+    ColDesc *items_dev[SB_MAX_BANDS + 1] = {};
+    int n_items[SB_MAX_BANDS + 1] = {};
+
+    static void block_of(int n_images, int world, int r, int *first, int *count)
+    {
+        *first = (int)((long long)r * n_images / world);
+        *count = (int)((long long)(r + 1) * n_images / world) - *first;
+    }
+    // geometry from the plan of ALL images (identical on every rank)
+    int build(const BlendPlan &plan, int rank, int world);
+    // slab buffers and per-level item lists (own images + the slabs this rank receives), after plan.allocate()
+    int allocate(const BlendPlan &plan, cudaStream_t s);
+    void release(cudaStream_t s);
+    // output columns of this rank: [lo, hi) in pano-roi coordinates (hi <= roi.w; may be empty)
+    void strip(const BlendPlan &plan, int *lo, int *hi) const;
+    // phase 0: partial sums of the own images over every region a neighbour needs -> send slabs
+    int partial_out(const BlendPlan &plan, cudaStream_t s);
+    // the NCCL exchange of the slabs (grouped send/recv on stream s)
+    int exchange(cudaStream_t s);
+    // phase 1: sum slabs + own images in rank order, normalise, collapse the own strip; `out` is strip-local
+    int finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s);
+
+private:
+    void region_x(const BlendPlan &plan, int r, int l, int *a, int *b) const;
+    void slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab *ps) const;
+    void *items_arena_ = nullptr;
+};
+
+int comm_exchange(int n, const int *peers, void *const *sendp, const size_t *sendb, void *const *recvp, const size_t *recvb,
+                  cudaStream_t s);
+bool comm_ready();
+
+}  // namespace sb

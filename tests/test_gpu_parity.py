@@ -191,6 +191,32 @@ def test_compositor_with_seam_like_blend_masks(cuda_lib, oracle, name, scale_dow
     c.close()
 
 
+@pytest.mark.parametrize("name,scale_down,world", [("cfg2", 4, 2), ("cfg3", 8, 8)])
+def test_sharded_roles_on_one_gpu(cuda_lib, name, scale_down, world):
+    """The kernels' multi-GPU roles (partial sums out, slabs in, strips) with all ranks on ONE device and the slabs
+    moved by device copies instead of NCCL (tests/test_gpu_sharded.py covers NCCL itself when 2 GPUs are there)."""
+    import test_sharded
+
+    cfg = rigs.config(name, scale_down)
+    cams = cfg["cameras"]
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 70 + i) if i % 2 else rigs.synth_image(cfg["h"], cfg["w"], 70 + i)
+            for i in range(len(cams))]
+    single = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+    ref_pano, ref_mask = single.composite(imgs)
+    single.close()
+
+    def copy(dst, src, n):
+        from stitching_b200 import _lib
+
+        _lib.check(cuda_lib.sb_device_copy(dst, src, n), "sb_device_copy")
+
+    pano, mask, moved = test_sharded.run_sharded(cfg, cams, imgs, world, copy)
+    assert moved > 0 and np.array_equal(mask, ref_mask)
+    d = np.abs(pano.astype(np.int32) - ref_pano.astype(np.int32))
+    assert d.max() <= 1, histogram(pano, ref_pano)
+    print(f"{name} x{world}: {int((d != 0).sum())} of {d.size} values differ by 1, {moved / 1e6:.1f} MB of slabs")
+
+
 def test_pipelined_submit_wait(cuda_lib):
     """The 2-deep pipelined end-to-end path returns exactly what the synchronous path returns, batch by batch."""
     cfg = rigs.config("cfg2", 4)
