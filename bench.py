@@ -377,6 +377,7 @@ def run_sharded(args, rank, local_rank, world):
     from stitching_b200 import Compositor, _lib, rigs
     from stitching_b200 import dist as sbdist
 
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep the one-JSON-line contract
     dist = Dist(world)
     L = _lib.lib()
 

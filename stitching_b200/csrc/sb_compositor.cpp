@@ -21,6 +21,14 @@ using namespace sb;
 
 #define SB_PIPE_DEPTH 3  // buffer sets of the pipelined submit / wait path
 
+// rows copy; a fully contiguous image goes as ONE linear transfer (the DMA engines reach PCIe line rate with those)
+static inline cudaError_t sb_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                                    cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
+
 struct sb_compositor {
     int n = 0;
     int warp_type = 0, blend_kind_requested = 0, mask_mode = 0;
@@ -456,7 +464,7 @@ int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pit
         set_error("sb_compositor_upload: image %d belongs to another rank (this rank owns %d..%d)", i, c->first, c->first + c->count - 1);
         return SB_ERR_INVALID;
     }
-    SB_CUDA(cudaMemcpy2DAsync(c->src_dev[i], (size_t)c->src_w[i] * 3, src, pitch, (size_t)c->src_w[i] * 3, c->src_h[i],
+    SB_CUDA(sb_copy2d(c->src_dev[i], (size_t)c->src_w[i] * 3, src, pitch, (size_t)c->src_w[i] * 3, c->src_h[i],
                               cudaMemcpyHostToDevice, c->stream));
     if (!pinned) SB_CUDA(cudaStreamSynchronize(c->stream));
     return SB_OK;
@@ -472,7 +480,7 @@ int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t 
     // the validity mask in the weight byte of the packed warped image from the next run on
     const int w = c->rects[i].w, h = c->rects[i].h;
     if (!c->usermask_dev[i]) SB_TRY(dev_alloc((void **)&c->usermask_dev[i], (size_t)w * h, c->stream));
-    SB_CUDA(cudaMemcpy2DAsync(c->usermask_dev[i], w, mask, pitch, w, h, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(sb_copy2d(c->usermask_dev[i], w, mask, pitch, w, h, cudaMemcpyHostToDevice, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
     c->jobs[i].blend_mask = c->usermask_dev[i];
     c->jobs[i].blend_mask_pitch = w;
@@ -514,10 +522,10 @@ int sb_compositor_download(sb_compositor *c, uint8_t *dst, size_t dst_pitch, uin
         return SB_ERR_INVALID;
     }
     if (dst)
-        SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, c->out.rgb, (size_t)c->out.rgb_pitch, (size_t)c->out.w * 3, c->out.h,
+        SB_CUDA(sb_copy2d(dst, dst_pitch, c->out.rgb, (size_t)c->out.rgb_pitch, (size_t)c->out.w * 3, c->out.h,
                                   cudaMemcpyDeviceToHost, c->stream));
     if (dst_mask)
-        SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, c->out.mask, (size_t)c->out.mask_pitch, c->out.w, c->out.h,
+        SB_CUDA(sb_copy2d(dst_mask, mask_pitch, c->out.mask, (size_t)c->out.mask_pitch, c->out.w, c->out.h,
                                   cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
     return SB_OK;
@@ -549,7 +557,7 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
     // sources of this slot are free once the previous compute that read them has finished
     if (t >= SB_PIPE_DEPTH) SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
     for (int i = 0; i < c->n; ++i)
-        SB_CUDA(cudaMemcpy2DAsync(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
+        SB_CUDA(sb_copy2d(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
                                   cudaMemcpyHostToDevice, c->h2d));
     SB_CUDA(cudaEventRecord(c->e_h2d[slot], c->h2d));
     SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_h2d[slot], 0));
@@ -559,9 +567,9 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
     SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
     SB_CUDA(cudaStreamWaitEvent(c->d2h, c->e_comp[slot], 0));
     if (dst)
-        SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, o.rgb, (size_t)o.rgb_pitch, (size_t)o.w * 3, o.h, cudaMemcpyDeviceToHost, c->d2h));
+        SB_CUDA(sb_copy2d(dst, dst_pitch, o.rgb, (size_t)o.rgb_pitch, (size_t)o.w * 3, o.h, cudaMemcpyDeviceToHost, c->d2h));
     if (dst_mask)
-        SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, o.mask, (size_t)o.mask_pitch, o.w, o.h, cudaMemcpyDeviceToHost, c->d2h));
+        SB_CUDA(sb_copy2d(dst_mask, mask_pitch, o.mask, (size_t)o.mask_pitch, o.w, o.h, cudaMemcpyDeviceToHost, c->d2h));
     SB_CUDA(cudaEventRecord(c->e_d2h[slot], c->d2h));
     c->submitted = t + 1;
     if (ticket) *ticket = t;
