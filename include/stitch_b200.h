@@ -144,6 +144,9 @@ SB_API int sb_compositor_sync(sb_compositor *c);
 /* time `iters` back-to-back runs with CUDA events on the compositor stream; flush_l2 != 0 writes a
  * buffer larger than L2 between runs (outside the timed intervals).  ms_total = sum of the intervals. */
 SB_API int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_total);
+/* throughput with several batches in flight: `iters` steps dealt round-robin to n (<= 8) compositors of the same rig,
+ * each on its own stream; ms_total = device time from the common start event to the last stream's end event */
+SB_API int sb_compositor_time_multi(sb_compositor *const *cs, int n, int iters, float *ms_total);
 /* device time of every kernel launch of the last sb_compositor_time call, averaged per run, in launch order:
  * names[] receives up to `cap` strings owned by the compositor, ms[] the matching times.  Returns count. */
 SB_API int sb_compositor_stage_times(sb_compositor *c, const char **names, float *ms, int cap);

@@ -68,6 +68,7 @@ SIGNATURES = [
                                        C.c_void_p, C.c_size_t, C.POINTER(C.c_ulonglong)]),
     ("sb_compositor_wait", C.c_int, [C.c_void_p, C.c_ulonglong]),
     ("sb_compositor_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
+    ("sb_compositor_time_multi", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, c_float_p]),
     ("sb_compositor_stage_times", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), c_float_p, C.c_int]),
     ("sb_compositor_create_sharded", C.c_void_p, [C.POINTER(Rig), C.c_int, C.c_int]),
     ("sb_compositor_shard_info", C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),

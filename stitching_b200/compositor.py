@@ -15,6 +15,15 @@ from .stitching_error import StitchingError
 from .warper import Warper
 
 
+def time_multi(compositors, iters):
+    """Device time (ms) of `iters` steps dealt round-robin to several compositors of the same rig (batches in flight)."""
+    n = len(compositors)
+    arr = (C.c_void_p * n)(*[c._c for c in compositors])
+    ms = C.c_float()
+    _lib.check(_lib.lib().sb_compositor_time_multi(arr, n, int(iters), C.byref(ms)), "sb_compositor_time_multi")
+    return ms.value
+
+
 class Compositor:
     def __init__(self, cameras, sizes, warper_type="spherical", blender_type="multiband", blend_strength=5, scale=None,
                  aspect=1, rank=0, world=1):

@@ -64,6 +64,17 @@ __device__ __forceinline__ void up_quad(const int16_t *__restrict__ S, const Nbr
 
 __device__ __forceinline__ int trunc16(float v) { return (int)(short)__float2int_rz(v); }  // |v| < 2^31 here
 
+// the blend step for one channel: (short)trunc((short)acc / den), x86 cast semantics.  A zero accumulator -- the
+// common case in smooth image regions -- gives 0 exactly (den > 0), and must not reach the division: the IEEE
+// division's range check (FCHK) sends zero numerators to a ~100-instruction slow path, which the second profile
+// showed to be most of this kernel's instruction stream.  Substituting 1.0 keeps the fast path for every lane.
+__device__ __forceinline__ int norm16(int acc, float den)
+{
+    const int a = (int)(short)acc;
+    const float q = fdiv(a == 0 ? 1.f : (float)a, den);
+    return a == 0 ? 0 : f2s_wrap(q);
+}
+
 // LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
 template <int LV>
 __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_constant__ CollapseArgs A)
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx)
-                    v[dy][dx][c] = sat_s16(u[dy][dx] + f2s_wrap(fdiv((float)(short)acc[dy][dx][c], den[dy][dx])));
+                    v[dy][dx][c] = sat_s16(u[dy][dx] + norm16(acc[dy][dx][c], den[dy][dx]));
         }
     } else {
 #pragma unroll
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = f2s_wrap(fdiv((float)(short)acc[dy][dx][c], den[dy][dx]));
+                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = norm16(acc[dy][dx][c], den[dy][dx]);
     }
     if (LV == 1) {
 #pragma unroll

@@ -610,6 +610,40 @@ int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t 
     return SB_OK;
 }
 
+// Throughput with several batches in flight: `iters` steps dealt round-robin to n compositors of the same rig (each
+// has its own stream and buffers, so the small latency-bound kernels of one step overlap the large kernels of
+// another).  One start event; every stream waits for it; the time is up to the LAST stream's end event.
+int sb_compositor_time_multi(sb_compositor *const *cs, int n, int iters, float *ms_total)
+{
+    if (!cs || n < 1 || n > 8 || iters <= 0 || !ms_total) {
+        set_error("sb_compositor_time_multi: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    for (int k = 0; k < n; ++k)
+        if (!cs[k] || cs[k]->sharded) {
+            set_error("sb_compositor_time_multi: null or sharded compositor");
+            return SB_ERR_INVALID;
+        }
+    cudaEvent_t start = nullptr, ends[8] = {};
+    SB_CUDA(cudaEventCreate(&start));
+    for (int k = 0; k < n; ++k) SB_CUDA(cudaEventCreate(&ends[k]));
+    SB_CUDA(cudaEventRecord(start, cs[0]->stream));
+    for (int k = 1; k < n; ++k) SB_CUDA(cudaStreamWaitEvent(cs[k]->stream, start, 0));
+    int rc = SB_OK;
+    for (int it = 0; it < iters && rc == SB_OK; ++it) rc = compositor_enqueue(cs[it % n], false);
+    float worst = 0.f;
+    for (int k = 0; k < n; ++k) {
+        if (cudaEventRecord(ends[k], cs[k]->stream) != cudaSuccess || cudaEventSynchronize(ends[k]) != cudaSuccess) rc = rc == SB_OK ? SB_ERR_CUDA : rc;
+        float t = 0.f;
+        if (rc == SB_OK && cudaEventElapsedTime(&t, start, ends[k]) == cudaSuccess) worst = t > worst ? t : worst;
+    }
+    (void)cudaEventDestroy(start);
+    for (int k = 0; k < n; ++k) (void)cudaEventDestroy(ends[k]);
+    if (rc != SB_OK && rc == SB_ERR_CUDA) set_error("sb_compositor_time_multi: CUDA failure while timing");
+    *ms_total = worst;
+    return rc;
+}
+
 int sb_compositor_time(sb_compositor *c, int iters, int flush_l2, float *ms_total)
 {
     if (!c || iters <= 0 || !ms_total) {

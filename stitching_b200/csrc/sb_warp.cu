@@ -127,36 +127,51 @@ __device__ __forceinline__ void fetch_pair(const uint8_t *__restrict__ src, unsi
     }
 }
 
-// reflect() with a branch-free single-bounce path; the modulo form only when the coordinate is far outside
-__device__ __forceinline__ int reflect_near(int p, int n)
-{
-    const int q = p < 0 ? -p - 1 : (p >= n ? 2 * n - 1 - p : p);
-    return (unsigned)q < (unsigned)n ? q : reflect(p, n);
-}
-
+// RGBM_ONLY: the compositor's case -- packed output only and source sides <= 32767, where int16 saturation can
+// neither move a coordinate across the inside test nor touch a footprint that lies inside the image.
+template <bool RGBM_ONLY>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_constant__ WarpBatch B)
 {
     const WarpJob &j = B.j[blockIdx.z];
     const int u = blockIdx.x * WARP_BX + threadIdx.x;
     const int v = blockIdx.y * WARP_BY + threadIdx.y;
     if (u >= j.dw || v >= j.dh) return;
+    const int sw = j.sw, sh = j.sh;
 
     float x, y;
     project(j, u, v, x, y);
-    const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
-    const unsigned m = ((unsigned)nx < (unsigned)j.sw && (unsigned)ny < (unsigned)j.sh) ? 255u : 0u;
-    if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
-    if (!j.dst_rgb && !j.dst_rgbm) return;
+    unsigned m;
+    if (RGBM_ONLY) {
+        m = ((unsigned)cvt_rn_x86(x) < (unsigned)sw && (unsigned)cvt_rn_x86(y) < (unsigned)sh) ? 255u : 0u;
+    } else {
+        const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
+        m = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255u : 0u;
+        if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
+        if (!j.dst_rgb && !j.dst_rgbm) return;
+    }
 
     const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
-    const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
     const int fx = sx & 31, fy = sy & 31;
-    const int x0 = reflect_near(ix, j.sw), x1 = reflect_near(ix + 1, j.sw);
-    const int y0 = reflect_near(iy, j.sh), y1 = reflect_near(iy + 1, j.sh);
+    int ix = sx >> 5, iy = sy >> 5;
+    if (!RGBM_ONLY) {
+        ix = sat_s16(ix);
+        iy = sat_s16(iy);
+    }
     unsigned a0, a1, b0, b1;
     const unsigned pitch = (unsigned)j.spitch;  // coordinates are int16-saturated: offsets stay below 2^32
-    fetch_pair(j.src, (unsigned)y0 * pitch, x0, x1, a0, a1);
-    fetch_pair(j.src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    if ((unsigned)ix < (unsigned)(sw - 1) && (unsigned)iy < (unsigned)(sh - 1)) {
+        // the 2x2 footprint lies inside the image: no border rule applies, the pairs are adjacent
+        const unsigned off = (unsigned)iy * pitch;
+        fetch_pair(j.src, off, ix, ix + 1, a0, a1);
+        fetch_pair(j.src, off + pitch, ix, ix + 1, b0, b1);
+    } else {
+        ix = sat_s16(ix);
+        iy = sat_s16(iy);
+        const int x0 = reflect(ix, sw), x1 = reflect(ix + 1, sw);
+        const int y0 = reflect(iy, sh), y1 = reflect(iy + 1, sh);
+        fetch_pair(j.src, (unsigned)y0 * pitch, x0, x1, a0, a1);
+        fetch_pair(j.src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    }
     // (sum_k w_k p_k + 2^14) >> 15 with w = 32 (32-fy|fy)(32-fx|fx), evaluated as two exact lerps:
     //   h = (32-fx) a + fx b  (<= 8160),  s = (32-fy) h0 + fy h1  (<= 261120),  out = (s + 512) >> 10
     // red and blue share a register as two 16-bit lanes through the horizontal lerp
@@ -168,7 +183,12 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_con
     const unsigned r = ((h0rb & 0xffffu) * hy + (h1rb & 0xffffu) * gy + 512u) >> 10;
     const unsigned b = ((h0rb >> 16) * hy + (h1rb >> 16) * gy + 512u) >> 10;
     const unsigned g = (h0g * hy + h1g * gy + 512u) >> 10;
-    store_pixel(j, u, v, r, g, b, m);
+    if (RGBM_ONLY) {
+        if (j.blend_mask) m = j.blend_mask[(unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u];
+        j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
+    } else {
+        store_pixel(j, u, v, r, g, b, m);
+    }
 }
 #endif  // SB_EMU
 
@@ -201,7 +221,13 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), cnt);
 #ifndef SB_EMU
         if (!use_simple_kernels()) {
-            launch(k_warp_wide, grid, block, 0, s, B);
+            bool rgbm_only = true;
+            for (int i = 0; i < cnt; ++i)
+                rgbm_only = rgbm_only && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767;
+            if (rgbm_only)
+                launch(k_warp_wide<true>, grid, block, 0, s, B);
+            else
+                launch(k_warp_wide<false>, grid, block, 0, s, B);
             SB_TRY(launch_check("k_warp_wide"));
             continue;
         }
