@@ -6,8 +6,10 @@
 One "step" = one pass of the hot path over one batch of synthetic frames for a fixed rig: fused warp of
 every image (+ validity mask), Gaussian/weight pyramids, per-band weighted accumulate + normalise + collapse,
 final uint8 panorama + mask.  At N = 1 the workload is BASELINE.json configs[1] (8 x 4000x3000 RGB, spherical
-warp, multiband blend).  With N > 1 (torchrun, one rank per GPU) every rank composites its own 8-image ring
-(weak scaling, no data-path collective in this round).
+warp, multiband blend).  With N > 1 (torchrun, one rank per GPU) the ranks composite ONE panorama of the
+BASELINE configs[2] family (4 images of 4000x3000 per GPU, cylindrical; N = 8 is configs[2] itself): image blocks
+and pano column strips per rank, one grouped NCCL send/recv of the per-band partial sums (weak scaling);
+`--replicas` runs one independent configs[1] panorama per GPU instead.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM, CUDA events on
 the launching stream); `e2e` goes through the public API with pinned HOST buffers, host<->device copies inside

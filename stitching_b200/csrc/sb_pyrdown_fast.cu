@@ -3,15 +3,19 @@
 // Same arithmetic as k_pyrdown_gather (sb_pyramid.cu; reference chain stitching/blender.py:41 ->
 // MultiBandBlender::feed -> copyMakeBorder + pyrDown(int16x3) + pyrDown(float32)).
 //
-// One warp walks down a strip of 32 destination columns.  Each lane owns the source pair (2x, 2x+1) of its
-// column and gets the other three taps of the horizontal [1 4 6 4 1] from its neighbours with warp shuffles;
-// the five horizontally filtered rows live in registers as a sliding window (a destination row consumes two
-// new source rows), so every source pixel is fetched once (plus a 3-row warm-up per chunk and the strip-edge
-// halo lanes).  The two source rows of the NEXT destination row are requested before the current one is
-// computed (software prefetch).  No shared memory, no atomics.
+// One warp walks down a strip of destination columns.  Lane k owns destination column x = strip + k - 1 and the
+// source pair (2x, 2x+1); it gets the other three taps of the horizontal [1 4 6 4 1] from lanes k-1 and k+1 with
+// warp shuffles.  Lanes 0 and 31 are HALO lanes: they own the virtual columns just outside the strip, load their
+// pair like everybody else (through the same border index maps, so a virtual column beyond the level's edge holds
+// exactly the reflected samples its neighbour needs) and store nothing -- 30 output columns per warp and not a
+// single conditional load.  The five horizontally filtered rows live in registers as a sliding window (a
+// destination row consumes two new source rows), so every source pixel is fetched once (plus a 3-row warm-up per
+// chunk and the two halo pairs per row).  The two source rows of the NEXT destination row are requested before the
+// current one is computed (software prefetch).  No shared memory, no atomics.
 //   level 0 (packed RGBM bytes): red/blue and green run as two 16-bit lanes of one 32-bit word through both
 //     filter passes (5x5 weights sum to 256, 256*255+128 < 2^16, so a lane never carries into its neighbour);
-//     mask byte -> float via the 2^23 mantissa trick (exact for integers < 2^23, keeps the XU pipe free);
+//     each lane converts its own two mask bytes to float (2^23 mantissa trick, exact, keeps the XU pipe free) and
+//     the weights travel by shuffle as well;
 //   levels >= 1 (planar int16 + float32): pairs are single 4-/8-byte loads.
 // The float summation orders (position dependent, sb_pyramid.cuh) are per-lane constants.
 #include "sb_launch.h"
@@ -23,6 +27,8 @@ namespace sb {
 namespace {
 
 constexpr int WK_WARPS = 4;  // warps per block: consecutive row chunks of the same strip
+constexpr int WK_COLS = 30;  // destination columns per warp (lanes 1..30; lanes 0 and 31 are halo lanes)
+constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float byte3_to_float(unsigned p)
 {
@@ -30,18 +36,9 @@ __device__ __forceinline__ float byte3_to_float(unsigned p)
     return fadd(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7443)), -8388608.f);
 }
 
-struct Cols {        // per-lane column constants
-    int c[5];        // element offsets of the five taps inside a source row
-    bool in[5];      // level 0: tap lies inside the fed image (weight != 0 possible)
-    bool load_left, load_right, h_simd, v_simd;
-};
-
-// ---- level 0 ------------------------------------------------------------------------------------
-struct Raw0 { unsigned p2, p3, pa, pb, pc; };
+struct Raw0 { unsigned p2, p3; };                 // own pair of packed pixels (mask byte cleared outside the image)
 struct H0 { unsigned rb, gm; float w; };
-
-// ---- levels >= 1 ----------------------------------------------------------------------------------
-struct Raw1 { unsigned pr[3], hl[3], hn[3]; float2 wp; float wa, wb, wc; };
+struct Raw1 { unsigned pr[3]; float2 wp; };       // own pairs: three int16 planes + weights
 struct H1 { int r, g, b; float w; };
 
 template <bool L0>
@@ -51,12 +48,12 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
     const int4 da = __ldg(reinterpret_cast<const int4 *>(&D.sw));  // sw, sh, dpitch, dplane
     const int sw = da.x, sh = da.y, dw = sw >> 1, dh = sh >> 1;
     const int lane = threadIdx.x;
-    const int x_raw = blockIdx.x * 32 + lane;
+    const int strip = blockIdx.x * WK_COLS;
     const int y_begin = (blockIdx.y * WK_WARPS + threadIdx.y) * rows_per_warp;
-    if ((int)blockIdx.x * 32 >= dw || y_begin >= dh) return;  // warp-uniform
+    if (strip >= dw || y_begin >= dh) return;  // warp-uniform
     const int y_end = min(y_begin + rows_per_warp, dh);
-    const bool valid = x_raw < dw;
-    const int x = valid ? x_raw : dw - 1;
+    const int x = strip + lane - 1;            // -1 .. dw: virtual columns at both ends
+    const bool stores = lane >= 1 && lane <= WK_COLS && x < dw;
 
     // every descriptor field goes to registers once (the stores below could alias it otherwise)
     const int4 db = __ldg(reinterpret_cast<const int4 *>(&D.ih));          // ih, left, top, spitch
@@ -69,106 +66,79 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
     float *__restrict__ dwt = D.dwt;
     const int ih = db.x, left = db.y, top = db.z, spitch = db.w, rgbm_pitch = dc.x, iw = dc.y;
 
-    Cols C;
-    C.load_left = lane == 0;                       // taps 2x-2, 2x-1 are not in lane-1
-    C.load_right = lane == 31 || x_raw + 1 >= dw;  // tap 2x+2 is not in lane+1
-    C.h_simd = x >= 1 && x < pyrdown_hs_end(sw);
-    C.v_simd = x < (dw / 4) * 4;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        int c = reflect101(2 * x + k - 2, sw);
-        C.in[k] = true;
-        if (L0) {
-            c -= left;
-            C.in[k] = (unsigned)c < (unsigned)iw;
-            c = reflect(c, iw);
-        }
-        C.c[k] = c;
+    // own pair (2x, 2x+1) through the level's border rule; at level 0 additionally into the fed image.
+    // For x in [0, dw) the pair is (2x, 2x+1) itself; the virtual columns x = -1 and x >= dw reflect.
+    const int xc = min(x, dw);  // columns beyond dw are never used by a storing lane: keep the indices tame
+    int c2 = reflect101(2 * xc, sw), c3 = reflect101(2 * xc + 1, sw);
+    const bool pair_adjacent = c3 == c2 + 1;
+    unsigned keep2 = 0xffffffffu, keep3 = 0xffffffffu;  // level 0: mask byte survives only inside the fed image
+    if (L0) {
+        c2 -= left;
+        c3 -= left;
+        if ((unsigned)c2 >= (unsigned)iw) keep2 = 0x00ffffffu;
+        if ((unsigned)c3 >= (unsigned)iw) keep3 = 0x00ffffffu;
+        c2 = reflect(c2, iw);
+        c3 = reflect(c3, iw);
     }
+    const bool h_simd = x >= 1 && x < pyrdown_hs_end(sw);
+    const bool v_simd = x < (dw / 4) * 4;
 
-    // -------- row fetch (issue loads only) and horizontal pass (shuffles + arithmetic) --------------
     auto fetch0 = [&](int src_row) -> Raw0 {
         const int iy = reflect101(src_row, sh) - top;
-        const bool rin = (unsigned)iy < (unsigned)ih;
+        const unsigned rowkeep = (unsigned)iy < (unsigned)ih ? 0xffffffffu : 0x00ffffffu;
         const uint32_t *row = rgbm + reflect(iy, ih) * rgbm_pitch;
         Raw0 r;
-        r.p2 = __ldg(row + C.c[2]);
-        r.p3 = __ldg(row + C.c[3]);
-        r.pa = r.pb = r.pc = 0u;
-        if (C.load_left) {
-            r.pa = __ldg(row + C.c[0]);
-            r.pb = __ldg(row + C.c[1]);
-        }
-        if (C.load_right) r.pc = __ldg(row + C.c[4]);
-        // outside the fed image the weight is 0: clear the mask byte (0 * (1/255) == 0 exactly)
-        if (!(rin && C.in[2])) r.p2 &= 0x00ffffffu;
-        if (!(rin && C.in[3])) r.p3 &= 0x00ffffffu;
-        if (!(rin && C.in[0])) r.pa &= 0x00ffffffu;
-        if (!(rin && C.in[1])) r.pb &= 0x00ffffffu;
-        if (!(rin && C.in[4])) r.pc &= 0x00ffffffu;
+        r.p2 = __ldg(row + c2) & keep2 & rowkeep;  // outside the fed image the weight is 0: 0 * (1/255) == 0 exactly
+        r.p3 = __ldg(row + c3) & keep3 & rowkeep;
         return r;
     };
     auto hpass0 = [&](const Raw0 &r) -> H0 {
-        unsigned p0 = __shfl_up_sync(0xffffffffu, r.p2, 1), p1 = __shfl_up_sync(0xffffffffu, r.p3, 1);
-        unsigned p4 = __shfl_down_sync(0xffffffffu, r.p2, 1);
-        if (C.load_left) {
-            p0 = r.pa;
-            p1 = r.pb;
-        }
-        if (C.load_right) p4 = r.pc;
+        const unsigned p0 = __shfl_up_sync(FULL, r.p2, 1), p1 = __shfl_up_sync(FULL, r.p3, 1);
+        const unsigned p4 = __shfl_down_sync(FULL, r.p2, 1);
+        const float w2 = fmul(byte3_to_float(r.p2), SB_INV255), w3 = fmul(byte3_to_float(r.p3), SB_INV255);
+        const float w0 = __shfl_up_sync(FULL, w2, 1), w1 = __shfl_up_sync(FULL, w3, 1), w4 = __shfl_down_sync(FULL, w2, 1);
         const unsigned M = 0x00ff00ffu;
         H0 h;
         h.rb = (p0 & M) + (p4 & M) + 4u * ((p1 & M) + (r.p3 & M)) + 6u * (r.p2 & M);
         h.gm = __byte_perm(p0, 0u, 0x4341) + __byte_perm(p4, 0u, 0x4341) +
                4u * (__byte_perm(p1, 0u, 0x4341) + __byte_perm(r.p3, 0u, 0x4341)) + 6u * __byte_perm(r.p2, 0u, 0x4341);
-        h.w = tap5_h(fmul(byte3_to_float(p0), SB_INV255), fmul(byte3_to_float(p1), SB_INV255), fmul(byte3_to_float(r.p2), SB_INV255),
-                     fmul(byte3_to_float(r.p3), SB_INV255), fmul(byte3_to_float(p4), SB_INV255), C.h_simd);
+        h.w = tap5_h(w0, w1, w2, w3, w4, h_simd);
         return h;
     };
     auto fetch1 = [&](int src_row) -> Raw1 {
         const int ro = reflect101(src_row, sh) * spitch;
         Raw1 r;
+        if (pair_adjacent) {  // (2x, 2x+1): one 4-byte / 8-byte load per plane (true for every real column)
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const int16_t *row = sg + ch * splane + ro;
-            r.pr[ch] = __ldg(reinterpret_cast<const unsigned *>(row + C.c[2]));  // (2x, 2x+1): 4-byte aligned
-            r.hl[ch] = r.hn[ch] = 0u;
-            if (C.load_left) r.hl[ch] = ((unsigned)(unsigned short)__ldg(row + C.c[0])) | ((unsigned)(unsigned short)__ldg(row + C.c[1]) << 16);
-            if (C.load_right) r.hn[ch] = (unsigned)(unsigned short)__ldg(row + C.c[4]);
+            for (int ch = 0; ch < 3; ++ch) r.pr[ch] = __ldg(reinterpret_cast<const unsigned *>(sg + ch * splane + ro + c2));
+            r.wp = __ldg(reinterpret_cast<const float2 *>(swt + ro + c2));
+        } else {              // a reflected virtual column
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int16_t *row = sg + ch * splane + ro;
+                r.pr[ch] = (unsigned)(unsigned short)__ldg(row + c2) | ((unsigned)(unsigned short)__ldg(row + c3) << 16);
+            }
+            r.wp.x = __ldg(swt + ro + c2);
+            r.wp.y = __ldg(swt + ro + c3);
         }
-        const float *wrow = swt + ro;
-        r.wp = __ldg(reinterpret_cast<const float2 *>(wrow + C.c[2]));
-        r.wa = r.wb = r.wc = 0.f;
-        if (C.load_left) {
-            r.wa = __ldg(wrow + C.c[0]);
-            r.wb = __ldg(wrow + C.c[1]);
-        }
-        if (C.load_right) r.wc = __ldg(wrow + C.c[4]);
         return r;
     };
     auto hpass1 = [&](const Raw1 &r) -> H1 {
         int hs[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            unsigned pl = __shfl_up_sync(0xffffffffu, r.pr[ch], 1), pn = __shfl_down_sync(0xffffffffu, r.pr[ch], 1);
-            if (C.load_left) pl = r.hl[ch];
-            if (C.load_right) pn = r.hn[ch];
+            const unsigned pl = __shfl_up_sync(FULL, r.pr[ch], 1), pn = __shfl_down_sync(FULL, r.pr[ch], 1);
             const int v0 = (short)(pl & 0xffffu), v1 = (int)pl >> 16, v2 = (short)(r.pr[ch] & 0xffffu), v3 = (int)r.pr[ch] >> 16;
             const int v4 = (short)(pn & 0xffffu);
             hs[ch] = v0 + v4 + 4 * (v1 + v3) + 6 * v2;
         }
-        float w0 = __shfl_up_sync(0xffffffffu, r.wp.x, 1), w1 = __shfl_up_sync(0xffffffffu, r.wp.y, 1);
-        float w4 = __shfl_down_sync(0xffffffffu, r.wp.x, 1);
-        if (C.load_left) {
-            w0 = r.wa;
-            w1 = r.wb;
-        }
-        if (C.load_right) w4 = r.wc;
+        const float w0 = __shfl_up_sync(FULL, r.wp.x, 1), w1 = __shfl_up_sync(FULL, r.wp.y, 1);
+        const float w4 = __shfl_down_sync(FULL, r.wp.x, 1);
         H1 h;
         h.r = hs[0];
         h.g = hs[1];
         h.b = hs[2];
-        h.w = tap5_h(w0, w1, r.wp.x, r.wp.y, w4, C.h_simd);
+        h.w = tap5_h(w0, w1, r.wp.x, r.wp.y, w4, h_simd);
         return h;
     };
 
@@ -183,14 +153,14 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
                 nb = fetch0(2 * y + 4);
             }
             const H0 h3 = hpass0(ra), h4 = hpass0(rb);
-            if (valid) {
+            if (stores) {
                 const unsigned vrb = h0.rb + h4.rb + 4u * (h1.rb + h3.rb) + 6u * h2.rb + 0x00800080u;
                 const unsigned vgm = h0.gm + h4.gm + 4u * (h1.gm + h3.gm) + 6u * h2.gm + 0x00800080u;
                 const int o = y * dpitch + x;
                 dg[o] = (int16_t)((vrb >> 8) & 0xffu);
                 dg[dplane + o] = (int16_t)((vgm >> 8) & 0xffu);
                 dg[2 * dplane + o] = (int16_t)(vrb >> 24);
-                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, C.v_simd);
+                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
             }
             h0 = h2;
             h1 = h3;
@@ -208,12 +178,12 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
                 nb = fetch1(2 * y + 4);
             }
             const H1 h3 = hpass1(ra), h4 = hpass1(rb);
-            if (valid) {
+            if (stores) {
                 const int o = y * dpitch + x;
                 dg[o] = (int16_t)((h0.r + h4.r + 4 * (h1.r + h3.r) + 6 * h2.r + 128) >> 8);
                 dg[dplane + o] = (int16_t)((h0.g + h4.g + 4 * (h1.g + h3.g) + 6 * h2.g + 128) >> 8);
                 dg[2 * dplane + o] = (int16_t)((h0.b + h4.b + 4 * (h1.b + h3.b) + 6 * h2.b + 128) >> 8);
-                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, C.v_simd);
+                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
             }
             h0 = h2;
             h1 = h3;
@@ -230,10 +200,10 @@ int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int coun
 {
     // rows per warp: long chunks amortise the 3-row warm-up, but the small levels need more warps in flight
     long long strips = 0;
-    for (int i = 0; i < count; ++i) strips += (long long)div_up((imgs_host[i].pw >> (l + 1)), 32) * ((imgs_host[i].ph >> (l + 1)));
+    for (int i = 0; i < count; ++i) strips += (long long)div_up((imgs_host[i].pw >> (l + 1)), WK_COLS) * ((imgs_host[i].ph >> (l + 1)));
     int rows = 32;
     while (rows > 4 && strips / rows < 16384) rows >>= 1;
-    dim3 block(32, WK_WARPS), grid(div_up(max_w, 32), div_up(div_up(max_h, rows), WK_WARPS), count);
+    dim3 block(32, WK_WARPS), grid(div_up(max_w, WK_COLS), div_up(div_up(max_h, rows), WK_WARPS), count);
     if (l == 0)
         launch(k_pyrdown_walk<true>, grid, block, 0, s, pyr, rows);
     else

@@ -42,13 +42,20 @@ void ShardPlan::slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab 
     for (int l = 0; l <= plan.nb; ++l) {
         SlabLevel &L = ps->lv[l];
         if (fc == 0) continue;
-        int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -1, fy1 = -1;  // bounding box of the source rank's padded footprints
+        // Bounding box of where the source rank's weights can be non-zero at this level.  W_0 is non-zero only inside
+        // the fed image's own rect (the padding is a constant-0 border); every pyrDown grows that support by at most
+        // 2 samples per side, i.e. it stays within 3 level-l pixels of the scaled image rect.  Outside it the partial
+        // sums are exactly (acc, wsum) = (0, 0) and need not travel.  Clipped to the padded footprint, kept even.
+        int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -1, fy1 = -1;
+        const int even = l < plan.nb ? ~1 : ~0;
         for (int i = f0; i < f0 + fc; ++i) {
             const FeedImage &im = plan.imgs[i];
-            fx0 = std::min(fx0, im.px >> l);
-            fy0 = std::min(fy0, im.py >> l);
-            fx1 = std::max(fx1, (im.px + im.pw) >> l);
-            fy1 = std::max(fy1, (im.py + im.ph) >> l);
+            const int X0 = im.px + im.left, Y0 = im.py + im.top, X1 = X0 + im.w, Y1 = Y0 + im.h;
+            const int px0 = im.px >> l, py0 = im.py >> l, px1 = (im.px + im.pw) >> l, py1 = (im.py + im.ph) >> l;
+            fx0 = std::min(fx0, std::max(px0, ((X0 >> l) - 3) & even));
+            fy0 = std::min(fy0, std::max(py0, ((Y0 >> l) - 3) & even));
+            fx1 = std::max(fx1, std::min(px1, ((((X1 - 1) >> l) + 4) + 1) & even));
+            fy1 = std::max(fy1, std::min(py1, ((((Y1 - 1) >> l) + 4) + 1) & even));
         }
         int a, b;
         region_x(plan, dst, l, &a, &b);
