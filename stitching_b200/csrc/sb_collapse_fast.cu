@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
         if (LV != 2) {
             const Nbr q = neighbours(X >> 1, Y >> 1, r.z >> 1, r.w >> 1, s1.w);
             const int16_t *ug = d.ug;
+            // all four weights exactly 1 (the interior of a full-weight image): (short)trunc(L * 1.0f) == L
+            const bool unit = wt[0][0] == 1.f && wt[0][1] == 1.f && wt[1][0] == 1.f && wt[1][1] == 1.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 int u[2][2];
@@ -207,8 +209,23 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
                     for (int dx = 0; dx < 2; ++dx) {
                         int lap = g[dy][dx][c] - u[dy][dx];
                         if (LV != 0) lap = sat_s16(lap);  // bytes minus an average of bytes cannot leave int16
-                        acc[dy][dx][c] += trunc16(fmul((float)lap, wt[dy][dx]));
+                        g[dy][dx][c] = lap;
                     }
+            }
+            if (unit) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += g[dy][dx][c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += trunc16(fmul((float)g[dy][dx][c], wt[dy][dx]));
             }
         } else {
 #pragma unroll
@@ -247,6 +264,31 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) den[dy][dx] = fadd(wsum[dy][dx], SB_WEIGHT_EPS);
+    // n = (short)trunc(a / den) without a division where the weight sum is exactly 1 or exactly 0 (one full-weight
+    // image, or nothing): den = fl(1 + 1e-5) = 1 + 84 ulp, so for an integer 0 < |a| <= 32768 the quotient lies
+    // strictly between |a| - 1 and |a| (a * 1e-5 is far above the float spacing and below 1) and truncates to
+    // a - sign(a); with weight sum 0 the accumulator is 0 as well and the same formula gives 0.
+    const bool unit = (wsum[0][0] == 1.f || wsum[0][0] == 0.f) && (wsum[0][1] == 1.f || wsum[0][1] == 0.f) &&
+                      (wsum[1][0] == 1.f || wsum[1][0] == 0.f) && (wsum[1][1] == 1.f || wsum[1][1] == 0.f);
+    int nrm[2][2][3];
+    if (unit) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int a = (int)(short)acc[dy][dx][c];
+                    nrm[dy][dx][c] = a - (a > 0) + (a < 0);
+                }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) nrm[dy][dx][c] = norm16(acc[dy][dx][c], den[dy][dx]);
+    }
     if (LV != 2) {
         const Nbr q = neighbours(x >> 1, y >> 1, A.up.w_px, A.up.h_px, A.up.pitch);
 #pragma unroll
@@ -256,8 +298,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx)
-                    v[dy][dx][c] = sat_s16(u[dy][dx] + norm16(acc[dy][dx][c], den[dy][dx]));
+                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = sat_s16(u[dy][dx] + nrm[dy][dx][c]);
         }
     } else {
 #pragma unroll
@@ -265,7 +306,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = norm16(acc[dy][dx][c], den[dy][dx]);
+                for (int dx = 0; dx < 2; ++dx) v[dy][dx][c] = nrm[dy][dx][c];
     }
     if (LV == 1) {
 #pragma unroll

@@ -57,6 +57,17 @@ def test_compositor_matches_oracle(use_emu, oracle):
         c.close()
 
 
+def test_unit_weight_shortcuts_are_exact():
+    """The two identities the fast collapse kernel uses instead of float work (sb_collapse_fast.cu):
+    (short)trunc(L * 1.0f) == L, and (short)trunc(a / fl(1 + 1e-5f)) == a - sign(a) for every int16 a."""
+    a = np.arange(-32768, 32768, dtype=np.int32)
+    den = np.float32(1.0) + np.float32(1e-5)
+    q = (a.astype(np.float32) / den).astype(np.float32)
+    assert np.array_equal(np.trunc(q).astype(np.int32), a - np.sign(a))
+    assert np.float32(255.0) * np.float32(1.0 / 255.0) == np.float32(1.0)  # a 255 mask byte is weight exactly 1
+    assert np.array_equal(np.trunc(a.astype(np.float32) * np.float32(1.0)).astype(np.int32), a)
+
+
 def test_compositor_with_seam_like_blend_masks(use_emu, oracle):
     """Mask set B (gray ramps, 256 levels) through Compositor.set_mask == oracle fed with the same masks."""
     for name, sd in (("cfg2", 25), ("cfg5", 12)):
