@@ -221,8 +221,13 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
     return launch_check("k_collapse_gather");
 }
 
+int launch_feather_weights_fast(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
+
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s)
 {
+#ifndef SB_EMU
+    if (!use_simple_kernels()) return launch_feather_weights_fast(imgs_dev, imgs_host, n, sharpness, s);
+#endif
     for (int i = 0; i < n; ++i) {
         launch(k_dt_rows, dim3(div_up(imgs_host[i].h, 64)), dim3(64), 0, s, imgs_dev, i);
         launch(k_dt_cols, dim3(div_up(imgs_host[i].w, 64)), dim3(64), 0, s, imgs_dev, i, sharpness);
