@@ -1,0 +1,145 @@
+"""Drop-in check against the real reference pipeline (build container only: needs /root/reference and cv2).
+
+stitching.Stitcher(crop=False) runs unmodified on three synthetic perspective views of a textured plane.  The
+reference's registration is not deterministic from run to run (RANSAC), so two whole runs cannot be compared;
+instead every call that crosses the hot-path boundary is RECORDED while the reference runs with its own classes
+(the exact cv.detail.CameraParams, numpy-float aspect, cv.UMat blend masks, corner tuples it hands over, and what
+cv2 returned), and then REPLAYED through the B200 classes (here on the emulation build, tests/emu): every warped
+image, mask, roi and the final panorama must be identical.  A second part runs the whole pipeline with
+stitching_b200.install() to show that it executes end to end on the swapped classes.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+
+
+@pytest.fixture()
+def reference_stitching():
+    cv = pytest.importorskip("cv2")
+    if not os.path.isdir(os.path.join(REF, "stitching")):
+        pytest.skip("the reference checkout is not on this box")
+    sys.path.insert(0, REF)
+    for name in [m for m in sys.modules if m == "stitching" or m.startswith("stitching.")]:
+        del sys.modules[name]
+    mod = importlib.import_module("stitching")
+    yield mod, cv
+    for name in [m for m in sys.modules if m == "stitching" or m.startswith("stitching.")]:
+        del sys.modules[name]
+    sys.path.remove(REF)
+
+
+def synthetic_views(cv):
+    rng = np.random.default_rng(5)
+    scene = np.zeros((1400, 3000, 3), np.uint8)
+    scene[:] = cv.resize(rng.integers(0, 256, (24, 50, 3), dtype=np.uint8), (3000, 1400), interpolation=cv.INTER_CUBIC)
+    for _ in range(900):  # random shapes give ORB something to hold on to
+        c = tuple(int(v) for v in rng.integers(0, 256, 3))
+        p = (int(rng.integers(0, 3000)), int(rng.integers(0, 1400)))
+        if rng.random() < 0.5:
+            cv.circle(scene, p, int(rng.integers(5, 40)), c, -1)
+        else:
+            q = (p[0] + int(rng.integers(10, 90)), p[1] + int(rng.integers(10, 90)))
+            cv.rectangle(scene, p, q, c, -1)
+    views = []
+    f, w, h = 900.0, 1000, 750
+    K = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]])
+    Ks = np.array([[f, 0, 1500], [0, f, 700], [0, 0, 1]])
+    for yaw in (-0.35, 0.0, 0.35):
+        R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        H = K @ R @ np.linalg.inv(Ks)
+        views.append(cv.warpPerspective(scene, H, (w, h)))
+    return views
+
+
+SETTINGS = dict(crop=False, detector="orb", confidence_threshold=0.3)
+
+
+def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu):
+    stitching, cv = reference_stitching
+    from stitching.blender import Blender as RefBlender
+    from stitching.warper import Warper as RefWarper
+
+    import stitching_b200
+
+    log = []
+
+    class RecWarper(RefWarper):
+        def warp_image(self, img, camera, aspect=1):
+            out = super().warp_image(img, camera, aspect)
+            log.append(("warp_image", self.warper_type, self.scale, np.array(img).copy(), camera, aspect, out.copy()))
+            return out
+
+        def create_and_warp_mask(self, size, camera, aspect=1):
+            out = super().create_and_warp_mask(size, camera, aspect)
+            log.append(("warp_mask", self.warper_type, self.scale, tuple(size), camera, aspect, out.copy()))
+            return out
+
+        def warp_roi(self, size, camera, aspect=1):
+            out = super().warp_roi(size, camera, aspect)
+            log.append(("warp_roi", self.warper_type, self.scale, tuple(size), camera, aspect, tuple(out)))
+            return out
+
+    class RecBlender(RefBlender):
+        def prepare(self, corners, sizes):
+            log.append(("prepare", self.blender_type, self.blend_strength, list(corners), list(sizes)))
+            super().prepare(corners, sizes)
+
+        def feed(self, img, mask, corner):
+            log.append(("feed", np.array(img).copy(), mask, tuple(corner)))  # mask stays the cv.UMat the pipeline passes
+            super().feed(img, mask, corner)
+
+        def blend(self):
+            pano, mask = super().blend()
+            log.append(("blend", pano.copy(), np.array(mask).copy()))
+            return pano, mask
+
+    stitching.stitcher.Warper, stitching.stitcher.Blender = RecWarper, RecBlender
+    stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in synthetic_views(cv)])
+    kinds = [e[0] for e in log]
+    assert kinds.count("warp_image") >= 6 and kinds.count("feed") == 3 and kinds.count("blend") == 1
+    assert any(type(e[2]).__name__ == "UMat" for e in log if e[0] == "feed"), "the pipeline hands cv.UMat masks to feed"
+
+    blender = None
+    checked = 0
+    for e in log:
+        if e[0] in ("warp_image", "warp_mask", "warp_roi"):
+            w = stitching_b200.Warper(e[1])
+            w.scale = e[2]
+            got = {"warp_image": w.warp_image, "warp_mask": w.create_and_warp_mask, "warp_roi": w.warp_roi}[e[0]](e[3], e[4], e[5])
+            if e[0] == "warp_roi":
+                assert tuple(got) == e[6]
+            else:
+                assert got.shape == e[6].shape and np.array_equal(got, e[6]), f"{e[0]}: {int((got != e[6]).sum())} values differ"
+            checked += 1
+        elif e[0] == "prepare":
+            blender = stitching_b200.Blender(e[1], e[2])
+            blender.prepare(e[3], e[4])
+        elif e[0] == "feed":
+            blender.feed(e[1], e[2], e[3])
+        elif e[0] == "blend":
+            pano, mask = blender.blend()
+            assert np.array_equal(mask, e[2]) and pano.shape == e[1].shape
+            d = np.abs(pano.astype(np.int32) - e[1].astype(np.int32))
+            assert d.max() == 0, f"panorama: max |diff| {int(d.max())}, {int((d != 0).sum())} values"
+            checked += 1
+    assert checked >= 13
+
+
+def test_stitcher_runs_end_to_end_on_the_swapped_classes(reference_stitching, use_emu):
+    stitching, cv = reference_stitching
+    import stitching_b200
+
+    views = synthetic_views(cv)
+    ref_pano = stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in views])
+    stitching_b200.install(stitching)
+    assert stitching.stitcher.Warper is stitching_b200.Warper and stitching.stitcher.Blender is stitching_b200.Blender
+    pano = stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in views])
+    # registration is re-estimated (RANSAC): same geometry up to a few pixels, same kind of picture
+    assert pano.ndim == 3 and pano.dtype == np.uint8
+    assert abs(pano.shape[0] - ref_pano.shape[0]) <= 30 and abs(pano.shape[1] - ref_pano.shape[1]) <= 30  # tests/test_stitcher.py:229-231 style
+    assert (pano.sum(axis=2) > 0).mean() > 0.5
