@@ -34,8 +34,10 @@ class _NativeBlender:
 
     def feed(self, img, mask, corner):
         img = np.asarray(img)
-        if img.ndim != 3 or img.shape[2] != 3 or img.dtype not in (np.uint8, np.int16):
-            raise StitchingError("Blender.feed takes a uint8 or int16 HxWx3 image")
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise StitchingError("Blender.feed takes an HxWx3 image")
+        if img.dtype not in (np.uint8, np.int16):
+            img = img.astype(np.int16)  # what blender.py:41 does with every input
         if hasattr(mask, "get") and not isinstance(mask, np.ndarray):
             mask = mask.get()  # cv.UMat (seam_finder.py:38-43 hands those out)
         mask = np.asarray(mask)

@@ -18,6 +18,8 @@
 // over a rectangle -- which is simply added; and with `partial` set the kernel stops after the accumulation and
 // writes such a slab for a neighbour instead of normalising.  A launch covers a REGION of the level (a rank's
 // pano strip plus a 2-pixel margin per level, enough for the pyrUp of the next finer level).
+#include <cstdlib>
+
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -76,8 +78,10 @@ __device__ __forceinline__ int norm16(int acc, float den)
 }
 
 // LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
-template <int LV>
-__global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_constant__ CollapseArgs A)
+// MINB: minimum resident blocks per SM the register allocation is tuned for (4: no spills; 5: 48 registers, more warps
+// in flight against the long-scoreboard stalls the profile shows, at the price of a few spilled values)
+template <int LV, int MINB>
+__global__ void __launch_bounds__(CF_BX *CF_BY, MINB) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
     const ColDesc *__restrict__ col = A.col;
     const int n = A.n;
@@ -386,12 +390,16 @@ int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s)
         return SB_ERR_INVALID;
     }
     dim3 block(CF_BX, CF_BY), grid(div_up(A.rw, 2 * CF_BX), div_up(A.rh, 2 * CF_BY));
+    static const bool occ5 = [] {
+        const char *e = getenv("SB_COLLAPSE_OCC");
+        return e && e[0] == '5';
+    }();
     if (l == nb)
-        launch(k_collapse_fast<2>, grid, block, 0, s, A);
+        launch(k_collapse_fast<2, 4>, grid, block, 0, s, A);
     else if (l == 0)
-        launch(k_collapse_fast<0>, grid, block, 0, s, A);
+        launch(occ5 ? k_collapse_fast<0, 5> : k_collapse_fast<0, 4>, grid, block, 0, s, A);
     else
-        launch(k_collapse_fast<1>, grid, block, 0, s, A);
+        launch(occ5 ? k_collapse_fast<1, 5> : k_collapse_fast<1, 4>, grid, block, 0, s, A);
     return launch_check("k_collapse_fast");
 }
 
