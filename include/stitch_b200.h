@@ -174,6 +174,11 @@ SB_API int sb_compositor_shard_slab(sb_compositor *c, int peer, int outgoing, vo
 /* plain device-to-device copy on the library's default stream, synchronous (utility for the hooks above) */
 SB_API int sb_device_copy(void *dst, const void *src, size_t bytes);
 
+/* Device self test of the shared-reciprocal division the warp (mode 0) and collapse (mode 1) kernels use in place of
+ * one IEEE division per quotient: n pseudo-random operand pairs from the ranges those kernels guarantee, compared bit
+ * for bit with the IEEE division on the device; *mismatches must come back 0. */
+SB_API int sb_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches);
+
 #define SB_COMM_ID_BYTES 128
 SB_API int sb_comm_unique_id(uint8_t id[SB_COMM_ID_BYTES]);
 SB_API int sb_comm_init(const uint8_t id[SB_COMM_ID_BYTES], int rank, int world);

@@ -40,8 +40,9 @@ int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, f
                   std::vector<float> &host_tab)
 {
     const int w = rect[2], h = rect[3];
-    host_tab.resize((size_t)2 * w + 2 * h);
-    float *colX = host_tab.data(), *colZ = colX + w, *rowA = colZ + w, *rowY = rowA + h;
+    const int wp = (w + 3) & ~3;
+    host_tab.assign(warp_table_floats(w, h), 0.f);
+    float *colX = host_tab.data(), *colZ = colX + wp, *rowA = colZ + wp, *rowY = rowA + h;
     projector_tables(p, rect, colX, colZ, rowA, rowY);
     SB_CUDA(cudaMemcpyAsync(tab_dev, host_tab.data(), host_tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     std::memset(job, 0, sizeof *job);
@@ -50,11 +51,13 @@ int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, f
     job->dw = w;
     job->dh = h;
     job->colX = tab_dev;
-    job->colZ = tab_dev + w;
-    job->rowA = tab_dev + 2 * w;
-    job->rowY = tab_dev + 2 * w + h;
+    job->colZ = tab_dev + wp;
+    job->rowA = tab_dev + 2 * wp;
+    job->rowY = tab_dev + 2 * wp + h;
     std::memcpy(job->k, p.k_rinv, sizeof job->k);
     job->always_divide = p.type == SB_WARP_PLANE;
+    job->xin_hi = 32.f * (float)(src_w - 1) - 0.5f;
+    job->yin_hi = 32.f * (float)(src_h - 1) - 0.5f;
     return SB_OK;
 }
 }  // namespace sb
@@ -101,7 +104,7 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
     Scratch tmp(s);
     float *tab = nullptr;
     uint8_t *d_src = nullptr, *d_img = nullptr, *d_mask = nullptr;
-    SB_TRY(tmp.get(&tab, (size_t)2 * w + 2 * h));
+    SB_TRY(tmp.get(&tab, warp_table_floats(w, h)));
     std::vector<float> host_tab;
     WarpJob job;
     SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));

@@ -18,8 +18,6 @@
 // over a rectangle -- which is simply added; and with `partial` set the kernel stops after the accumulation and
 // writes such a slab for a neighbour instead of normalising.  A launch covers a REGION of the level (a rank's
 // pano strip plus a 2-pixel margin per level, enough for the pyrUp of the next finer level).
-#include <cstdlib>
-
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -66,22 +64,19 @@ __device__ __forceinline__ void up_quad(const int16_t *__restrict__ S, const Nbr
 
 __device__ __forceinline__ int trunc16(float v) { return (int)(short)__float2int_rz(v); }  // |v| < 2^31 here
 
-// the blend step for one channel: (short)trunc((short)acc / den), x86 cast semantics.  A zero accumulator -- the
-// common case in smooth image regions -- gives 0 exactly (den > 0), and must not reach the division: the IEEE
-// division's range check (FCHK) sends zero numerators to a ~100-instruction slow path, which the second profile
-// showed to be most of this kernel's instruction stream.  Substituting 1.0 keeps the fast path for every lane.
-__device__ __forceinline__ int norm16(int acc, float den)
+// the blend step for one channel: (short)trunc((short)acc / den), x86 cast semantics.  The three channels of a pixel
+// share the refined reciprocal of den (sb_device.cuh: the IEEE division's own fast path without its per-quotient range
+// check and branch -- the second profile showed the generic division, whose check sends zero numerators to a
+// ~100-instruction slow path, to be most of this kernel's instruction stream).  Ranges: den = wsum + 1e-5 lies in
+// [2^-17, 2^9], |acc| in [1, 2^15] or acc == 0, which gives exactly 0.
+__device__ __forceinline__ int norm16(int acc, float den, float rr)
 {
-    const int a = (int)(short)acc;
-    const float q = fdiv(a == 0 ? 1.f : (float)a, den);
-    return a == 0 ? 0 : f2s_wrap(q);
+    return f2s_wrap(fdiv_by((float)(int)(short)acc, den, rr));
 }
 
 // LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
-// MINB: minimum resident blocks per SM the register allocation is tuned for (4: no spills; 5: 48 registers, more warps
-// in flight against the long-scoreboard stalls the profile shows, at the price of a few spilled values)
-template <int LV, int MINB>
-__global__ void __launch_bounds__(CF_BX *CF_BY, MINB) k_collapse_fast(const __grid_constant__ CollapseArgs A)
+template <int LV>
+__global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
     const ColDesc *__restrict__ col = A.col;
     const int n = A.n;
@@ -274,6 +269,10 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, MINB) k_collapse_fast(const __gr
     // a - sign(a); with weight sum 0 the accumulator is 0 as well and the same formula gives 0.
     const bool unit = (wsum[0][0] == 1.f || wsum[0][0] == 0.f) && (wsum[0][1] == 1.f || wsum[0][1] == 0.f) &&
                       (wsum[1][0] == 1.f || wsum[1][0] == 0.f) && (wsum[1][1] == 1.f || wsum[1][1] == 0.f);
+    // weight sum exactly 2 (two full-weight images, the bulk of an overlap): den = fl(2 + 1e-5) = 2 + 42 ulp; for even
+    // |a| = 2k the quotient is k (1 - 5e-6), strictly inside (k-1, k); for odd |a| = 2k+1 it lies inside (k, k+1/2):
+    // either way it truncates to (|a| - 1) / 2 rounded toward zero, with the sign of a.
+    const bool two = wsum[0][0] == 2.f && wsum[0][1] == 2.f && wsum[1][0] == 2.f && wsum[1][1] == 2.f;
     int nrm[2][2][3];
     if (unit) {
 #pragma unroll
@@ -285,13 +284,29 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, MINB) k_collapse_fast(const __gr
                     const int a = (int)(short)acc[dy][dx][c];
                     nrm[dy][dx][c] = a - (a > 0) + (a < 0);
                 }
-    } else {
+    } else if (two) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) nrm[dy][dx][c] = norm16(acc[dy][dx][c], den[dy][dx]);
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int a = (int)(short)acc[dy][dx][c];
+                    const int t = a - (a > 0) + (a < 0);
+                    nrm[dy][dx][c] = (t + (int)((unsigned)t >> 31)) >> 1;
+                }
+    } else {
+        float rr[2][2];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) rr[dy][dx] = rcp_refined(den[dy][dx]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) nrm[dy][dx][c] = norm16(acc[dy][dx][c], den[dy][dx], rr[dy][dx]);
     }
     if (LV != 2) {
         const Nbr q = neighbours(x >> 1, y >> 1, A.up.w_px, A.up.h_px, A.up.pitch);
@@ -390,16 +405,12 @@ int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s)
         return SB_ERR_INVALID;
     }
     dim3 block(CF_BX, CF_BY), grid(div_up(A.rw, 2 * CF_BX), div_up(A.rh, 2 * CF_BY));
-    static const bool occ5 = [] {
-        const char *e = getenv("SB_COLLAPSE_OCC");
-        return e && e[0] == '5';
-    }();
     if (l == nb)
-        launch(k_collapse_fast<2, 4>, grid, block, 0, s, A);
+        launch(k_collapse_fast<2>, grid, block, 0, s, A);
     else if (l == 0)
-        launch(occ5 ? k_collapse_fast<0, 5> : k_collapse_fast<0, 4>, grid, block, 0, s, A);
+        launch(k_collapse_fast<0>, grid, block, 0, s, A);
     else
-        launch(occ5 ? k_collapse_fast<1, 5> : k_collapse_fast<1, 4>, grid, block, 0, s, A);
+        launch(k_collapse_fast<1>, grid, block, 0, s, A);
     return launch_check("k_collapse_fast");
 }
 

@@ -14,6 +14,8 @@
 #include "sb_shard.h"
 
 namespace sb {
+inline int rgbm_pitch_of(int w) { return (w + 31) & ~31; }
+
 int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, float *tab_dev, WarpJob *job, cudaStream_t s,
                   std::vector<float> &host_tab);
 }
@@ -39,7 +41,7 @@ struct sb_compositor {
     std::vector<WarpJob> jobs;         // host copy
     std::vector<WarpJob> jobsx[SB_PIPE_DEPTH - 1];  // the same jobs reading the extra source buffer sets (pipelined path)
     std::vector<uint8_t *> src_dev;    // u8x3 sources
-    std::vector<uint32_t *> rgbm_dev;  // warped, packed
+    std::vector<uint32_t *> rgbm_dev;  // warped, packed; row pitch = width rounded up to 32 pixels (128-byte rows)
     std::vector<float *> tab_dev;
     std::vector<uint8_t *> usermask_dev;
     int max_w = 0, max_h = 0;
@@ -160,14 +162,14 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         c->max_h = std::max(c->max_h, rect[3]);
         if (!mine(i)) continue;  // another rank warps this image: only its geometry is needed here
         SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
-        SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rect[2] * rect[3] * 4, s));
-        SB_TRY(dev_alloc((void **)&c->tab_dev[i], ((size_t)2 * rect[2] + 2 * rect[3]) * sizeof(float), s));
+        SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rgbm_pitch_of(rect[2]) * rect[3] * 4, s));
+        SB_TRY(dev_alloc((void **)&c->tab_dev[i], warp_table_floats(rect[2], rect[3]) * sizeof(float), s));
         SB_TRY(make_warp_job(p, rect, c->src_w[i], c->src_h[i], c->tab_dev[i], &c->jobs[i], s, host_tab));
         SB_CUDA(cudaStreamSynchronize(s));  // host_tab is reused by the next image
         c->jobs[i].src = c->src_dev[i];
         c->jobs[i].spitch = (long long)c->src_w[i] * 3;
         c->jobs[i].dst_rgbm = c->rgbm_dev[i];
-        c->jobs[i].rgbm_pitch = rect[2];
+        c->jobs[i].rgbm_pitch = rgbm_pitch_of(rect[2]);
         c->warp_bytes += 3.0 * c->src_w[i] * c->src_h[i] + 4.0 * rect[2] * rect[3];
     }
 
@@ -185,7 +187,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         f.tlx = c->rects[i].x;
         f.tly = c->rects[i].y;
         f.rgbm = c->rgbm_dev[i];
-        f.rgbm_pitch = c->rects[i].w;
+        f.rgbm_pitch = rgbm_pitch_of(c->rects[i].w);
         SB_TRY(c->plan.add_feed(f));
     }
     int out_w = roi.w;
@@ -593,12 +595,13 @@ int sb_compositor_download_warped(sb_compositor *c, int i, uint8_t *dst, size_t 
         return SB_ERR_INVALID;
     }
     const int w = c->rects[i].w, h = c->rects[i].h;
-    std::vector<uint32_t> tmp((size_t)w * h);
+    const size_t wp = (size_t)rgbm_pitch_of(w);
+    std::vector<uint32_t> tmp(wp * h);
     SB_CUDA(cudaMemcpyAsync(tmp.data(), c->rgbm_dev[i], tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(cudaStreamSynchronize(c->stream));
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
-            const uint32_t p = tmp[(size_t)y * w + x];
+            const uint32_t p = tmp[(size_t)y * wp + x];
             if (dst) {
                 uint8_t *d = dst + (size_t)y * dst_pitch + (size_t)x * 3;
                 d[0] = p & 255;

@@ -136,6 +136,23 @@ int sb_device_copy(void *dst, const void *src, size_t bytes)
     return SB_OK;
 }
 
+int sb_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *mismatches)
+{
+    SB_TRY(sb::ensure_device());
+    if (!mismatches || mode < 0 || mode > 1) {
+        sb::set_error("sb_selftest_division: bad arguments");
+        return SB_ERR_INVALID;
+    }
+    unsigned long long *bad = nullptr;
+    SB_TRY(sb::dev_alloc((void **)&bad, sizeof *bad, sb::g_stream));
+    SB_CUDA(cudaMemsetAsync(bad, 0, sizeof *bad, sb::g_stream));
+    int rc = sb::launch_selftest_division(n, seed, mode, bad, sb::g_stream);
+    if (rc == SB_OK && cudaMemcpyAsync(mismatches, bad, sizeof *bad, cudaMemcpyDeviceToHost, sb::g_stream) != cudaSuccess) rc = SB_ERR_CUDA;
+    if (rc == SB_OK && cudaStreamSynchronize(sb::g_stream) != cudaSuccess) rc = SB_ERR_CUDA;
+    sb::dev_free(bad, sb::g_stream);
+    return rc;
+}
+
 void *sb_host_alloc(size_t bytes)
 {
     if (sb::ensure_device() != SB_OK) return nullptr;

@@ -74,7 +74,11 @@ struct WarpJob {
     const float *colX, *colZ, *rowA, *rowY;
     float k[9];
     int always_divide;  // plane / affine: x/z, y/z unconditionally
+    float xin_hi, yin_hi;  // 32 (sw-1) - 0.5, 32 (sh-1) - 0.5: upper limits of x*32, y*32 for a footprint inside the image
 };
+
+// floats in the device tables of a w x h warp: colX, colZ (each padded to a multiple of 4), rowA, rowY
+inline size_t warp_table_floats(int w, int h) { return (size_t)2 * ((w + 3) & ~3) + (size_t)2 * h; }
 
 // one pyramid level of one fed image: planar int16 x3 + float32 weights
 struct Level {
@@ -176,5 +180,6 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
+int launch_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *bad_dev, cudaStream_t s);
 
 }  // namespace sb

@@ -1,4 +1,5 @@
 // sb_util.cu -- small utility kernels (L2 flush for benchmarking hygiene).
+#include "sb_device.cuh"
 #include "sb_launch.h"
 
 namespace sb {
@@ -9,7 +10,50 @@ __global__ void k_flush(uint4 *p, size_t n, unsigned v)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) p[i] = make_uint4(v, v, v, v);
 }
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// rcp_refined / fdiv_by (sb_device.cuh) against __fdiv_rn over the ranges their callers guarantee:
+// mode 0 (warp kernel): b in [2^-60, 2^60], a = 0 or |a / b| in about [2^-40, 2^60], random signs and mantissas;
+// mode 1 (collapse kernel): a an int16 value, b = w + 1e-5 with w a sum of up to 256 weights in [0, 1].
+__global__ void k_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *bad)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, local = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned long long h = mix64(seed + i), h2 = mix64(h);
+        float a, b;
+        if (mode == 0) {
+            const int be = (int)(h % 121) - 60, qe = (int)((h >> 8) % 101) - 40;
+            b = __uint_as_float(((unsigned)(be + 127) << 23) | ((unsigned)(h >> 20) & 0x7fffffu));
+            a = __uint_as_float(((unsigned)(be + qe + 127) << 23) | ((unsigned)(h2 >> 20) & 0x7fffffu) | ((unsigned)(h2 & 1) << 31));
+            if (b > 0x1p60f) b = 0x1p60f;
+            if ((h2 >> 1) % 61 == 0) a = 0.f;
+        } else {
+            a = (float)((int)(h % 65536) - 32768);
+            const unsigned k = (unsigned)(h2 % 5);
+            float w = k == 0 ? 0.f : k == 1 ? 1.f : k == 2 ? 2.f : __uint_as_float(0x3f800000u | ((unsigned)(h2 >> 8) & 0x7fffffu)) - 1.f;
+            if (k == 4) w = __fmul_rn(w, (float)((h2 >> 40) % 256 + 1));
+            b = __fadd_rn(w, 1e-5f);
+        }
+        const float q = fdiv_by(a, b, rcp_refined(b)), ref = __fdiv_rn(a, b);
+        local += (__float_as_uint(q) != __float_as_uint(ref)) && !(q == 0.f && ref == 0.f);
+    }
+    if (local) atomicAdd(bad, local);
+}
 }  // namespace
+
+int launch_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *bad_dev, cudaStream_t s)
+{
+    launch(k_selftest_division, dim3(148 * 8), dim3(256), 0, s, n, seed, mode, bad_dev);
+    return launch_check("k_selftest_division");
+}
 
 // overwrite a buffer larger than L2 so that the next kernel starts from a cold cache
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s)

@@ -127,9 +127,7 @@ __device__ __forceinline__ void fetch_pair(const uint8_t *__restrict__ src, unsi
     }
 }
 
-// RGBM_ONLY: the compositor's case -- packed output only and source sides <= 32767, where int16 saturation can
-// neither move a coordinate across the inside test nor touch a footprint that lies inside the image.
-template <bool RGBM_ONLY>
+// Generic fast variant (sb_warp with separate image / mask outputs, sources wider than int16): one pixel per thread.
 __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_constant__ WarpBatch B)
 {
     const WarpJob &j = B.j[blockIdx.z];
@@ -140,23 +138,14 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_con
 
     float x, y;
     project(j, u, v, x, y);
-    unsigned m;
-    if (RGBM_ONLY) {
-        m = ((unsigned)cvt_rn_x86(x) < (unsigned)sw && (unsigned)cvt_rn_x86(y) < (unsigned)sh) ? 255u : 0u;
-    } else {
-        const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
-        m = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255u : 0u;
-        if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
-        if (!j.dst_rgb && !j.dst_rgbm) return;
-    }
+    const int nx = sat_s16(cvt_rn_x86(x)), ny = sat_s16(cvt_rn_x86(y));
+    const unsigned m = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? 255u : 0u;
+    if (j.dst_mask) j.dst_mask[(long long)v * j.mask_pitch + u] = (uint8_t)m;
+    if (!j.dst_rgb && !j.dst_rgbm) return;
 
     const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
     const int fx = sx & 31, fy = sy & 31;
-    int ix = sx >> 5, iy = sy >> 5;
-    if (!RGBM_ONLY) {
-        ix = sat_s16(ix);
-        iy = sat_s16(iy);
-    }
+    const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
     unsigned a0, a1, b0, b1;
     const unsigned pitch = (unsigned)j.spitch;  // coordinates are int16-saturated: offsets stay below 2^32
     if ((unsigned)ix < (unsigned)(sw - 1) && (unsigned)iy < (unsigned)(sh - 1)) {
@@ -165,8 +154,6 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_con
         fetch_pair(j.src, off, ix, ix + 1, a0, a1);
         fetch_pair(j.src, off + pitch, ix, ix + 1, b0, b1);
     } else {
-        ix = sat_s16(ix);
-        iy = sat_s16(iy);
         const int x0 = reflect(ix, sw), x1 = reflect(ix + 1, sw);
         const int y0 = reflect(iy, sh), y1 = reflect(iy + 1, sh);
         fetch_pair(j.src, (unsigned)y0 * pitch, x0, x1, a0, a1);
@@ -183,12 +170,136 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_wide(const __grid_con
     const unsigned r = ((h0rb & 0xffffu) * hy + (h1rb & 0xffffu) * gy + 512u) >> 10;
     const unsigned b = ((h0rb >> 16) * hy + (h1rb >> 16) * gy + 512u) >> 10;
     const unsigned g = (h0g * hy + h1g * gy + 512u) >> 10;
-    if (RGBM_ONLY) {
-        if (j.blend_mask) m = j.blend_mask[(unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u];
-        j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
+    store_pixel(j, u, v, r, g, b, m);
+}
+
+// ---- the compositor's kernel: packed RGBM output only, source sides <= 32767 (int16 saturation can then neither
+// move a coordinate across the inside test nor touch a footprint that lies inside the image), TWO horizontally
+// adjacent output pixels per thread (descriptor reads, row tables and the k*y_ products are shared; 8-byte table
+// loads and stores).
+
+// six bytes starting at src + off as two words (bytes 0-3, bytes 4-7): three aligned 4-byte loads and two funnel
+// shifts, no selects.  Reads at most 11 bytes past the aligned start (SB_SRC_PAD covers the end of the image).
+__device__ __forceinline__ void fetch6(const uint8_t *__restrict__ src, unsigned off, unsigned &lo, unsigned &hi)
+{
+    const unsigned long long addr = (unsigned long long)src + off;
+    const unsigned *q = reinterpret_cast<const unsigned *>(addr & ~3ull);
+    const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const unsigned sh = ((unsigned)addr & 3u) * 8u;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+// the bilinear sum of a 2x2 footprint given as rows of six bytes (l = bytes 0-3, h = bytes 4-7): two exact lerps as
+// above; PRMT places red|blue (per row) and green (both rows) into 16-bit lanes, the vertical lerp is a two-way
+// 16x8-bit dot product (IDP.2A) per channel.  Returns r | g<<8 | b<<16.
+template <bool DP2A>
+__device__ __forceinline__ unsigned lerp6(unsigned l0, unsigned h0, unsigned l1, unsigned h1, unsigned fx, unsigned fy)
+{
+    h0 &= 0xffffu;
+    h1 &= 0xffffu;
+    const unsigned hx = 32u - fx, hy = 32u - fy;
+    const unsigned rb0 = __byte_perm(l0, h0, 0x7270) * hx + __byte_perm(l0, h0, 0x7573) * fx;  // [r | b<<16] of row 0
+    const unsigned rb1 = __byte_perm(l1, h1, 0x7270) * hx + __byte_perm(l1, h1, 0x7573) * fx;
+    const unsigned g01 = (__byte_perm(l0, l1, 0x5511) & 0x00ff00ffu) * hx + __byte_perm(h0, h1, 0x6420) * fx;  // [row0 | row1<<16]
+    unsigned r, g, b;
+    if (DP2A) {
+        const unsigned wy = hy | (fy << 8);
+        r = __dp2a_lo(__byte_perm(rb0, rb1, 0x5410), wy, 512u);
+        b = __dp2a_lo(__byte_perm(rb0, rb1, 0x7632), wy, 512u);
+        g = __dp2a_lo(g01, wy, 512u);
     } else {
-        store_pixel(j, u, v, r, g, b, m);
+        r = (rb0 & 0xffffu) * hy + (rb1 & 0xffffu) * fy + 512u;
+        b = (rb0 >> 16) * hy + (rb1 >> 16) * fy + 512u;
+        g = (g01 & 0xffffu) * hy + (g01 >> 16) * fy + 512u;
     }
+    return (r >> 10) | ((g >> 2) & 0xff00u) | ((b << 6) & 0xff0000u);
+}
+
+// the general rule for one pixel, from the projected numerators: exact division, x86 rounding, int16 saturation,
+// BORDER_REFLECT, validity from the nearest-neighbour test.  Called for the few pixels the streamlined path of
+// k_warp_rgbm does not cover (footprint on the border or outside, z <= 0, values outside the shortcut's ranges).
+__device__ __noinline__ unsigned sample_general(const uint8_t *__restrict__ src, int sw, int sh, unsigned pitch, float x, float y,
+                                                float z, int always_divide)
+{
+    if (always_divide || z > 0.f) {
+        x = fdiv(x, z);
+        y = fdiv(y, z);
+    } else {
+        x = -1.f;
+        y = -1.f;
+    }
+    const unsigned m = ((unsigned)cvt_rn_x86(x) < (unsigned)sw && (unsigned)cvt_rn_x86(y) < (unsigned)sh) ? 255u : 0u;
+    const int sx = cvt_rn_x86(fmul(x, 32.f)), sy = cvt_rn_x86(fmul(y, 32.f));
+    const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
+    const int x0 = reflect(ix, sw), x1 = reflect(ix + 1, sw);
+    const int y0 = reflect(iy, sh), y1 = reflect(iy + 1, sh);
+    unsigned a0, a1, b0, b1;
+    fetch_pair(src, (unsigned)y0 * pitch, x0, x1, a0, a1);
+    fetch_pair(src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    // as six-byte rows: left pixel in bytes 0-2, right pixel in bytes 3-5
+    return lerp6<false>(a0 | (a1 << 24), a1 >> 8, b0 | (b1 << 24), b1 >> 8, (unsigned)sx & 31u, (unsigned)sy & 31u) | (m << 24);
+}
+
+template <bool HAS_BM, bool DP2A>
+__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_rgbm(const __grid_constant__ WarpBatch B)
+{
+    const WarpJob &j = B.j[blockIdx.z];
+    const int u = 2 * (blockIdx.x * WARP_BX + threadIdx.x);
+    const int v = blockIdx.y * WARP_BY + threadIdx.y;
+    if (u >= j.dw || v >= j.dh) return;
+    // column tables are padded to an even length and 8-byte aligned (warp_table_floats)
+    const float2 cx = __ldg(reinterpret_cast<const float2 *>(j.colX + u)), cz = __ldg(reinterpret_cast<const float2 *>(j.colZ + u));
+    const float ra = __ldg(j.rowA + v), ry = __ldg(j.rowY + v);
+    const float ty0 = fmul(j.k[1], ry), ty1 = fmul(j.k[4], ry), ty2 = fmul(j.k[7], ry);
+    const unsigned pitch = (unsigned)j.spitch;
+    float xn[2], yn[2], zn[2], x32[2], y32[2];
+    bool fast = true;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const float x_ = fmul(ra, p ? cx.y : cx.x), z_ = fmul(ra, p ? cz.y : cz.x);
+        xn[p] = fadd(fadd(fmul(j.k[0], x_), ty0), fmul(j.k[2], z_));
+        yn[p] = fadd(fadd(fmul(j.k[3], x_), ty1), fmul(j.k[5], z_));
+        zn[p] = fadd(fadd(fmul(j.k[6], x_), ty2), fmul(j.k[8], z_));
+        const float rr = rcp_refined(zn[p]);
+        x32[p] = fmul(fdiv_by(xn[p], zn[p], rr), 32.f);
+        y32[p] = fmul(fdiv_by(yn[p], zn[p], rr), 32.f);
+        // The streamlined path: z in the shortcut division's range (which implies z > 0) and the 2x2 footprint inside
+        // the image, i.e. 0 <= cvRound(32x) >> 5 <= sw-2, decided on the floats: cvRound is half-even and the upper
+        // threshold 32(sw-1)-0.5 is exact and rounds up to the even 32(sw-1).  The lower threshold is 2^-30 rather
+        // than -0.5, which keeps zero and tiny quotients (outside the shortcut's range) out; the sliver in between,
+        // 1/32 of the first source column, takes the general path.  NaN fails every test.  In this region x lies in
+        // (0, sw-1-1/64), so the nearest-neighbour validity test holds as well: the mask byte is 255.
+        fast = fast && zn[p] >= 0x1p-60f && zn[p] <= 0x1p60f && x32[p] >= 0x1p-30f && x32[p] < j.xin_hi && y32[p] >= 0x1p-30f &&
+               y32[p] < j.yin_hi;
+    }
+    unsigned out[2];
+    if (fast) {
+        unsigned l0[2], h0[2], l1[2], h1[2], sx[2], sy[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            sx[p] = (unsigned)__float2int_rn(x32[p]);
+            sy[p] = (unsigned)__float2int_rn(y32[p]);
+            const unsigned off = (sy[p] >> 5) * pitch + 3u * (sx[p] >> 5);
+            fetch6(j.src, off, l0[p], h0[p]);
+            fetch6(j.src, off + pitch, l1[p], h1[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) out[p] = lerp6<DP2A>(l0[p], h0[p], l1[p], h1[p], sx[p] & 31u, sy[p] & 31u) | 0xff000000u;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) out[p] = sample_general(j.src, j.sw, j.sh, pitch, xn[p], yn[p], zn[p], j.always_divide);
+    }
+    if (HAS_BM) {
+        const uint8_t *bm = j.blend_mask + (unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u;
+        out[0] = (out[0] & 0xffffffu) | ((unsigned)bm[0] << 24);
+        if (u + 1 < j.dw) out[1] = (out[1] & 0xffffffu) | ((unsigned)bm[1] << 24);
+    }
+    uint32_t *d = j.dst_rgbm + (unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u;  // pitch is a multiple of 64: 8-byte aligned
+    if (u + 1 < j.dw)
+        *reinterpret_cast<uint2 *>(d) = make_uint2(out[0], out[1]);
+    else
+        d[0] = out[0];
 }
 #endif  // SB_EMU
 
@@ -221,13 +332,22 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), cnt);
 #ifndef SB_EMU
         if (!use_simple_kernels()) {
-            bool rgbm_only = true;
-            for (int i = 0; i < cnt; ++i)
-                rgbm_only = rgbm_only && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767;
-            if (rgbm_only)
-                launch(k_warp_wide<true>, grid, block, 0, s, B);
-            else
-                launch(k_warp_wide<false>, grid, block, 0, s, B);
+            bool rgbm_only = true, has_bm = false;
+            for (int i = 0; i < cnt; ++i) {
+                rgbm_only = rgbm_only && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767 &&
+                            B.j[i].sw >= 2 && B.j[i].sh >= 2 && B.j[i].rgbm_pitch % 2 == 0;
+                has_bm = has_bm || B.j[i].blend_mask;
+            }
+            for (int i = 0; i < cnt; ++i) rgbm_only = rgbm_only && (!has_bm || B.j[i].blend_mask);  // all or none
+            if (rgbm_only) {
+                dim3 grid2(div_up(max_w, 2 * WARP_BX), div_up(max_h, WARP_BY), cnt);
+                if (has_bm)
+                    launch(k_warp_rgbm<true, true>, grid2, block, 0, s, B);
+                else
+                    launch(k_warp_rgbm<false, true>, grid2, block, 0, s, B);
+            } else {
+                launch(k_warp_wide, grid, block, 0, s, B);
+            }
             SB_TRY(launch_check("k_warp_wide"));
             continue;
         }

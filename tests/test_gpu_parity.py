@@ -47,6 +47,17 @@ def test_native_library_is_the_one_running(cuda_lib):
         assert "libstitch_b200.so" in f.read()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_shared_reciprocal_division_is_the_ieee_division(cuda_lib, mode):
+    """The warp and collapse kernels divide through one refined reciprocal per pixel (sb_device.cuh); over the operand
+    ranges they guarantee it must be the IEEE quotient bit for bit: 2^32 pseudo-random pairs per mode on the device."""
+    import ctypes as C
+
+    bad = C.c_ulonglong(123)
+    assert cuda_lib.sb_selftest_division(1 << 32, 2026 + mode, mode, C.byref(bad)) == 0
+    assert bad.value == 0, f"mode {mode}: {bad.value} of 2^32 quotients differ from __fdiv_rn"
+
+
 def test_warper_goldens(cuda_lib):
     replay.run_warper_goldens(Warper)
 

@@ -64,6 +64,11 @@ def test_unit_weight_shortcuts_are_exact():
     den = np.float32(1.0) + np.float32(1e-5)
     q = (a.astype(np.float32) / den).astype(np.float32)
     assert np.array_equal(np.trunc(q).astype(np.int32), a - np.sign(a))
+    # weight sum exactly 2: (short)trunc(a / fl(2 + 1e-5f)) == (|a| - 1) / 2 toward zero, signed
+    den2 = np.float32(2.0) + np.float32(1e-5)
+    q2 = (a.astype(np.float32) / den2).astype(np.float32)
+    t = a - np.sign(a)
+    assert np.array_equal(np.trunc(q2).astype(np.int32), (t + (t < 0)) >> 1)
     assert np.float32(255.0) * np.float32(1.0 / 255.0) == np.float32(1.0)  # a 255 mask byte is weight exactly 1
     assert np.array_equal(np.trunc(a.astype(np.float32) * np.float32(1.0)).astype(np.int32), a)
 
