@@ -52,7 +52,7 @@ __device__ __forceinline__ void up_quad(const int16_t *__restrict__ S, const Nbr
     const int cols[3] = {q.xp, q.xc, q.xn};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int a0 = S[q.rp + cols[k]], a1 = S[q.rc + cols[k]], a2 = S[q.rn + cols[k]];
+        const int a0 = __ldg(S + q.rp + cols[k]), a1 = __ldg(S + q.rc + cols[k]), a2 = __ldg(S + q.rn + cols[k]);
         e[k] = a0 + a2 + 6 * a1;
         o[k] = a1 + a2;
     }
@@ -76,18 +76,32 @@ __device__ __forceinline__ int norm16(int acc, float den, float rr)
 
 // LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
 template <int LV>
-__global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_constant__ CollapseArgs A)
+__global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
     const ColDesc *__restrict__ col = A.col;
     const int n = A.n;
     const int tile_x = A.rx0 + blockIdx.x * (2 * CF_BX), tile_y = A.ry0 + blockIdx.y * (2 * CF_BY);
 #ifndef SB_EMU
-    __shared__ unsigned char cover[SB_MAX_ITEMS];
-    for (int i = threadIdx.y * CF_BX + threadIdx.x; i < n; i += CF_BX * CF_BY) {
-        const int4 r = __ldg(reinterpret_cast<const int4 *>(&col[i].ox));
-        cover[i] = tile_x < r.x + r.z && tile_x + 2 * CF_BX > r.x && tile_y < r.y + r.w && tile_y + 2 * CF_BY > r.y;
+    // the items whose rect touches this tile, in feed order: warp 0 compacts them into shared memory
+    __shared__ unsigned short list[SB_MAX_ITEMS];
+    __shared__ int list_n;
+    if (threadIdx.y == 0) {
+        int cnt = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + threadIdx.x;
+            bool c = false;
+            if (i < n) {
+                const int4 r = __ldg(reinterpret_cast<const int4 *>(&col[i].ox));
+                c = tile_x < r.x + r.z && tile_x + 2 * CF_BX > r.x && tile_y < r.y + r.w && tile_y + 2 * CF_BY > r.y;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            if (c) list[cnt + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)i;
+            cnt += __popc(m);
+        }
+        if (threadIdx.x == 0) list_n = cnt;
     }
     __syncthreads();
+    const int n_cover = list_n;
 #endif
     const int x = tile_x + 2 * threadIdx.x, y = tile_y + 2 * threadIdx.y;  // top-left pixel of the quad
     if (x >= A.rx0 + A.rw || y >= A.ry0 + A.rh) return;
@@ -100,11 +114,13 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
 
     int acc[2][2][3] = {};
     float wsum[2][2] = {};
-    for (int i = 0; i < n; ++i) {
 #ifndef SB_EMU
-        if (!cover[i]) continue;
-#endif
+    for (int k = 0; k < n_cover; ++k) {
+        const ColDesc &d = col[list[k]];
+#else
+    for (int i = 0; i < n; ++i) {
         const ColDesc &d = col[i];
+#endif
         const int4 r = __ldg(reinterpret_cast<const int4 *>(&d.ox));
         const int X = x - r.x, Y = y - r.y;
         bool in[2][2];
@@ -292,8 +308,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const int a = (int)(short)acc[dy][dx][c];
-                    const int t = a - (a > 0) + (a < 0);
-                    nrm[dy][dx][c] = (t + (int)((unsigned)t >> 31)) >> 1;
+                    nrm[dy][dx][c] = (a - ((a >> 31) | 1)) / 2;  // a == 0: -1 / 2 == 0
                 }
     } else {
         float rr[2][2];
@@ -351,6 +366,34 @@ __global__ void __launch_bounds__(CF_BX *CF_BY) k_collapse_fast(const __grid_con
     }
     // level 0: mask, zero outside it, crop to the roi / the rank's strip, |v| saturated to uint8 (convertScaleAbs)
     const PanoOut &out = A.out;
+    // the usual case (launch-uniform test): image + mask, even pitches and origin, buffers below 4 GB -- 32-bit offsets
+    // and 2-byte stores; a quad whose two columns are both stored takes it
+    const bool plain = out.rgb && out.mask && !out.s16 && ((out.rgb_pitch | out.mask_pitch | A.out_x0) & 1) == 0 &&
+                       out.rgb_pitch * out.h < (1ll << 32);
+    if (plain && x >= A.out_lo && x + 1 < A.out_hi) {
+        const unsigned xo = (unsigned)(x - A.out_x0);
+        unsigned o_rgb = (unsigned)y * (unsigned)out.rgb_pitch + 3u * xo, o_m = (unsigned)y * (unsigned)out.mask_pitch + xo;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            if (y + dy < out.h) {
+                const bool on0 = wsum[dy][0] > SB_WEIGHT_EPS, on1 = wsum[dy][1] > SB_WEIGHT_EPS;
+                unsigned b[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    b[c] = on0 ? (unsigned)min(abs(v[dy][0][c]), 255) : 0u;
+                    b[3 + c] = on1 ? (unsigned)min(abs(v[dy][1][c]), 255) : 0u;
+                }
+                unsigned short *p2 = reinterpret_cast<unsigned short *>(out.rgb + o_rgb);
+                p2[0] = (unsigned short)(b[0] | (b[1] << 8));
+                p2[1] = (unsigned short)(b[2] | (b[3] << 8));
+                p2[2] = (unsigned short)(b[4] | (b[5] << 8));
+                *reinterpret_cast<unsigned short *>(out.mask + o_m) = (unsigned short)((on0 ? 255u : 0u) | (on1 ? 0xff00u : 0u));
+            }
+            o_rgb += (unsigned)out.rgb_pitch;
+            o_m += (unsigned)out.mask_pitch;
+        }
+        return;
+    }
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
         if (y + dy >= out.h) continue;
