@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(CL_BX *CL_BY)
         float wt;
         load_level(im, l, X, Y, g, wt);
         if (l < nb) {
-            const Level &U = im.lv[l + 1];
+            int up[3];
+            pyrup_level_at(im.lv[l + 1], w_l >> 1, h_l >> 1, X, Y, up);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) g[c] = sat_s16(g[c] - pyrup_at(U.g + c * U.plane, U.pitch, w_l >> 1, h_l >> 1, X, Y));
+            for (int c = 0; c < 3; ++c) g[c] = sat_s16(g[c] - up[c]);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) acc[c] += f2s_wrap(fmul((float)g[c], wt));
@@ -200,10 +201,10 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
 {
     int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
     if (gw <= 0 || gh <= 0) return SB_OK;
-    // the fast kernel reads level 0 through the packed RGBM layout and needs at least one band
+    // the fast kernel works on byte-fed images (RGBM level 0, lane-pair levels) and needs at least one band
     bool packed = true;
     for (int i = 0; i < n; ++i) packed = packed && imgs_host[i].rgbm != nullptr;
-    if (!use_simple_kernels() && nb >= 1 && (l > 0 || packed)) {
+    if (!use_simple_kernels() && nb >= 1 && packed) {
         CollapseArgs A;
         std::memset(&A, 0, sizeof A);
         A.col = col;

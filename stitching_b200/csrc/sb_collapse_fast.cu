@@ -62,6 +62,37 @@ __device__ __forceinline__ void up_quad(const int16_t *__restrict__ S, const Nbr
     u[1][1] = (o[1] + o[2] + 2) >> 2;
 }
 
+// two signed 16-bit lanes in one word
+__device__ __forceinline__ unsigned lanes(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ int lane_lo(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int lane_hi(unsigned v) { return (int)v >> 16; }
+
+// The same pyrUp for a fed image's level stored as lane pairs (x = r | b << 16, y = g; all bytes): red and blue go
+// through the column sums and the final sums as two lanes of one word -- the largest intermediate, 64 * 255 + 32,
+// stays below 2^15, so the lanes never meet.  Results: u_rb = r | b << 16, u_g = g, each 0..255.
+__device__ __forceinline__ void up_quad_lanes(const uint2 *__restrict__ S, const Nbr &q, unsigned u_rb[2][2], unsigned u_g[2][2])
+{
+    unsigned e_rb[3], o_rb[3], e_g[3], o_g[3];
+    const int cols[3] = {q.xp, q.xc, q.xn};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint2 a0 = __ldg(S + q.rp + cols[k]), a1 = __ldg(S + q.rc + cols[k]), a2 = __ldg(S + q.rn + cols[k]);
+        e_rb[k] = a0.x + a2.x + 6u * a1.x;
+        o_rb[k] = a1.x + a2.x;
+        e_g[k] = a0.y + a2.y + 6u * a1.y;
+        o_g[k] = a1.y + a2.y;
+    }
+    const unsigned M = 0x00ff00ffu;
+    u_rb[0][0] = ((e_rb[0] + e_rb[2] + 6u * e_rb[1] + 0x00200020u) >> 6) & M;
+    u_rb[0][1] = ((e_rb[1] + e_rb[2] + 0x00080008u) >> 4) & M;
+    u_rb[1][0] = ((o_rb[0] + o_rb[2] + 6u * o_rb[1] + 0x00080008u) >> 4) & M;
+    u_rb[1][1] = ((o_rb[1] + o_rb[2] + 0x00020002u) >> 2) & M;
+    u_g[0][0] = (e_g[0] + e_g[2] + 6u * e_g[1] + 32u) >> 6;
+    u_g[0][1] = (e_g[1] + e_g[2] + 8u) >> 4;
+    u_g[1][0] = (o_g[0] + o_g[2] + 6u * o_g[1] + 8u) >> 4;
+    u_g[1][1] = (o_g[1] + o_g[2] + 2u) >> 2;
+}
+
 __device__ __forceinline__ int trunc16(float v) { return (int)(short)__float2int_rz(v); }  // |v| < 2^31 here
 
 // the blend step for one channel: (short)trunc((short)acc / den), x86 cast semantics.  The three channels of a pixel
@@ -112,7 +143,10 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) pv[dy][dx] = LV != 2 || (x + dx < A.rx0 + A.rw && y + dy < A.ry0 + A.rh);
 
-    int acc[2][2][3] = {};
+    // the accumulators (int16 with wrap-around in the reference): red | blue << 16 as two lanes of one word, added
+    // with the lane-wise VIADD.16x2 (exactly the wrap-around of a short); green in the low half of an int
+    unsigned acc_rb[2][2] = {};
+    int acc_g[2][2] = {};
     float wsum[2][2] = {};
 #ifndef SB_EMU
     for (int k = 0; k < n_cover; ++k) {
@@ -140,7 +174,7 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_
             if (!any) continue;
         }
         const int4 s1 = __ldg(reinterpret_cast<const int4 *>(&d.top));      // top, pitch, plane, upitch
-        const int4 s2 = __ldg(reinterpret_cast<const int4 *>(&d.uplane));   // uplane, kind, -, -
+        const int4 s2 = __ldg(reinterpret_cast<const int4 *>(&d.pad0));     // -, kind, -, -
         if (s2.y == 1) {
             // a slab of partial sums from another rank: add (int16 wrap-around, float in rank order)
 #pragma unroll
@@ -149,14 +183,14 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_
                 for (int dx = 0; dx < 2; ++dx) {
                     if (!in[dy][dx]) continue;
                     const int o = (Y + dy) * s1.y + X + dx;
-                    acc[dy][dx][0] += d.g[o];
-                    acc[dy][dx][1] += d.g[s1.z + o];
-                    acc[dy][dx][2] += d.g[2 * s1.z + o];
+                    acc_rb[dy][dx] = __vadd2(acc_rb[dy][dx], lanes(d.g[o], d.g[2 * s1.z + o]));
+                    acc_g[dy][dx] += d.g[s1.z + o];
                     wsum[dy][dx] = fadd(wsum[dy][dx], d.w[o]);
                 }
             continue;
         }
-        int g[2][2][3];
+        // the level's own colours as lanes: g_rb = r | b << 16, g_g = green (bytes at every level, see sb_internal.h)
+        unsigned g_rb[2][2], g_g[2][2];
         float wt[2][2];
         if (LV == 0) {
             const int4 s0 = __ldg(reinterpret_cast<const int4 *>(&d.rgbm_pitch));  // rgbm_pitch, iw, ih, left
@@ -176,79 +210,79 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    g[dy][dx][0] = p[dy][dx] & 255u;
-                    g[dy][dx][1] = (p[dy][dx] >> 8) & 255u;
-                    g[dy][dx][2] = (p[dy][dx] >> 16) & 255u;
+                    g_rb[dy][dx] = p[dy][dx] & 0x00ff00ffu;
+                    g_g[dy][dx] = (p[dy][dx] >> 8) & 255u;
                     wt[dy][dx] = fmul((float)(p[dy][dx] >> 24), SB_INV255);
                 }
         } else if (LV == 1) {
-            const int o0 = Y * s1.y + X;  // X even: the pairs are 4- / 8-byte aligned
+            const int o0 = Y * s1.y + X;  // X even: the pairs are 8- / 16-byte aligned
             const float2 w0 = __ldg(reinterpret_cast<const float2 *>(d.w + o0));
             const float2 w1 = __ldg(reinterpret_cast<const float2 *>(d.w + o0 + s1.y));
             if (w0.x == 0.f && w0.y == 0.f && w1.x == 0.f && w1.y == 0.f) continue;  // contributes exactly nothing
             wt[0][0] = w0.x; wt[0][1] = w0.y; wt[1][0] = w1.x; wt[1][1] = w1.y;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const unsigned a = __ldg(reinterpret_cast<const unsigned *>(d.g + c * s1.z + o0));
-                const unsigned b = __ldg(reinterpret_cast<const unsigned *>(d.g + c * s1.z + o0 + s1.y));
-                g[0][0][c] = (short)(a & 0xffffu); g[0][1][c] = (int)a >> 16;
-                g[1][0][c] = (short)(b & 0xffffu); g[1][1][c] = (int)b >> 16;
-            }
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(d.q + o0));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(d.q + o0 + s1.y));
+            g_rb[0][0] = a.x; g_g[0][0] = a.y; g_rb[0][1] = a.z; g_g[0][1] = a.w;
+            g_rb[1][0] = b.x; g_g[1][0] = b.y; g_rb[1][1] = b.z; g_g[1][1] = b.w;
         } else {
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     wt[dy][dx] = 0.f;
-                    g[dy][dx][0] = g[dy][dx][1] = g[dy][dx][2] = 0;
+                    g_rb[dy][dx] = g_g[dy][dx] = 0u;
                     if (!in[dy][dx]) continue;
                     const int o = (Y + dy) * s1.y + X + dx;
                     wt[dy][dx] = d.w[o];
-                    g[dy][dx][0] = d.g[o];
-                    g[dy][dx][1] = d.g[s1.z + o];
-                    g[dy][dx][2] = d.g[2 * s1.z + o];
+                    const uint2 v = __ldg(d.q + o);
+                    g_rb[dy][dx] = v.x;
+                    g_g[dy][dx] = v.y;
                 }
         }
+        // Laplacian = level - pyrUp(next level); both are bytes, the difference fits a signed 16-bit lane (and the
+        // reference's saturation to int16 can never act)
+        unsigned lap_rb[2][2];
+        int lap_g[2][2];
         if (LV != 2) {
             const Nbr q = neighbours(X >> 1, Y >> 1, r.z >> 1, r.w >> 1, s1.w);
-            const int16_t *ug = d.ug;
-            // all four weights exactly 1 (the interior of a full-weight image): (short)trunc(L * 1.0f) == L
-            const bool unit = wt[0][0] == 1.f && wt[0][1] == 1.f && wt[1][0] == 1.f && wt[1][1] == 1.f;
+            unsigned u_rb[2][2], u_g[2][2];
+            up_quad_lanes(d.uq, q, u_rb, u_g);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                int u[2][2];
-                up_quad(ug + c * s2.x, q, u);
+            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        int lap = g[dy][dx][c] - u[dy][dx];
-                        if (LV != 0) lap = sat_s16(lap);  // bytes minus an average of bytes cannot leave int16
-                        g[dy][dx][c] = lap;
-                    }
-            }
-            if (unit) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += g[dy][dx][c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += trunc16(fmul((float)g[dy][dx][c], wt[dy][dx]));
-            }
+                for (int dx = 0; dx < 2; ++dx) {
+                    lap_rb[dy][dx] = __vsub2(g_rb[dy][dx], u_rb[dy][dx]);
+                    lap_g[dy][dx] = (int)g_g[dy][dx] - (int)u_g[dy][dx];
+                }
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    lap_rb[dy][dx] = g_rb[dy][dx];
+                    lap_g[dy][dx] = (int)g_g[dy][dx];
+                }
+        }
+        // all four weights exactly 1 (the interior of a full-weight image): (short)trunc(L * 1.0f) == L
+        const bool unit = LV != 2 && wt[0][0] == 1.f && wt[0][1] == 1.f && wt[1][0] == 1.f && wt[1][1] == 1.f;
+        if (unit) {
 #pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) acc[dy][dx][c] += trunc16(fmul((float)g[dy][dx][c], wt[dy][dx]));
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    acc_rb[dy][dx] = __vadd2(acc_rb[dy][dx], lap_rb[dy][dx]);
+                    acc_g[dy][dx] += lap_g[dy][dx];
+                }
+        } else {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int tr = trunc16(fmul((float)lane_lo(lap_rb[dy][dx]), wt[dy][dx]));
+                    const int tb = trunc16(fmul((float)lane_hi(lap_rb[dy][dx]), wt[dy][dx]));
+                    acc_rb[dy][dx] = __vadd2(acc_rb[dy][dx], lanes(tr, tb));
+                    acc_g[dy][dx] += trunc16(fmul((float)lap_g[dy][dx], wt[dy][dx]));
+                }
         }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
@@ -264,15 +298,24 @@ __global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_
             for (int dx = 0; dx < 2; ++dx) {
                 if (!pv[dy][dx]) continue;
                 const int o = (y + dy - A.ry0) * A.slab_pitch + (x + dx - A.rx0);
-                A.slab_acc[o] = (int16_t)acc[dy][dx][0];
-                A.slab_acc[A.slab_plane + o] = (int16_t)acc[dy][dx][1];
-                A.slab_acc[2 * A.slab_plane + o] = (int16_t)acc[dy][dx][2];
+                A.slab_acc[o] = (int16_t)lane_lo(acc_rb[dy][dx]);
+                A.slab_acc[A.slab_plane + o] = (int16_t)acc_g[dy][dx];
+                A.slab_acc[2 * A.slab_plane + o] = (int16_t)lane_hi(acc_rb[dy][dx]);
                 A.slab_w[o] = wsum[dy][dx];
             }
         return;
     }
 
     // blend step + collapse: v = sat16(pyrUp(C_{l+1}) + (short)trunc(acc / (wsum + eps)))
+    int acc[2][2][3];  // the three accumulators of each pixel as sign-extended shorts
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            acc[dy][dx][0] = lane_lo(acc_rb[dy][dx]);
+            acc[dy][dx][1] = (int)(short)acc_g[dy][dx];
+            acc[dy][dx][2] = lane_hi(acc_rb[dy][dx]);
+        }
     int v[2][2][3];
     float den[2][2];
 #pragma unroll

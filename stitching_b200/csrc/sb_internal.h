@@ -81,11 +81,16 @@ struct WarpJob {
 inline size_t warp_table_floats(int w, int h) { return (size_t)2 * ((w + 3) & ~3) + (size_t)2 * h; }
 
 // one pyramid level of one fed image: planar int16 x3 + float32 weights
+// Two colour layouts.  An image fed as bytes (RGBM) keeps every Gaussian level inside 0..255 (the 5x5 weights sum
+// to 256), so its levels are stored as LANE PAIRS: q[y*pitch + x] = (r | b << 16, g), 8 bytes per pixel -- red and
+// blue travel as two 16-bit lanes of one word through every filter (no lane ever carries: 256*255+128 < 2^16).
+// A generic int16 feed (arbitrary values) keeps planar int16 and is served by the simple kernels only.
 struct Level {
-    int16_t *g;        // [3][h][pitch]
+    uint2 *q;          // [h][pitch] lane pairs, or null
+    int16_t *g;        // [3][h][pitch] planar, or null
     float *w;          // [h][pitch]
     int w_px, h_px;    // level size
-    int pitch;         // elements, both for g rows and w rows
+    int pitch;         // elements, for q / g rows and w rows
     long long plane;   // elements between colour planes of g
 };
 
@@ -111,23 +116,26 @@ struct FeedImage {
 struct alignas(16) ColDesc {       // collapse of level l
     int ox, oy, w_l, h_l;          // padded rect of the image at level l, pano level coordinates
     const uint32_t *rgbm;          // level 0: packed fed image
-    const int16_t *g;              // level l >= 1: colour planes
-    const float *w;                //              weights
-    const int16_t *ug;             // level l+1 colour planes (null at the top level)
+    union {
+        const uint2 *q;            // kind 0, level l >= 1: colour lane pairs
+        const int16_t *g;          // kind 1: the slab's three int16 planes of partial sums
+    };
+    const float *w;                // weights (kind 1: weight sums)
+    const uint2 *uq;               // level l+1 colour lane pairs (null at the top level)
     int rgbm_pitch, iw, ih, left;  // level 0: image size and origin inside the padded rect
-    int top, pitch, plane, upitch; // level l / l+1 pitches and plane strides, in elements
-    int uplane, kind, pad1, pad2;  // kind 0: a fed image; 1: a slab of partial sums (g = acc planes, w = weight sums)
+    int top, pitch, plane, upitch; // level l / l+1 pitches, in elements; plane: stride of a slab's planes
+    int pad0, kind, pad1, pad2;    // kind 0: a fed image; 1: a slab of partial sums
 };
 struct alignas(16) PyrDesc {       // pyrDown of level l -> l+1
-    int sw, sh, dpitch, dplane;    // source level size; destination pitch / plane stride (elements)
+    int sw, sh, dpitch, pad3;      // source level size; destination pitch (elements)
     const uint32_t *rgbm;          // level 0 source
-    const int16_t *sg;             // level >= 1 source planes
+    const uint2 *sq;               // level >= 1 source lane pairs
     const float *swt;
-    int16_t *dg;
+    uint2 *dq;
     float *dwt;
     int rgbm_pitch, iw;
     int ih, left, top, spitch;
-    int splane, pad0, pad1, pad2;
+    int pad0, pad1, pad2, pad4;
 };
 
 struct PanoLevel {

@@ -165,7 +165,8 @@ int BlendPlan::allocate(cudaStream_t s)
             if (!active(i)) continue;  // another rank owns this image: geometry only
             for (int l = 1; l <= nb; ++l) {
                 const int w = imgs[i].pw >> l, h = imgs[i].ph >> l, pitch = level_pitch(w);
-                slots[i][l].g = carve((size_t)3 * h * pitch * sizeof(int16_t));
+                // byte-fed images: lane pairs (8 bytes per pixel); generic int16 feeds: three int16 planes
+                slots[i][l].g = carve(imgs[i].rgbm ? (size_t)h * pitch * sizeof(uint2) : (size_t)3 * h * pitch * sizeof(int16_t));
                 slots[i][l].w = carve((size_t)h * pitch * sizeof(float));
             }
         }
@@ -192,7 +193,8 @@ int BlendPlan::allocate(cudaStream_t s)
                 L.h_px = imgs[i].ph >> l;
                 L.pitch = level_pitch(L.w_px);
                 L.plane = (long long)L.h_px * L.pitch;
-                L.g = active(i) ? (int16_t *)(base + slots[i][l].g) : nullptr;
+                L.q = active(i) && imgs[i].rgbm ? (uint2 *)(base + slots[i][l].g) : nullptr;
+                L.g = active(i) && !imgs[i].rgbm ? (int16_t *)(base + slots[i][l].g) : nullptr;
                 L.w = active(i) ? (float *)(base + slots[i][l].w) : nullptr;
             }
         for (int l = 1; l <= nb; ++l) {
@@ -232,15 +234,13 @@ int BlendPlan::allocate(cudaStream_t s)
                 c.left = im.left;
                 c.top = im.top;
                 if (l >= 1) {
-                    c.g = im.lv[l].g;
+                    c.q = im.lv[l].q;
                     c.w = im.lv[l].w;
                     c.pitch = im.lv[l].pitch;
-                    c.plane = (int)im.lv[l].plane;
                 }
                 if (l < nb) {
-                    c.ug = im.lv[l + 1].g;
+                    c.uq = im.lv[l + 1].q;
                     c.upitch = im.lv[l + 1].pitch;
-                    c.uplane = (int)im.lv[l + 1].plane;
                 }
                 PyrDesc &p = pyr[(size_t)l * n + i];
                 std::memset(&p, 0, sizeof p);
@@ -254,15 +254,13 @@ int BlendPlan::allocate(cudaStream_t s)
                     p.left = im.left;
                     p.top = im.top;
                     if (l >= 1) {
-                        p.sg = im.lv[l].g;
+                        p.sq = im.lv[l].q;
                         p.swt = im.lv[l].w;
                         p.spitch = im.lv[l].pitch;
-                        p.splane = (int)im.lv[l].plane;
                     }
-                    p.dg = im.lv[l + 1].g;
+                    p.dq = im.lv[l + 1].q;
                     p.dwt = im.lv[l + 1].w;
                     p.dpitch = im.lv[l + 1].pitch;
-                    p.dplane = (int)im.lv[l + 1].plane;
                 }
             }
         if (n) {

@@ -53,9 +53,8 @@ __global__ void __launch_bounds__(PD_BX *PD_BY) k_pyrdown_gather(const FeedImage
     }
     const Level &D = im.lv[l + 1];
     const long long o = (long long)y * D.pitch + x;
-    D.g[o] = (int16_t)((acc[0] + 128) >> 8);
-    D.g[D.plane + o] = (int16_t)((acc[1] + 128) >> 8);
-    D.g[2 * D.plane + o] = (int16_t)((acc[2] + 128) >> 8);
+    const int out[3] = {(acc[0] + 128) >> 8, (acc[1] + 128) >> 8, (acc[2] + 128) >> 8};
+    store_colours(D, o, out);
     D.w[o] = tap5_v(rowf[0], rowf[1], rowf[2], rowf[3], rowf[4], v_simd);
 }
 
@@ -71,10 +70,10 @@ int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const 
     // max_w / max_h: largest DESTINATION level size among the images of the batch
     if (count <= 0 || max_w <= 0 || max_h <= 0) return SB_OK;
 #ifndef SB_EMU
-    // the fast kernel reads level 0 through the packed RGBM layout; generic int16 feeds use the gather kernel
+    // the fast kernel works on byte-fed images (RGBM level 0, lane-pair levels); generic int16 feeds use the gather kernel
     bool packed = true;
     for (int i = first; i < first + count; ++i) packed = packed && imgs_host[i].rgbm != nullptr;
-    if (!use_simple_kernels() && (l > 0 || packed)) return launch_pyrdown_fast(pyr + first, imgs_host + first, count, l, max_w, max_h, s);
+    if (!use_simple_kernels() && packed) return launch_pyrdown_fast(pyr + first, imgs_host + first, count, l, max_w, max_h, s);
 #else
     (void)imgs_host; (void)pyr;
 #endif

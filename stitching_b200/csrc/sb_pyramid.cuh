@@ -38,6 +38,31 @@ __device__ __forceinline__ void load_level0(const FeedImage &im, int X, int Y, i
     wt = inside ? fmul((float)m, SB_INV255) : 0.f;
 }
 
+// the three colours of element o of a level >= 1, either layout (sb_internal.h: lane pairs or planar int16)
+__device__ __forceinline__ void load_colours(const Level &L, long long o, int c[3])
+{
+    if (L.q) {
+        const uint2 v = L.q[o];
+        c[0] = (int)(v.x & 0xffffu);
+        c[1] = (int)v.y;
+        c[2] = (int)(v.x >> 16);
+    } else {
+        c[0] = L.g[o];
+        c[1] = L.g[L.plane + o];
+        c[2] = L.g[2 * L.plane + o];
+    }
+}
+__device__ __forceinline__ void store_colours(const Level &L, long long o, const int c[3])
+{
+    if (L.q) {
+        L.q[o] = make_uint2((unsigned)c[0] | ((unsigned)c[2] << 16), (unsigned)c[1]);  // bytes: see sb_internal.h
+    } else {
+        L.g[o] = (int16_t)c[0];
+        L.g[L.plane + o] = (int16_t)c[1];
+        L.g[2 * L.plane + o] = (int16_t)c[2];
+    }
+}
+
 // sample of level l (l >= 0) at level-rect coordinates (X, Y) inside the level
 __device__ __forceinline__ void load_level(const FeedImage &im, int l, int X, int Y, int c[3], float &wt)
 {
@@ -47,9 +72,7 @@ __device__ __forceinline__ void load_level(const FeedImage &im, int l, int X, in
     }
     const Level &L = im.lv[l];
     const long long o = (long long)Y * L.pitch + X;
-    c[0] = L.g[o];
-    c[1] = L.g[L.plane + o];
-    c[2] = L.g[2 * L.plane + o];
+    load_colours(L, o, c);
     wt = L.w[o];
 }
 
@@ -62,10 +85,7 @@ __device__ __forceinline__ void load_level_rgb(const FeedImage &im, int l, int X
         return;
     }
     const Level &L = im.lv[l];
-    const long long o = (long long)Y * L.pitch + X;
-    c[0] = L.g[o];
-    c[1] = L.g[L.plane + o];
-    c[2] = L.g[2 * L.plane + o];
+    load_colours(L, (long long)Y * L.pitch + X, c);
 }
 
 // pyrUp tap geometry along one axis for destination index d of a 2x upsample of n samples:
@@ -97,6 +117,25 @@ __device__ __forceinline__ int pyrup_at(const int16_t *__restrict__ S, int pitch
     const int hc = tx.wp * rc[tx.ip] + tx.wc * rc[tx.ic] + tx.wn * rc[tx.in];
     const int hn = tx.wp * rn[tx.ip] + tx.wc * rn[tx.ic] + tx.wn * rn[tx.in];
     return (ty.wp * hp + ty.wc * hc + ty.wn * hn + 32) >> 6;
+}
+
+// the same for the three colours of a fed image's level (either layout), destination pixel (x, y) of level l
+__device__ __forceinline__ void pyrup_level_at(const Level &U, int sw, int sh, int x, int y, int out[3])
+{
+    const UpTap tx = up_tap(x, sw), ty = up_tap(y, sh);
+    const int xs[3] = {tx.ip, tx.ic, tx.in}, xw[3] = {tx.wp, tx.wc, tx.wn};
+    const int ys[3] = {ty.ip, ty.ic, ty.in}, yw[3] = {ty.wp, ty.wc, ty.wn};
+    int acc[3] = {0, 0, 0};
+    for (int j = 0; j < 3; ++j) {
+        int h[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i) {
+            int c[3];
+            load_colours(U, (long long)ys[j] * U.pitch + xs[i], c);
+            for (int k = 0; k < 3; ++k) h[k] += xw[i] * c[k];
+        }
+        for (int k = 0; k < 3; ++k) acc[k] += yw[j] * h[k];
+    }
+    for (int k = 0; k < 3; ++k) out[k] = (acc[k] + 32) >> 6;
 }
 
 // float 5-tap [1 4 6 4 1] with the two summation orders of the reference build (4-lane SSE body vs scalar

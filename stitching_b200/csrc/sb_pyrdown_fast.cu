@@ -16,7 +16,8 @@
 //     filter passes (5x5 weights sum to 256, 256*255+128 < 2^16, so a lane never carries into its neighbour);
 //     each lane converts its own two mask bytes to float (2^23 mantissa trick, exact, keeps the XU pipe free) and
 //     the weights travel by shuffle as well;
-//   levels >= 1 (planar int16 + float32): pairs are single 4-/8-byte loads.
+//   levels >= 1 (lane pairs r|b<<16, g per pixel + float32 weights): the own pair is one 16-byte load and the colours
+//     run through the same two-lane arithmetic; every level is written as lane pairs (one 8-byte store per pixel).
 // The float summation orders (position dependent, sb_pyramid.cuh) are per-lane constants.
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
@@ -38,8 +39,8 @@ __device__ __forceinline__ float byte3_to_float(unsigned p)
 
 struct Raw0 { unsigned p2, p3; };                 // own pair of packed pixels (mask byte cleared outside the image)
 struct H0 { unsigned rb, gm; float w; };
-struct Raw1 { unsigned pr[3]; float2 wp; };       // own pairs: three int16 planes + weights
-struct H1 { int r, g, b; float w; };
+struct Raw1 { uint2 p2, p3; float2 wp; };         // own pair of lane-pair pixels + weights
+struct H1 { unsigned rb, g; float w; };
 
 template <bool L0>
 __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
@@ -58,11 +59,10 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
     // every descriptor field goes to registers once (the stores below could alias it otherwise)
     const int4 db = __ldg(reinterpret_cast<const int4 *>(&D.ih));          // ih, left, top, spitch
     const int2 dc = __ldg(reinterpret_cast<const int2 *>(&D.rgbm_pitch));  // rgbm_pitch, iw
-    const int splane = __ldg(&D.splane);
     const uint32_t *__restrict__ rgbm = D.rgbm;
-    const int16_t *__restrict__ sg = D.sg;
+    const uint2 *__restrict__ sq = D.sq;
     const float *__restrict__ swt = D.swt;
-    int16_t *__restrict__ dg = D.dg;
+    uint2 *__restrict__ dq = D.dq;
     float *__restrict__ dwt = D.dwt;
     const int ih = db.x, left = db.y, top = db.z, spitch = db.w, rgbm_pitch = dc.x, iw = dc.y;
 
@@ -108,41 +108,36 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
     auto fetch1 = [&](int src_row) -> Raw1 {
         const int ro = reflect101(src_row, sh) * spitch;
         Raw1 r;
-        if (pair_adjacent) {  // (2x, 2x+1): one 4-byte / 8-byte load per plane (true for every real column)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) r.pr[ch] = __ldg(reinterpret_cast<const unsigned *>(sg + ch * splane + ro + c2));
+        if (pair_adjacent) {  // (2x, 2x+1): one 16-byte / 8-byte load (true for every real column)
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(sq + ro + c2));
+            r.p2 = make_uint2(v.x, v.y);
+            r.p3 = make_uint2(v.z, v.w);
             r.wp = __ldg(reinterpret_cast<const float2 *>(swt + ro + c2));
         } else {              // a reflected virtual column
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const int16_t *row = sg + ch * splane + ro;
-                r.pr[ch] = (unsigned)(unsigned short)__ldg(row + c2) | ((unsigned)(unsigned short)__ldg(row + c3) << 16);
-            }
+            r.p2 = __ldg(sq + ro + c2);
+            r.p3 = __ldg(sq + ro + c3);
             r.wp.x = __ldg(swt + ro + c2);
             r.wp.y = __ldg(swt + ro + c3);
         }
         return r;
     };
     auto hpass1 = [&](const Raw1 &r) -> H1 {
-        int hs[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const unsigned pl = __shfl_up_sync(FULL, r.pr[ch], 1), pn = __shfl_down_sync(FULL, r.pr[ch], 1);
-            const int v0 = (short)(pl & 0xffffu), v1 = (int)pl >> 16, v2 = (short)(r.pr[ch] & 0xffffu), v3 = (int)r.pr[ch] >> 16;
-            const int v4 = (short)(pn & 0xffffu);
-            hs[ch] = v0 + v4 + 4 * (v1 + v3) + 6 * v2;
+        H1 h;
+        {
+            const unsigned p0 = __shfl_up_sync(FULL, r.p2.x, 1), p1 = __shfl_up_sync(FULL, r.p3.x, 1), p4 = __shfl_down_sync(FULL, r.p2.x, 1);
+            h.rb = p0 + p4 + 4u * (p1 + r.p3.x) + 6u * r.p2.x;
+        }
+        {
+            const unsigned p0 = __shfl_up_sync(FULL, r.p2.y, 1), p1 = __shfl_up_sync(FULL, r.p3.y, 1), p4 = __shfl_down_sync(FULL, r.p2.y, 1);
+            h.g = p0 + p4 + 4u * (p1 + r.p3.y) + 6u * r.p2.y;
         }
         const float w0 = __shfl_up_sync(FULL, r.wp.x, 1), w1 = __shfl_up_sync(FULL, r.wp.y, 1);
         const float w4 = __shfl_down_sync(FULL, r.wp.x, 1);
-        H1 h;
-        h.r = hs[0];
-        h.g = hs[1];
-        h.b = hs[2];
         h.w = tap5_h(w0, w1, r.wp.x, r.wp.y, w4, h_simd);
         return h;
     };
 
-    const int dpitch = da.z, dplane = da.w;
+    const int dpitch = da.z;
     if (L0) {
         H0 h0 = hpass0(fetch0(2 * y_begin - 2)), h1 = hpass0(fetch0(2 * y_begin - 1)), h2 = hpass0(fetch0(2 * y_begin));
         Raw0 ra = fetch0(2 * y_begin + 1), rb = fetch0(2 * y_begin + 2);
@@ -157,9 +152,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
                 const unsigned vrb = h0.rb + h4.rb + 4u * (h1.rb + h3.rb) + 6u * h2.rb + 0x00800080u;
                 const unsigned vgm = h0.gm + h4.gm + 4u * (h1.gm + h3.gm) + 6u * h2.gm + 0x00800080u;
                 const int o = y * dpitch + x;
-                dg[o] = (int16_t)((vrb >> 8) & 0xffu);
-                dg[dplane + o] = (int16_t)((vgm >> 8) & 0xffu);
-                dg[2 * dplane + o] = (int16_t)(vrb >> 24);
+                dq[o] = make_uint2((vrb >> 8) & 0x00ff00ffu, (vgm >> 8) & 0xffu);
                 dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
             }
             h0 = h2;
@@ -179,10 +172,10 @@ __global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *_
             }
             const H1 h3 = hpass1(ra), h4 = hpass1(rb);
             if (stores) {
+                const unsigned vrb = h0.rb + h4.rb + 4u * (h1.rb + h3.rb) + 6u * h2.rb + 0x00800080u;
+                const unsigned vg = h0.g + h4.g + 4u * (h1.g + h3.g) + 6u * h2.g + 128u;
                 const int o = y * dpitch + x;
-                dg[o] = (int16_t)((h0.r + h4.r + 4 * (h1.r + h3.r) + 6 * h2.r + 128) >> 8);
-                dg[dplane + o] = (int16_t)((h0.g + h4.g + 4 * (h1.g + h3.g) + 6 * h2.g + 128) >> 8);
-                dg[2 * dplane + o] = (int16_t)((h0.b + h4.b + 4 * (h1.b + h3.b) + 6 * h2.b + 128) >> 8);
+                dq[o] = make_uint2((vrb >> 8) & 0x00ff00ffu, vg >> 8);
                 dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
             }
             h0 = h2;

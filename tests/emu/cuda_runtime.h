@@ -21,12 +21,16 @@ enum { cudaStreamNonBlocking = 1 };
 enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
 struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
-struct uint4 { unsigned x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(8) float2 { float x, y; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+// lane-wise 16-bit add / subtract with wrap-around (VIADD.16x2)
+static inline unsigned __vadd2(unsigned a, unsigned b) { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }
+static inline unsigned __vsub2(unsigned a, unsigned b) { return ((a - b) & 0xffffu) | (((a >> 16) - (b >> 16)) << 16); }
 
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
