@@ -107,7 +107,7 @@ __device__ __forceinline__ int norm16(int acc, float den, float rr)
 
 // LV: 0 = level 0 (packed RGBM images), 1 = a middle level, 2 = the top level (no pyrUp anywhere, odd sizes allowed)
 template <int LV>
-__global__ void __launch_bounds__(CF_BX *CF_BY, 4) k_collapse_fast(const __grid_constant__ CollapseArgs A)
+__global__ void __launch_bounds__(CF_BX *CF_BY, 5) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
     const ColDesc *__restrict__ col = A.col;
     const int n = A.n;

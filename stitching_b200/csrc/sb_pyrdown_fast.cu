@@ -43,7 +43,7 @@ struct Raw1 { uint2 p2, p3; float2 wp; };         // own pair of lane-pair pixel
 struct H1 { unsigned rb, g; float w; };
 
 template <bool L0>
-__global__ void __launch_bounds__(32 * WK_WARPS) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
+__global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
 {
     const PyrDesc &D = descs[blockIdx.z];
     const int4 da = __ldg(reinterpret_cast<const int4 *>(&D.sw));  // sw, sh, dpitch, dplane
