@@ -42,7 +42,9 @@ struct H0 { unsigned rb, gm; float w; };
 struct Raw1 { uint2 p2, p3; float2 wp; };         // own pair of lane-pair pixels + weights
 struct H1 { unsigned rb, g; float w; };
 
-template <bool L0>
+// NEAR: every row index the walk produces is at most one reflection away from its range (the launcher checks the
+// geometry of all images of the batch): the border rules are two selects instead of an integer modulo per row.
+template <bool L0, bool NEAR>
 __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
 {
     const PyrDesc &D = descs[blockIdx.z];
@@ -84,9 +86,9 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
     const bool v_simd = x < (dw / 4) * 4;
 
     auto fetch0 = [&](int src_row) -> Raw0 {
-        const int iy = reflect101(src_row, sh) - top;
+        const int iy = (NEAR ? reflect101_once(src_row, sh) : reflect101(src_row, sh)) - top;
         const unsigned rowkeep = (unsigned)iy < (unsigned)ih ? 0xffffffffu : 0x00ffffffu;
-        const uint32_t *row = rgbm + reflect(iy, ih) * rgbm_pitch;
+        const uint32_t *row = rgbm + (NEAR ? reflect_once(iy, ih) : reflect(iy, ih)) * rgbm_pitch;
         Raw0 r;
         r.p2 = __ldg(row + c2) & keep2 & rowkeep;  // outside the fed image the weight is 0: 0 * (1/255) == 0 exactly
         r.p3 = __ldg(row + c3) & keep3 & rowkeep;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
         return h;
     };
     auto fetch1 = [&](int src_row) -> Raw1 {
-        const int ro = reflect101(src_row, sh) * spitch;
+        const int ro = (NEAR ? reflect101_once(src_row, sh) : reflect101(src_row, sh)) * spitch;
         Raw1 r;
         if (pair_adjacent) {  // (2x, 2x+1): one 16-byte / 8-byte load (true for every real column)
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(sq + ro + c2));
@@ -197,10 +199,22 @@ int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int coun
     int rows = 32;
     while (rows > 4 && strips / rows < 16384) rows >>= 1;
     dim3 block(32, WK_WARPS), grid(div_up(max_w, WK_COLS), div_up(div_up(max_h, rows), WK_WARPS), count);
-    if (l == 0)
-        launch(k_pyrdown_walk<true>, grid, block, 0, s, pyr, rows);
+    // single-reflection border rules: source rows run from -2 to sh+1 (needs sh >= 4); at level 0 the padded rect may
+    // not reach further beyond the fed image than the image is high
+    bool near = true;
+    for (int i = 0; i < count; ++i) {
+        const FeedImage &im = imgs_host[i];
+        near = near && (im.ph >> l) >= 4;
+        if (l == 0) near = near && im.top <= im.h && im.ph - im.top - im.h <= im.h;
+    }
+    if (l == 0 && near)
+        launch(k_pyrdown_walk<true, true>, grid, block, 0, s, pyr, rows);
+    else if (l == 0)
+        launch(k_pyrdown_walk<true, false>, grid, block, 0, s, pyr, rows);
+    else if (near)
+        launch(k_pyrdown_walk<false, true>, grid, block, 0, s, pyr, rows);
     else
-        launch(k_pyrdown_walk<false>, grid, block, 0, s, pyr, rows);
+        launch(k_pyrdown_walk<false, false>, grid, block, 0, s, pyr, rows);
     return launch_check("k_pyrdown_walk");
 }
 #else

@@ -242,7 +242,7 @@ __device__ __noinline__ unsigned sample_general(const uint8_t *__restrict__ src,
 }
 
 template <bool HAS_BM, bool DP2A>
-__global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_rgbm(const __grid_constant__ WarpBatch B)
+__global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_constant__ WarpBatch B)
 {
     const WarpJob &j = B.j[blockIdx.z];
     const int u = 2 * (blockIdx.x * WARP_BX + threadIdx.x);
