@@ -475,10 +475,11 @@ def run_sharded(args, rank, local_rank, world):
                 "workload": f"cfg3 family: {n}x{w}x{h} RGB, cylindrical warp + multiband blend, ONE panorama sharded over {world} GPUs "
                             f"({per_gpu} images per GPU; N=8 is BASELINE configs[2])" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""),
                 "images_per_gpu": per_gpu, "pano": [comp.roi[2], comp.roi[3]], "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
-                "parallelism": f"{world} GPUs: image blocks per rank, pano column strips per rank, one grouped NCCL send/recv of "
-                               f"the per-band partial sums ({slab_total / 1e6:.1f} MB per step in total)",
+                "parallelism": f"{world} GPUs: image blocks per rank, pano column strips per rank, grouped NCCL send/recv of the "
+                               f"per-band partial sums in two parts on a communication stream, overlapped with the kernels "
+                               f"({slab_total / 1e6:.1f} MB per step in total)",
                 "l2": f"no flush: each rank streams its {per_gpu * src_bytes / 1e6:.0f} MB of sources every step (> 126 MB L2)",
-                "timed": "plan built once; a step = warp + pyramids + partial sums + NCCL exchange + collapse of the own strip",
+                "timed": "plan built once; a step = warp + pyramids + partial sums + NCCL exchange (level-0 slabs leave after the first pyrDown) + collapse of the own strip",
             },
             "clocks": clocks,
             "e2e": {"value": total_mpix * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -68,6 +68,9 @@ struct sb_compositor {
     // multi-GPU: this process composites images [first, first + count) and one column strip of the panorama
     bool sharded = false;
     int first = 0, count = 0;
+    // the slab exchange runs on its own stream, in two parts, beside the kernels (see compositor_enqueue_kernels)
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t e_part[2] = {}, e_xchg[2] = {};  // partial sums of part k written / part k received
     ShardPlan shard;
 };
 
@@ -100,6 +103,14 @@ static void compositor_free(sb_compositor *c)
     }
     if (c->h2d) (void)cudaStreamDestroy(c->h2d);
     if (c->d2h) (void)cudaStreamDestroy(c->d2h);
+    if (c->comm_stream) {
+        (void)cudaStreamSynchronize(c->comm_stream);
+        (void)cudaStreamDestroy(c->comm_stream);
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (c->e_part[k]) (void)cudaEventDestroy(c->e_part[k]);
+        if (c->e_xchg[k]) (void)cudaEventDestroy(c->e_xchg[k]);
+    }
 #ifndef SB_EMU
     for (auto &g : c->graph_exec)
         if (g) (void)cudaGraphExecDestroy(g);
@@ -250,21 +261,27 @@ static int compositor_enqueue(sb_compositor *c, bool events, int slot = 0)
     return compositor_enqueue_kernels(c, events, slot);
 }
 
-// sharded step, local part: pyramids of the own images, then the partial sums every neighbour needs
-static int shard_local(sb_compositor *c, cudaStream_t s, const std::function<int(const std::string &)> &mark)
+// sharded step: pyrDown of level l -> l+1 for the own images
+static int shard_pyrdown(sb_compositor *c, cudaStream_t s, int l)
 {
     BlendPlan &P = c->plan;
     const int n = (int)P.imgs.size();
-    for (int l = 0; l < P.nb; ++l) {
-        int mw = 0, mh = 0;
-        for (int i = c->first; i < c->first + c->count; ++i) {
-            mw = std::max(mw, P.imgs[i].pw >> (l + 1));
-            mh = std::max(mh, P.imgs[i].ph >> (l + 1));
-        }
-        SB_TRY(launch_pyrdown(P.imgs_dev, P.imgs.data(), P.pyr_dev + (size_t)l * n, c->first, c->count, l, mw, mh, s));
+    int mw = 0, mh = 0;
+    for (int i = c->first; i < c->first + c->count; ++i) {
+        mw = std::max(mw, P.imgs[i].pw >> (l + 1));
+        mh = std::max(mh, P.imgs[i].ph >> (l + 1));
+    }
+    return launch_pyrdown(P.imgs_dev, P.imgs.data(), P.pyr_dev + (size_t)l * n, c->first, c->count, l, mw, mh, s);
+}
+
+// sharded step, local part: pyramids of the own images, then the partial sums every neighbour needs
+static int shard_local(sb_compositor *c, cudaStream_t s, const std::function<int(const std::string &)> &mark)
+{
+    for (int l = 0; l < c->plan.nb; ++l) {
+        SB_TRY(shard_pyrdown(c, s, l));
         SB_TRY(mark("pyrdown_l" + std::to_string(l)));
     }
-    SB_TRY(c->shard.partial_out(P, s));
+    SB_TRY(c->shard.partial_out(c->plan, s));
     SB_TRY(mark("partial_out"));
     return SB_OK;
 }
@@ -293,11 +310,41 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
     SB_TRY(mark("warp"));
     const PanoOut &out = slot ? c->outx[slot - 1] : c->out;
     if (!c->sharded) return c->plan.run(out, s, events ? std::function<int(const std::string &)>(mark) : nullptr);
-    SB_TRY(shard_local(c, s, std::function<int(const std::string &)>(mark)));
-    SB_TRY(c->shard.exchange(s));
-    SB_TRY(mark("exchange"));
-    SB_TRY(c->shard.finish(c->plan, out, s));
-    SB_TRY(mark("finish"));
+    // The exchange overlaps the kernels.  Level 0 of the partial sums -- three quarters of the bytes -- needs only the
+    // first pyrDown, and the collapse reads it last: its slabs travel on the communication stream while the rest of the
+    // pyramid, the coarser partial sums, their (small) exchange and the collapse of levels nb..1 run.
+    if (!c->comm_stream) {
+        SB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            SB_CUDA(cudaEventCreateWithFlags(&c->e_part[k], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&c->e_xchg[k], cudaEventDisableTiming));
+        }
+    }
+    BlendPlan &P = c->plan;
+    SB_TRY(shard_pyrdown(c, s, 0));
+    SB_TRY(mark("pyrdown_l0"));
+    SB_TRY(c->shard.partial_out(P, s, 0, 0));
+    SB_TRY(mark("partial_l0"));
+    SB_CUDA(cudaEventRecord(c->e_part[0], s));
+    SB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->e_part[0], 0));
+    SB_TRY(c->shard.exchange(c->comm_stream, 0));
+    SB_CUDA(cudaEventRecord(c->e_xchg[0], c->comm_stream));
+    for (int l = 1; l < P.nb; ++l) {
+        SB_TRY(shard_pyrdown(c, s, l));
+        SB_TRY(mark("pyrdown_l" + std::to_string(l)));
+    }
+    SB_TRY(c->shard.partial_out(P, s, 1, P.nb));
+    SB_TRY(mark("partial_coarse"));
+    SB_CUDA(cudaEventRecord(c->e_part[1], s));
+    SB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->e_part[1], 0));
+    SB_TRY(c->shard.exchange(c->comm_stream, 1));
+    SB_CUDA(cudaEventRecord(c->e_xchg[1], c->comm_stream));
+    SB_CUDA(cudaStreamWaitEvent(s, c->e_xchg[1], 0));
+    SB_TRY(c->shard.finish(P, out, s, P.nb, 1));
+    SB_TRY(mark("finish_coarse"));  // includes waiting for the coarse slabs of the neighbours
+    SB_CUDA(cudaStreamWaitEvent(s, c->e_xchg[0], 0));
+    SB_TRY(c->shard.finish(P, out, s, 0, 0));
+    SB_TRY(mark("finish_l0"));      // includes waiting for the level-0 slabs
     return SB_OK;
 }
 

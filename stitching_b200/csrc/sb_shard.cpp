@@ -39,6 +39,7 @@ void ShardPlan::slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab 
     block_of((int)plan.imgs.size(), world, src, &f0, &fc);
     size_t off = 0;
     std::memset(ps->lv, 0, sizeof ps->lv);
+    ps->split = 0;
     for (int l = 0; l <= plan.nb; ++l) {
         SlabLevel &L = ps->lv[l];
         if (fc == 0) continue;
@@ -71,6 +72,7 @@ void ShardPlan::slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab 
         off = align_up(off + (size_t)3 * L.plane * sizeof(int16_t), 256);
         L.w_off = off;
         off = align_up(off + (size_t)L.plane * sizeof(float), 256);
+        if (l == 0) ps->split = off;
     }
     ps->bytes = off;
 }
@@ -184,12 +186,12 @@ void ShardPlan::release(cudaStream_t s)
     items_arena_ = nullptr;
 }
 
-int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s)
+int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo, int l_hi)
 {
     const int n = (int)plan.imgs.size();
     for (int p = 0; p < world; ++p) {
         if (p == rank || !send[p].bytes) continue;
-        for (int l = 0; l <= plan.nb; ++l) {
+        for (int l = std::max(l_lo, 0); l <= std::min(l_hi, plan.nb); ++l) {
             const SlabLevel &L = send[p].lv[l];
             if (L.w == 0) continue;
             CollapseArgs A;
@@ -211,28 +213,32 @@ int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s)
     return SB_OK;
 }
 
-int ShardPlan::exchange(cudaStream_t s)
+int ShardPlan::exchange(cudaStream_t s, int part)
 {
     std::vector<int> peers;
     std::vector<void *> sp, rp;
     std::vector<size_t> sb_, rb;
     for (int p = 0; p < world; ++p) {
         if (p == rank || (!send[p].bytes && !recv[p].bytes)) continue;
+        // byte range of the part: level 0 lies in front
+        const size_t s0 = part == 1 ? send[p].split : 0, s1 = part == 0 ? send[p].split : send[p].bytes;
+        const size_t r0 = part == 1 ? recv[p].split : 0, r1 = part == 0 ? recv[p].split : recv[p].bytes;
+        if (s1 <= s0 && r1 <= r0) continue;
         peers.push_back(p);
-        sp.push_back(send[p].buf);
-        sb_.push_back(send[p].bytes);
-        rp.push_back(recv[p].buf);
-        rb.push_back(recv[p].bytes);
+        sp.push_back((char *)send[p].buf + s0);
+        sb_.push_back(s1 > s0 ? s1 - s0 : 0);
+        rp.push_back((char *)recv[p].buf + r0);
+        rb.push_back(r1 > r0 ? r1 - r0 : 0);
     }
     if (peers.empty()) return SB_OK;
     return comm_exchange((int)peers.size(), peers.data(), sp.data(), sb_.data(), rp.data(), rb.data(), s);
 }
 
-int ShardPlan::finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s)
+int ShardPlan::finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s, int l_hi, int l_lo)
 {
     int lo, hi;
     strip(plan, &lo, &hi);
-    for (int l = plan.nb; l >= 0; --l) {
+    for (int l = std::min(l_hi, plan.nb); l >= std::max(l_lo, 0); --l) {
         int a, b;
         region_x(plan, rank, l, &a, &b);
         CollapseArgs A;

@@ -15,6 +15,7 @@ struct SlabLevel {
 struct PeerSlab {
     SlabLevel lv[SB_MAX_BANDS + 1];
     size_t bytes = 0;       // 0: no exchange with this peer in this direction
+    size_t split = 0;       // the level-0 part is [0, split), the coarser levels [split, bytes)
     void *buf = nullptr;    // device
 };
 
@@ -40,11 +41,15 @@ public:
     // output columns of this rank: [lo, hi) in pano-roi coordinates (hi <= roi.w; may be empty)
     void strip(const BlendPlan &plan, int *lo, int *hi) const;
     // phase 0: partial sums of the own images over every region a neighbour needs -> send slabs
-    int partial_out(const BlendPlan &plan, cudaStream_t s);
-    // the NCCL exchange of the slabs (grouped send/recv on stream s)
-    int exchange(cudaStream_t s);
+    // (levels l_lo .. l_hi only: level 0 needs just the first pyrDown, so its slabs -- three quarters of the bytes --
+    // can leave while the rest of the pyramid is still being built)
+    int partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo = 0, int l_hi = SB_MAX_BANDS);
+    // the NCCL exchange of the slabs (grouped send/recv on stream s); part 0: the level-0 part of every slab,
+    // part 1: the coarser levels, part -1: everything
+    int exchange(cudaStream_t s, int part = -1);
     // phase 1: sum slabs + own images in rank order, normalise, collapse the own strip; `out` is strip-local
-    int finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s);
+    // (levels l_hi down to l_lo)
+    int finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s, int l_hi = SB_MAX_BANDS, int l_lo = 0);
 
 private:
     void region_x(const BlendPlan &plan, int r, int l, int *a, int *b) const;
