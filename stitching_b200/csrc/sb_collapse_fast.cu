@@ -4,14 +4,16 @@
 // stitching/blender.py:41,46 -> MultiBandBlender::feed / ::blend), reorganised for the B200 SM, where the
 // profile showed the kernel to be issue-bound rather than HBM-bound:
 //   * one thread per 2x2 quad: the four pixels share the 3x3 neighbourhood of the coarser level, so each pyrUp
-//     (of the image's G_{l+1} and of the collapsed C_{l+1}) is 9 loads per channel per quad, evaluated through
-//     shared column sums;
+//     (of the image's G_{l+1} and of the collapsed C_{l+1}) is 9 taps per quad, evaluated through shared column sums;
+//   * the fed images' levels are byte-valued LANE PAIRS (sb_internal.h): red and blue run as two 16-bit lanes of
+//     one word through the pyrUp, the Laplacian and the accumulators (lane-wise VIADD.16x2 = the wrap-around of a
+//     short), a tap is one 8-byte load;
 //   * compact 16-byte-aligned descriptors (ColDesc) read with vector loads, 32-bit element offsets;
 //   * exact early-outs: a fed image whose four weights in the quad are all zero contributes
 //     (short)trunc(L * 0) = 0 and wsum + 0 = wsum, i.e. nothing -- at level 0 this is the whole padding ring
 //     (constant-0 border of the weight map) and everything outside the warped footprint (mask byte 0);
-//   * level 0 reads the packed RGBM layout; its colours are bytes, so the Laplacian cannot saturate there.
-// A block covers a 64x16 tile and first marks which items touch it; items are visited in feed order.
+//   * exact integer forms of the blend division for weight sums 0, 1 and 2, one refined reciprocal per pixel otherwise.
+// A block covers a 64x16 tile; warp 0 first compacts the items touching it (in feed order) into shared memory.
 //
 // Multi-GPU (one rank per GPU, images sharded over ranks): the same kernel runs in two more roles.  An item can
 // be a SLAB -- the partial sums (acc int16x3 wrap-around, wsum float32) another rank computed for its own images
