@@ -63,6 +63,9 @@ def lib():
         L.so_sb_feed.argtypes = [C.c_void_p, s16p, C.c_size_t, u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
         L.so_sb_blend.argtypes = [C.c_void_p, s16p, u8p]
         L.so_convert_scale_abs_s16.argtypes = [s16p, C.c_size_t, u8p]
+        L.so_dilate3x3_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
+        L.so_resize_linear_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.so_seam_resize.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.c_size_t, C.c_int, C.c_int, u8p]
         L.so_convert_scale_abs_s16.restype = None
         _lib = L
     return _lib
@@ -170,6 +173,36 @@ def convert_scale_abs(a):
     a = np.ascontiguousarray(a, np.int16)
     out = np.empty(a.shape, np.uint8)
     lib().so_convert_scale_abs_s16(_p(a, C.c_int16), a.size, _p(out, C.c_uint8))
+    return out
+
+
+def dilate3x3(a):
+    """cv.dilate(a, None) for a uint8 image."""
+    a = np.ascontiguousarray(a, np.uint8)
+    h, w = a.shape
+    out = np.empty((h, w), np.uint8)
+    lib().so_dilate3x3_u8(_p(a, C.c_uint8), a.strides[0], w, h, _p(out, C.c_uint8))
+    return out
+
+
+def resize_linear(a, size):
+    """cv.resize(a, size, interpolation=cv.INTER_LINEAR) for a uint8 image; size = (w, h)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    h, w = a.shape
+    out = np.empty((int(size[1]), int(size[0])), np.uint8)
+    lib().so_resize_linear_u8(_p(a, C.c_uint8), a.strides[0], w, h, int(size[0]), int(size[1]), _p(out, C.c_uint8))
+    return out
+
+
+def seam_resize(seam_mask, mask):
+    """SeamFinder.resize (seam_finder.py:38-43): dilate, bilinear resize to the mask's size, AND with the mask."""
+    seam_mask = np.ascontiguousarray(seam_mask, np.uint8)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    sh, sw = seam_mask.shape
+    h, w = mask.shape
+    out = np.empty((h, w), np.uint8)
+    lib().so_seam_resize(_p(seam_mask, C.c_uint8), seam_mask.strides[0], sw, sh, _p(mask, C.c_uint8), mask.strides[0], w, h,
+                         _p(out, C.c_uint8))
     return out
 
 

@@ -691,3 +691,107 @@ SO_API void so_convert_scale_abs_s16(const int16_t *src, size_t n, uint8_t *dst)
         dst[i] = (uint8_t)(v > 255 ? 255 : v);
     }
 }
+
+/* ----------------------------------------------------------------------------------------
+ * SeamFinder.resize (stitching/seam_finder.py:38-43):
+ *     cv.dilate(seam_mask, None) -> cv.resize(.., mask size, 0, 0, cv.INTER_LINEAR_EXACT) -> cv.bitwise_and(.., mask)
+ * dilate: 3x3 rectangle, anchor at the centre, one iteration, pixels outside the image are ignored
+ *     (BORDER_CONSTANT with morphologyDefaultBorderValue).
+ * resize: the call passes its arguments POSITIONALLY -- cv.resize(src, dsize, dst, fx, fy, interpolation) -- so
+ *     the constant lands in `fy` (ignored, dsize is given) and the interpolation is the default INTER_LINEAR.
+ *     For uint8 that is OpenCV's 11-bit fixed-point bilinear code (HResizeLinear / VResizeLinear):
+ *       scale = 1. / ((double)n_dst / n_src);  f = (float)((d + 0.5) * scale - 0.5);  s = floor(f);  fr = f - s (float);
+ *       weights cvRound((1.f - fr) * 2048.f), cvRound(fr * 2048.f);
+ *       columns: s < 0 -> (0, fr = 0);  s >= n_src - 1 -> (n_src - 1, fr = 0);
+ *       rows: weights kept, the two row indices clamped to the image;
+ *       horizontal sum in int (scale 2048), vertical ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16), then (+2) >> 2.
+ *     An exact 2x reduction in both axes is rerouted by cv::resize to the 2x2 box average (a+b+c+d+2) >> 2.
+ * Found by hypothesis testing against cv2 4.13 (0 mismatches over random sizes / contents, IPP on and off) and pinned
+ * against the reference function itself (cv.UMat inputs, as the pipeline passes them) by tests/golden/gen_golden.py
+ * -> golden_seam.npz.
+ * ---------------------------------------------------------------------------------------- */
+SO_API void so_dilate3x3_u8(const uint8_t *src, size_t pitch, int w, int h, uint8_t *dst)
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int m = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                    if (src[(size_t)yy * pitch + xx] > m) m = src[(size_t)yy * pitch + xx];
+                }
+            dst[(size_t)y * w + x] = (uint8_t)m;
+        }
+}
+
+/* per-axis taps of cv.resize(uint8, INTER_LINEAR): index pair and 11-bit weights; `columns` selects the border rule */
+SO_API void so_resize_linear_taps(int n_src, int n_dst, int columns, int *i0, int *i1, int *c0, int *c1)
+{
+    const double scale = 1. / ((double)n_dst / (double)n_src);
+    for (int d = 0; d < n_dst; ++d) {
+        const float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        float fr = f - (float)s;
+        int a, b;
+        if (columns) {
+            if (s < 0) {
+                fr = 0.f;
+                s = 0;
+            }
+            if (s >= n_src - 1) {
+                fr = 0.f;
+                s = n_src - 1;
+            }
+            a = s;
+            b = s + 1 < n_src ? s + 1 : n_src - 1;
+        } else {
+            a = s < 0 ? 0 : (s > n_src - 1 ? n_src - 1 : s);
+            b = s + 1 < 0 ? 0 : (s + 1 > n_src - 1 ? n_src - 1 : s + 1);
+        }
+        i0[d] = a;
+        i1[d] = b;
+        c0[d] = cv_round((1.f - fr) * 2048.f);
+        c1[d] = cv_round(fr * 2048.f);
+    }
+}
+
+SO_API void so_resize_linear_u8(const uint8_t *src, size_t pitch, int sw, int sh, int dw, int dh, uint8_t *dst)
+{
+    if (sw == 2 * dw && sh == 2 * dh) { /* cv::resize reroutes the exact 2x reduction to the box filter */
+        for (int y = 0; y < dh; ++y)
+            for (int x = 0; x < dw; ++x) {
+                const uint8_t *p = src + (size_t)(2 * y) * pitch + 2 * x;
+                dst[(size_t)y * dw + x] = (uint8_t)((p[0] + p[1] + p[pitch] + p[pitch + 1] + 2) >> 2);
+            }
+        return;
+    }
+    int *tx = (int *)malloc(sizeof(int) * 4 * (size_t)dw), *ty = (int *)malloc(sizeof(int) * 4 * (size_t)dh);
+    so_resize_linear_taps(sw, dw, 1, tx, tx + dw, tx + 2 * dw, tx + 3 * dw);
+    so_resize_linear_taps(sh, dh, 0, ty, ty + dh, ty + 2 * dh, ty + 3 * dh);
+    for (int y = 0; y < dh; ++y) {
+        const uint8_t *r0 = src + (size_t)ty[y] * pitch, *r1 = src + (size_t)ty[dh + y] * pitch;
+        const int b0 = ty[2 * dh + y], b1 = ty[3 * dh + y];
+        for (int x = 0; x < dw; ++x) {
+            const int a0 = tx[2 * dw + x], a1 = tx[3 * dw + x];
+            const int h0 = r0[tx[x]] * a0 + r0[tx[dw + x]] * a1; /* scale 2048 */
+            const int h1 = r1[tx[x]] * a0 + r1[tx[dw + x]] * a1;
+            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            dst[(size_t)y * dw + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(tx);
+    free(ty);
+}
+
+/* the whole of SeamFinder.resize: dst = resize(dilate(seam)) & mask, dst and mask are w x h */
+SO_API void so_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const uint8_t *mask, size_t mask_pitch, int w, int h,
+                           uint8_t *dst)
+{
+    uint8_t *d = (uint8_t *)malloc((size_t)sw * sh);
+    so_dilate3x3_u8(seam, seam_pitch, sw, sh, d);
+    so_resize_linear_u8(d, (size_t)sw, sw, sh, w, h, dst);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) dst[(size_t)y * w + x] &= mask[(size_t)y * mask_pitch + x];
+    free(d);
+}

@@ -192,12 +192,50 @@ def gen_e2e():
     np.savez_compressed(os.path.join(HERE, "golden_e2e.npz"), **out)
 
 
+def gen_seam():
+    """SeamFinder.resize (stitching/seam_finder.py:38-43) of the unmodified reference, fed the way stitcher.py:223-225
+    feeds it: a LOW-resolution seam mask as cv.UMat and the FINAL-resolution warped mask as ndarray."""
+    from stitching.seam_finder import SeamFinder as RefSeamFinder
+
+    rng = np.random.default_rng(20260923)
+    out = {}
+    # warped validity masks of a scaled cfg2 rig at "final" resolution; seam masks at ~1/3 of it, like 0.1 vs 1 MP
+    cfg = rigs.config("cfg2", 10)
+    cams = cfg["cameras"][:4]
+    wr = RefWarper(cfg["warper"])
+    wr.set_scale(cams)
+    masks = list(wr.create_and_warp_masks([(cfg["w"], cfg["h"])] * len(cams), cams))
+    cases = []
+    for i, m in enumerate(masks):
+        h, w = m.shape
+        sh, sw = int(round(h / 3.17)) + i, int(round(w / 3.17)) - i  # the two resolutions round independently
+        seam = np.zeros((sh, sw), np.uint8)
+        seam[:, : sw // 2 + int(rng.integers(-5, 6))] = 255  # a seam through the middle ...
+        for _ in range(6):  # ... with a ragged edge
+            cv.circle(seam, (sw // 2, int(rng.integers(0, sh))), int(rng.integers(2, 9)), int(rng.integers(0, 2)) * 255, -1)
+        cases.append((seam, m))
+    cases.append(((rng.random((37, 53)) < 0.5).astype(np.uint8) * 255, np.full((371, 533), 255, np.uint8)))  # noise, 10x
+    cases.append((rng.integers(0, 256, (40, 30), dtype=np.uint8), (rng.random((97, 61)) < 0.8).astype(np.uint8) * 255))  # gray levels
+    cases.append((rng.integers(0, 256, (64, 48), dtype=np.uint8), np.full((32, 24), 255, np.uint8)))  # exact 2x reduction
+    cases.append((rng.integers(0, 256, (50, 70), dtype=np.uint8), np.full((31, 45), 255, np.uint8)))  # other reduction
+    cases.append((np.array([[255]], np.uint8), np.full((5, 7), 255, np.uint8)))  # 1x1 source
+    for i, (seam, m) in enumerate(cases):
+        got = RefSeamFinder.resize(cv.UMat(seam), m)
+        out[f"seam_{i}"] = seam
+        out[f"mask_{i}"] = m
+        out[f"out_{i}"] = got.get() if hasattr(got, "get") else np.asarray(got)
+    out["n"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "golden_seam.npz"), **out)
+    print("seam cases", len(cases))
+
+
 if __name__ == "__main__":
     print("cv2", cv.__version__)
     gen_warp()
     gen_blend()
     gen_pyr()
     gen_e2e()
+    gen_seam()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -26,3 +26,10 @@ def test_oracle_pyramid_goldens(oracle):
     replay.assert_exact(oracle.convert_scale_abs(g["csa_in"]), g["csa_out"], "convertScaleAbs")
     d = oracle.dist_l1(g["dt_mask"])
     assert np.array_equal(d, g["dt_l1"]), "distanceTransform L1"
+
+
+def test_oracle_seam_resize_goldens(oracle):
+    """SeamFinder.resize of the reference (dilate + cv.resize + AND) == the oracle's restatement."""
+    g = replay.load("golden_seam.npz")
+    for i in range(int(g["n"])):
+        replay.assert_exact(oracle.seam_resize(g[f"seam_{i}"], g[f"mask_{i}"]), g[f"out_{i}"], f"seam resize case {i}")
