@@ -61,6 +61,13 @@ SB_API unsigned long long sb_launch_count(void);
 SB_API int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h,
                        int out_rect[4]);
 
+/* seam_finder.py:38-43 SeamFinder.resize(seam_mask, mask) with host buffers:
+ *   dst = cv.bitwise_and(cv.resize(cv.dilate(seam_mask, None), (w, h), 0, 0, cv.INTER_LINEAR_EXACT), mask)
+ * (the positional arguments of that cv.resize call select its default INTER_LINEAR; reproduced bit for bit).
+ * seam: uint8 sh x sw; mask, dst: uint8 h x w. */
+SB_API int sb_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const uint8_t *mask, size_t mask_pitch,
+                          int w, int h, uint8_t *dst, size_t dst_pitch);
+
 /* warper.py:43-52 Warper.warp_image   -> PyRotationWarper.warp(INTER_LINEAR, BORDER_REFLECT)
  * warper.py:58-68 create_and_warp_mask -> PyRotationWarper.warp(INTER_NEAREST, BORDER_CONSTANT) on a 255 mask
  * Both outputs come from ONE kernel pass.  dst_img / dst_mask may each be NULL; their extents must be
@@ -126,6 +133,10 @@ SB_API int sb_compositor_model_bytes(const sb_compositor *c, double *total_bytes
 SB_API int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pitch, int pinned);
 /* optional per-image blend mask in warped coordinates (mask_mode 1), uint8 h' x w' */
 SB_API int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t pitch);
+/* the same from the LOW-resolution seam mask of image i (uint8 sh x sw, what SeamFinder.find returns): the device
+ * performs SeamFinder.resize (seam_finder.py:38-43, called at stitcher.py:223-225) -- cv.dilate 3x3, cv.resize to the
+ * warped size, AND with the warped mask -- and uses the result as blend mask from the next run on */
+SB_API int sb_compositor_set_seam_mask(sb_compositor *c, int i, const uint8_t *seam, size_t seam_pitch, int sw, int sh);
 /* enqueue warp + blend on the compositor stream (no host sync) */
 SB_API int sb_compositor_run(sb_compositor *c);
 /* device -> host copy of the panorama (uint8 HxWx3 + uint8 mask); synchronises */

@@ -1,10 +1,11 @@
 """stitching_b200 -- the compositing hot path of OpenStitching/stitching on NVIDIA B200 (sm_100a).
 
-Drop-in replacements for `stitching.warper.Warper` and `stitching.blender.Blender` (same interface) backed
-by hand-written CUDA kernels behind a C ABI (include/stitch_b200.h), plus a fused `Compositor`.
+Drop-in replacements for `stitching.warper.Warper`, `stitching.blender.Blender` and `SeamFinder.resize` (same
+interface) backed by hand-written CUDA kernels behind a C ABI (include/stitch_b200.h), plus a fused `Compositor`.
 `install()` swaps them into an installed `stitching` package so that Stitcher / AffineStitcher / the CLI run
 unchanged.
 """
+from . import seam_finder  # noqa: F401
 from .blender import Blender  # noqa: F401
 from .compositor import Compositor  # noqa: F401
 from .stitching_error import StitchingError, StitchingWarning  # noqa: F401
@@ -35,4 +36,10 @@ def install(stitching_module=None):
         for name in names:
             if hasattr(m, name):
                 setattr(m, name, {"Warper": Warper, "Blender": Blender}[name])
+    # the FINAL-resolution step of the seam finder (seam_finder.py:38-43); stitcher.py calls it through the class
+    try:
+        sf = importlib.import_module(f"{pkg}.seam_finder")
+        sf.SeamFinder.resize = staticmethod(seam_finder.resize)
+    except Exception:
+        pass
     return stitching_module

@@ -97,6 +97,17 @@ class Compositor:
         _lib.check(_lib.lib().sb_compositor_set_mask(self._c, i, mask.ctypes.data_as(C.c_void_p), mask.strides[0]),
                    "sb_compositor_set_mask")
 
+    def set_seam_mask(self, i, seam_mask):
+        """Blend mask of image i from its LOW-resolution seam mask (what SeamFinder.find returns): SeamFinder.resize
+        (seam_finder.py:38-43) runs on the device -- dilate, resize to the warped size, AND with the warped mask."""
+        if hasattr(seam_mask, "get") and not isinstance(seam_mask, np.ndarray):
+            seam_mask = seam_mask.get()
+        seam_mask = np.ascontiguousarray(seam_mask, np.uint8)
+        if seam_mask.ndim != 2:
+            raise StitchingError(f"seam mask {i}: expected a 2-d uint8 array")
+        _lib.check(_lib.lib().sb_compositor_set_seam_mask(self._c, i, seam_mask.ctypes.data_as(C.c_void_p), seam_mask.strides[0],
+                                                          seam_mask.shape[1], seam_mask.shape[0]), "sb_compositor_set_seam_mask")
+
     def run(self):
         _lib.check(_lib.lib().sb_compositor_run(self._c), "sb_compositor_run")
 

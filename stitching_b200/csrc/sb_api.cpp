@@ -129,6 +129,55 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
     return SB_OK;
 }
 
+}  // extern "C"
+
+namespace sb {
+// SeamFinder.resize on the device: seam mask from the host, `mask_dev` / `dst_dev` on the device (mask_dev may be null)
+int seam_resize_device(const uint8_t *seam_host, size_t seam_pitch, int sw, int sh, const uint8_t *mask_dev, long long mask_pitch,
+                       uint8_t *dst_dev, long long dst_pitch, int w, int h, cudaStream_t s)
+{
+    Scratch tmp(s);
+    uint8_t *d_seam = nullptr, *d_dil = nullptr;
+    int *d_tx = nullptr, *d_ty = nullptr;
+    SB_TRY(tmp.get(&d_seam, (size_t)sw * sh));
+    SB_TRY(tmp.get(&d_dil, (size_t)sw * sh));
+    SB_TRY(tmp.get(&d_tx, (size_t)4 * w));
+    SB_TRY(tmp.get(&d_ty, (size_t)4 * h));
+    std::vector<int> tx((size_t)4 * w), ty((size_t)4 * h);
+    resize_linear_taps(sw, w, true, tx.data());
+    resize_linear_taps(sh, h, false, ty.data());
+    SB_CUDA(cudaMemcpy2DAsync(d_seam, sw, seam_host, seam_pitch, sw, sh, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(d_tx, tx.data(), tx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(d_ty, ty.data(), ty.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SB_TRY(launch_seam_resize(d_seam, sw, sh, d_dil, d_tx, d_ty, mask_dev, mask_pitch, dst_dev, dst_pitch, w, h, s));
+    SB_CUDA(cudaStreamSynchronize(s));  // the tap vectors and the scratch buffers go out of scope
+    return SB_OK;
+}
+}  // namespace sb
+
+extern "C" {
+
+int sb_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const uint8_t *mask, size_t mask_pitch, int w, int h,
+                   uint8_t *dst, size_t dst_pitch)
+{
+    if (!seam || !mask || !dst || sw <= 0 || sh <= 0 || w <= 0 || h <= 0 || seam_pitch < (size_t)sw || mask_pitch < (size_t)w ||
+        dst_pitch < (size_t)w || (long long)w * h > (1ll << 31) || (long long)sw * sh > (1ll << 31)) {
+        set_error("sb_seam_resize: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    uint8_t *d_mask = nullptr, *d_dst = nullptr;
+    SB_TRY(tmp.get(&d_mask, (size_t)w * h));
+    SB_TRY(tmp.get(&d_dst, (size_t)w * h));
+    SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
+    SB_TRY(seam_resize_device(seam, seam_pitch, sw, sh, d_mask, w, d_dst, w, w, h, s));
+    SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d_dst, w, w, h, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Blender
 // -------------------------------------------------------------------------------------------------

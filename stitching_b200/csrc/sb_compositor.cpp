@@ -533,10 +533,43 @@ int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t 
     SB_CUDA(cudaStreamSynchronize(c->stream));
     c->jobs[i].blend_mask = c->usermask_dev[i];
     c->jobs[i].blend_mask_pitch = w;
+    c->jobs[i].blend_mask_and = 0;
     for (auto &jx : c->jobsx)
         if (!jx.empty()) {
             jx[i].blend_mask = c->usermask_dev[i];
             jx[i].blend_mask_pitch = w;
+            jx[i].blend_mask_and = 0;
+        }
+#ifndef SB_EMU
+    for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture
+        if (g) {
+            (void)cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+#endif
+    return SB_OK;
+}
+
+int sb_compositor_set_seam_mask(sb_compositor *c, int i, const uint8_t *seam, size_t seam_pitch, int sw, int sh)
+{
+    if (!c || i < 0 || i >= c->n || !seam || sw <= 0 || sh <= 0 || seam_pitch < (size_t)sw || !c->rgbm_dev[i]) {
+        set_error("sb_compositor_set_seam_mask: invalid argument (or an image of another rank)");
+        return SB_ERR_INVALID;
+    }
+    // SeamFinder.resize(seam_mask, warped mask) (seam_finder.py:38-43, stitcher.py:223-225) without the host round
+    // trip: the LOW-resolution seam mask is dilated and resized on the device; the AND with the warped validity mask
+    // happens in the warp kernel, which computes that mask anyway
+    const int w = c->rects[i].w, h = c->rects[i].h;
+    if (!c->usermask_dev[i]) SB_TRY(dev_alloc((void **)&c->usermask_dev[i], (size_t)w * h, c->stream));
+    SB_TRY(seam_resize_device(seam, seam_pitch, sw, sh, nullptr, 0, c->usermask_dev[i], w, w, h, c->stream));
+    c->jobs[i].blend_mask = c->usermask_dev[i];
+    c->jobs[i].blend_mask_pitch = w;
+    c->jobs[i].blend_mask_and = 1;
+    for (auto &jx : c->jobsx)
+        if (!jx.empty()) {
+            jx[i].blend_mask = c->usermask_dev[i];
+            jx[i].blend_mask_pitch = w;
+            jx[i].blend_mask_and = 1;
         }
 #ifndef SB_EMU
     for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture

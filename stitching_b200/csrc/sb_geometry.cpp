@@ -10,6 +10,7 @@
 //
 // This translation unit MUST be compiled without FMA contraction (-ffp-contract=off): every fp32
 // multiply and add is rounded separately, as in the baseline-SSE OpenCV build.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -230,6 +231,38 @@ void projector_tables(const Projector &p, const int rect[4], float *colX, float 
                 rowY[j] = (float)(rect[1] + j) / p.scale - p.t[1];
             }
         }
+    }
+}
+
+// Per-axis taps of cv::resize(uint8, INTER_LINEAR) -- what SeamFinder.resize really calls (seam_finder.py:40-42: the
+// positional arguments put INTER_LINEAR_EXACT into `fy`).  OpenCV's order: scale = 1 / (n_dst / n_src) in double, the
+// coordinate rounded to float, its fraction taken in float, weights cvRound(w * 2048) (half to even).  Columns clamp the
+// index AND zero the fraction at the borders; rows keep the weights and clamp the two indices.  t = [i0 | i1 | c0 | c1].
+void resize_linear_taps(int n_src, int n_dst, bool columns, int *t)
+{
+    const double scale = 1. / ((double)n_dst / (double)n_src);
+    int *i0 = t, *i1 = t + n_dst, *c0 = t + 2 * (size_t)n_dst, *c1 = t + 3 * (size_t)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        const float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        float fr = f - (float)s;
+        if (columns) {
+            if (s < 0) {
+                fr = 0.f;
+                s = 0;
+            }
+            if (s >= n_src - 1) {
+                fr = 0.f;
+                s = n_src - 1;
+            }
+            i0[d] = s;
+            i1[d] = std::min(s + 1, n_src - 1);
+        } else {
+            i0[d] = std::min(std::max(s, 0), n_src - 1);
+            i1[d] = std::min(std::max(s + 1, 0), n_src - 1);
+        }
+        c0[d] = (int)std::lrintf((1.f - fr) * 2048.f);
+        c1[d] = (int)std::lrintf(fr * 2048.f);
     }
 }
 

@@ -68,6 +68,7 @@ struct WarpJob {
     long long mask_pitch;
     uint32_t *dst_rgbm;  // packed r | g<<8 | b<<16 | mask<<24, or null
     long long rgbm_pitch;  // elements
+    int blend_mask_and;         // 1: the stored weight byte is blend_mask & validity (sb_compositor_set_seam_mask)
     const uint8_t *blend_mask;  // optional blend mask (seam mask AND validity, stitcher.py:223-239) stored in the
     long long blend_mask_pitch; // mask byte of dst_rgbm instead of the validity mask
     int dw, dh;
@@ -188,6 +189,14 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
+// SeamFinder.resize (sb_seam.cu, sb_geometry.cpp)
+void resize_linear_taps(int n_src, int n_dst, bool columns, int *t);  // t: 4 * n_dst ints
+int launch_seam_resize(const uint8_t *seam, int sw, int sh, uint8_t *scratch, const int *tx, const int *ty, const uint8_t *mask,
+                       long long mask_pitch, uint8_t *dst, long long dst_pitch, int w, int h, cudaStream_t s);
+// device version of SeamFinder.resize for host or device `mask` / `dst` buffers already on the device: uploads the seam
+// mask, builds the taps, runs the two kernels (synchronises `s`)
+int seam_resize_device(const uint8_t *seam_host, size_t seam_pitch, int sw, int sh, const uint8_t *mask_dev, long long mask_pitch,
+                       uint8_t *dst_dev, long long dst_pitch, int w, int h, cudaStream_t s);
 int launch_selftest_division(unsigned long long n, unsigned long long seed, int mode, unsigned long long *bad_dev, cudaStream_t s);
 
 }  // namespace sb

@@ -54,7 +54,10 @@ __device__ __forceinline__ void store_pixel(const WarpJob &j, int u, int v, unsi
         d[2] = (uint8_t)b;
     }
     if (j.dst_rgbm) {
-        if (j.blend_mask) m = j.blend_mask[(long long)v * j.blend_mask_pitch + u];
+        if (j.blend_mask) {
+            const unsigned bm = j.blend_mask[(long long)v * j.blend_mask_pitch + u];
+            m = j.blend_mask_and ? (bm & m) : bm;
+        }
         j.dst_rgbm[(unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u] = r | (g << 8) | (b << 16) | (m << 24);
     }
 }
@@ -292,8 +295,13 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_
     }
     if (HAS_BM) {
         const uint8_t *bm = j.blend_mask + (unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u;
-        out[0] = (out[0] & 0xffffffu) | ((unsigned)bm[0] << 24);
-        if (u + 1 < j.dw) out[1] = (out[1] & 0xffffffu) | ((unsigned)bm[1] << 24);
+        // a user blend mask replaces the validity byte; a seam mask (sb_compositor_set_seam_mask) is ANDed with it
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+            if (p == 0 || u + 1 < j.dw) {
+                const unsigned b = (unsigned)bm[p] << 24;
+                out[p] = j.blend_mask_and ? (out[p] & (b | 0x00ffffffu)) : ((out[p] & 0x00ffffffu) | b);
+            }
     }
     uint32_t *d = j.dst_rgbm + (unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u;  // pitch is a multiple of 64: 8-byte aligned
     if (u + 1 < j.dw)

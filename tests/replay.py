@@ -176,3 +176,26 @@ def oracle_composite(O, cfg, cams, imgs, mask_fn=None):
         b.feed(wi, wm, c)
     pano, pmask = b.blend()
     return dict(warped=warped, masks=masks, corners=corners, sizes=sizes, pano=pano, pmask=pmask, num_bands=b.num_bands)
+
+
+def run_seam_goldens(resize_fn):
+    """SeamFinder.resize goldens (tests/golden/golden_seam.npz, written by the reference function)."""
+    g = load("golden_seam.npz")
+    for i in range(int(g["n"])):
+        assert_exact(np.asarray(resize_fn(g[f"seam_{i}"], g[f"mask_{i}"])), g[f"out_{i}"], f"SeamFinder.resize case {i}")
+
+
+def seam_masks_low(ref_masks, ratio=3.17, seed=0):
+    """LOW-resolution seam masks for warped masks of a rig: a ragged seam through the middle of each (test input)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i, m in enumerate(ref_masks):
+        h, w = m.shape
+        sh, sw = max(2, int(round(h / ratio)) + i % 2), max(2, int(round(w / ratio)) - i % 3)
+        s = np.zeros((sh, sw), np.uint8)
+        s[:, : sw // 2 + int(rng.integers(-3, 4))] = 255
+        ys = rng.integers(0, sh, 8)
+        for y in ys:
+            s[max(0, y - 2) : y + 3, sw // 2 - 4 : sw // 2 + 5] = 255 * int(rng.integers(0, 2))
+        out.append(s if i % 2 else 255 - s)
+    return out

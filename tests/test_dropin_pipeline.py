@@ -2,7 +2,7 @@
 
 stitching.Stitcher(crop=False) runs unmodified on three synthetic perspective views of a textured plane.  The
 reference's registration is not deterministic from run to run (RANSAC), so two whole runs cannot be compared;
-instead every call that crosses the hot-path boundary is RECORDED while the reference runs with its own classes
+instead every call that crosses the hot-path boundary (Warper, SeamFinder.resize, Blender) is RECORDED while the reference runs with its own classes
 (the exact cv.detail.CameraParams, numpy-float aspect, cv.UMat blend masks, corner tuples it hands over, and what
 cv2 returned), and then REPLAYED through the B200 classes (here on the emulation build, tests/emu): every warped
 image, mask, roi and the final panorama must be identical.  A second part runs the whole pipeline with
@@ -98,10 +98,24 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
             log.append(("blend", pano.copy(), np.array(mask).copy()))
             return pano, mask
 
+    from stitching.seam_finder import SeamFinder as RefSeamFinder
+
+    ref_resize = RefSeamFinder.resize
+
+    def rec_resize(seam_mask, mask):
+        out = ref_resize(seam_mask, mask)
+        log.append(("seam_resize", seam_mask, np.array(mask).copy(), out.get() if hasattr(out, "get") else np.array(out)))
+        return out
+
     stitching.stitcher.Warper, stitching.stitcher.Blender = RecWarper, RecBlender
-    stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in synthetic_views(cv)])
+    RefSeamFinder.resize = staticmethod(rec_resize)
+    try:
+        stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in synthetic_views(cv)])
+    finally:
+        RefSeamFinder.resize = staticmethod(ref_resize)
     kinds = [e[0] for e in log]
     assert kinds.count("warp_image") >= 6 and kinds.count("feed") == 3 and kinds.count("blend") == 1
+    assert kinds.count("seam_resize") == 3, "stitcher.py:223-225 resizes one seam mask per image"
     assert any(type(e[2]).__name__ == "UMat" for e in log if e[0] == "feed"), "the pipeline hands cv.UMat masks to feed"
 
     blender = None
@@ -116,6 +130,10 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
             else:
                 assert got.shape == e[6].shape and np.array_equal(got, e[6]), f"{e[0]}: {int((got != e[6]).sum())} values differ"
             checked += 1
+        elif e[0] == "seam_resize":  # the LOW-resolution seam mask arrives as cv.UMat, the warped mask as ndarray
+            got = stitching_b200.seam_finder.resize(e[1], e[2])
+            assert got.shape == e[3].shape and np.array_equal(got, e[3]), f"SeamFinder.resize: {int((got != e[3]).sum())} values differ"
+            checked += 1
         elif e[0] == "prepare":
             blender = stitching_b200.Blender(e[1], e[2])
             blender.prepare(e[3], e[4])
@@ -127,7 +145,7 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
             d = np.abs(pano.astype(np.int32) - e[1].astype(np.int32))
             assert d.max() == 0, f"panorama: max |diff| {int(d.max())}, {int((d != 0).sum())} values"
             checked += 1
-    assert checked >= 13
+    assert checked >= 16
 
 
 def test_stitcher_runs_end_to_end_on_the_swapped_classes(reference_stitching, use_emu):

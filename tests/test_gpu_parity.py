@@ -58,6 +58,39 @@ def test_shared_reciprocal_division_is_the_ieee_division(cuda_lib, mode):
     assert bad.value == 0, f"mode {mode}: {bad.value} of 2^32 quotients differ from __fdiv_rn"
 
 
+def test_seam_resize_goldens_fuzz_and_fused(cuda_lib, oracle):
+    """SeamFinder.resize on the device: the reference's goldens, fuzz against the oracle, and the fused
+    Compositor.set_seam_mask against set_mask(SeamFinder.resize(..)) -- all bit-exact."""
+    from stitching_b200 import seam_finder
+
+    replay.run_seam_goldens(seam_finder.resize)
+    rng = np.random.default_rng(12)
+    for t in range(16):
+        sh, sw = int(rng.integers(3, 200)), int(rng.integers(3, 260))
+        h, w = max(2, int(sh * rng.uniform(0.5, 8))), max(2, int(sw * rng.uniform(0.5, 8)))
+        seam = rng.integers(0, 256, (sh, sw), dtype=np.uint8) if t % 2 else (rng.random((sh, sw)) < 0.5).astype(np.uint8) * 255
+        mask = (rng.random((h, w)) < 0.9).astype(np.uint8) * 255
+        assert_parity(seam_finder.resize(seam, mask), oracle.seam_resize(seam, mask), f"seam resize fuzz {t}")
+    cfg = rigs.config("cfg2", 4)
+    cams = cfg["cameras"]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 60 + i) for i in range(len(cams))]
+    a = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    b = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    a.composite(imgs)
+    valid = [a.download_warped(i)[1] for i in range(len(cams))]
+    seams = replay.seam_masks_low(valid)
+    for i, s in enumerate(seams):
+        a.set_mask(i, oracle.seam_resize(s, valid[i]))
+        b.set_seam_mask(i, s)
+    pa, ma = a.composite(imgs)
+    pb, mb = b.composite(imgs)
+    assert_parity(pb, pa, "pano with fused seam masks")
+    assert_parity(mb, ma, "mask with fused seam masks")
+    a.close()
+    b.close()
+
+
 def test_warper_goldens(cuda_lib):
     replay.run_warper_goldens(Warper)
 

@@ -201,3 +201,37 @@ def test_umat_like_mask_and_create_panorama(use_emu, oracle):
         o.feed(i, m, c)
     ep, em = o.blend()
     assert np.array_equal(pano, ep) and np.array_equal(pmask, em)
+
+
+def test_seam_resize_drop_in_and_fused(use_emu, oracle):
+    """SeamFinder.resize through the C ABI (host buffers) == the reference's goldens == the oracle; the fused
+    Compositor.set_seam_mask == set_mask(SeamFinder.resize(seam, warped mask))."""
+    from stitching_b200 import seam_finder
+
+    replay.run_seam_goldens(seam_finder.resize)
+    rng = np.random.default_rng(11)
+    for t in range(12):
+        sh, sw = int(rng.integers(3, 60)), int(rng.integers(3, 80))
+        h, w = max(2, int(sh * rng.uniform(0.5, 6))), max(2, int(sw * rng.uniform(0.5, 6)))
+        seam = rng.integers(0, 256, (sh, sw), dtype=np.uint8) if t % 2 else (rng.random((sh, sw)) < 0.5).astype(np.uint8) * 255
+        mask = (rng.random((h, w)) < 0.9).astype(np.uint8) * 255
+        replay.assert_exact(seam_finder.resize(seam, mask), oracle.seam_resize(seam, mask), f"seam resize fuzz {t}")
+    cfg = rigs.config("cfg2", 25)
+    cams = cfg["cameras"]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 60 + i) for i in range(len(cams))]
+    a = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    b = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+    plain, _ = a.composite(imgs)  # also yields the warped validity masks of the rig
+    valid = [a.download_warped(i)[1] for i in range(len(cams))]
+    seams = replay.seam_masks_low(valid)
+    for i, s in enumerate(seams):
+        a.set_mask(i, oracle.seam_resize(s, valid[i]))
+        b.set_seam_mask(i, s)
+    pa, ma = a.composite(imgs)
+    pb, mb = b.composite(imgs)
+    replay.assert_exact(pb, pa, "pano with fused seam masks")
+    replay.assert_exact(mb, ma, "mask with fused seam masks")
+    assert not np.array_equal(pb, plain), "the seam masks must change the blend"
+    a.close()
+    b.close()
