@@ -63,6 +63,9 @@ def lib():
         L.so_sb_feed.argtypes = [C.c_void_p, s16p, C.c_size_t, u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
         L.so_sb_blend.argtypes = [C.c_void_p, s16p, u8p]
         L.so_convert_scale_abs_s16.argtypes = [s16p, C.c_size_t, u8p]
+        L.so_resize_linear_f32.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+        L.so_gain_apply_blocks.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int]
+        L.so_gain_apply_scalar.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.so_dilate3x3_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
         L.so_resize_linear_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.so_seam_resize.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.c_size_t, C.c_int, C.c_int, u8p]
@@ -203,6 +206,34 @@ def seam_resize(seam_mask, mask):
     out = np.empty((h, w), np.uint8)
     lib().so_seam_resize(_p(seam_mask, C.c_uint8), seam_mask.strides[0], sw, sh, _p(mask, C.c_uint8), mask.strides[0], w, h,
                          _p(out, C.c_uint8))
+    return out
+
+
+def resize_linear_f32(a, size):
+    """cv.resize(a, size, interpolation=cv.INTER_LINEAR) for a float32 image of 1 or 3 channels; size = (w, h)."""
+    a = np.ascontiguousarray(a, np.float32)
+    h, w = a.shape[:2]
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    out = np.empty((int(size[1]), int(size[0])) + (() if a.ndim == 2 else (cn,)), np.float32)
+    lib().so_resize_linear_f32(_p(a, C.c_float), w, h, cn, int(size[0]), int(size[1]), _p(out, C.c_float))
+    return out
+
+
+def gain_apply(img, gain):
+    """ExposureErrorCompensator.apply for one image (exposure_error_compensator.py:43-45), given the compensator's gain
+    for it (cv.detail ...Compensator.getMatGains()[idx]): a float32 map of 1 or 3 channels (gain_blocks /
+    channel_blocks), a float64 scalar (gain) or a float64 vector of >= 3 entries (channel).  Returns a new image."""
+    out = np.ascontiguousarray(img, np.uint8).copy()
+    h, w = out.shape[:2]
+    gain = np.asarray(gain)
+    if gain.dtype == np.float64:
+        g = gain.ravel()
+        g3 = np.array([g[0], g[0], g[0]] if g.size == 1 else g[:3], np.float64)
+        lib().so_gain_apply_scalar(_p(out, C.c_uint8), out.strides[0], w, h, g3.ctypes.data_as(C.POINTER(C.c_double)))
+    else:
+        gain = np.ascontiguousarray(gain, np.float32)
+        gc = 1 if gain.ndim == 2 else gain.shape[2]
+        lib().so_gain_apply_blocks(_p(out, C.c_uint8), out.strides[0], w, h, _p(gain, C.c_float), gain.shape[1], gain.shape[0], gc)
     return out
 
 

@@ -795,3 +795,88 @@ SO_API void so_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int s
         for (int x = 0; x < w; ++x) dst[(size_t)y * w + x] &= mask[(size_t)y * mask_pitch + x];
     free(d);
 }
+
+/* ----------------------------------------------------------------------------------------
+ * ExposureErrorCompensator.apply (stitching/exposure_error_compensator.py:43-45, called per FINAL-resolution image at
+ * stitcher.py:219-221) -> cv.detail compensators:
+ *   gain_blocks / channel_blocks (Blocks*Compensator::apply): the float32 gain map (1 or 3 channels, one sample per
+ *     block) is resized to the image size with cv::resize(INTER_LINEAR) and multiplied in:
+ *         image = saturate_cast<uchar>(cvRound(float(image) * gain))            (float32 product, half to even)
+ *     In the reference's wheel that float32 resize runs IPP's kernel, not OpenCV's own; found by hypothesis testing
+ *     (0 mismatches, cv2 4.13 with IPP on):  f = (d + 0.5) * (n_src / n_dst) - 0.5 in double, i0 = floor(f),
+ *     fraction = float(f - i0), zero where the index is clamped (both axes); horizontal pass first, each pass
+ *     a + (b - a) * t as ONE fused multiply-add.
+ *   gain / channel (GainCompensator / ChannelsCompensator::apply): a double scalar per image (per channel):
+ *         image = saturate_cast<uchar>(cvRound(double(image) * gain))           (double product)
+ *   no: identity.
+ * Pinned against the reference class (gains estimated by its own feed()) by tests/golden/gen_golden.py -> golden_gain.npz.
+ * ---------------------------------------------------------------------------------------- */
+static void resize_f32_taps(int n_src, int n_dst, int *i0, int *i1, float *fr)
+{
+    const double scale = (double)n_src / (double)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        const double f = ((double)d + 0.5) * scale - 0.5;
+        int s = (int)floor(f);
+        float t = (float)(f - (double)s);
+        if (s < 0 || s >= n_src - 1) t = 0.f;
+        i0[d] = s < 0 ? 0 : (s > n_src - 1 ? n_src - 1 : s);
+        i1[d] = s + 1 < 0 ? 0 : (s + 1 > n_src - 1 ? n_src - 1 : s + 1);
+        fr[d] = t;
+    }
+}
+
+/* cv.resize(float32, cn channels interleaved, INTER_LINEAR) as this wheel computes it */
+SO_API void so_resize_linear_f32(const float *src, int sw, int sh, int cn, int dw, int dh, float *dst)
+{
+    if (sw == dw && sh == dh) {
+        memcpy(dst, src, sizeof(float) * (size_t)sw * sh * cn);
+        return;
+    }
+    int *x0 = (int *)malloc(sizeof(int) * 2 * (size_t)dw), *y0 = (int *)malloc(sizeof(int) * 2 * (size_t)dh);
+    float *fx = (float *)malloc(sizeof(float) * (size_t)dw), *fy = (float *)malloc(sizeof(float) * (size_t)dh);
+    resize_f32_taps(sw, dw, x0, x0 + dw, fx);
+    resize_f32_taps(sh, dh, y0, y0 + dh, fy);
+    for (int y = 0; y < dh; ++y) {
+        const float *r0 = src + (size_t)y0[y] * sw * cn, *r1 = src + (size_t)y0[dh + y] * sw * cn;
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c) {
+                const float a0 = r0[x0[x] * cn + c], b0 = r0[x0[dw + x] * cn + c];
+                const float a1 = r1[x0[x] * cn + c], b1 = r1[x0[dw + x] * cn + c];
+                const float h0 = fmaf(b0 - a0, fx[x], a0), h1 = fmaf(b1 - a1, fx[x], a1);
+                dst[((size_t)y * dw + x) * cn + c] = fmaf(h1 - h0, fy[y], h0);
+            }
+    }
+    free(x0);
+    free(y0);
+    free(fx);
+    free(fy);
+}
+
+static uint8_t sat_round_u8(double v) /* saturate_cast<uchar>(cvRound(v)) */
+{
+    const double r = nearbyint(v);
+    return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+/* Blocks*Compensator::apply: img (uint8 h x w x 3, pitch in bytes) *= resize(gain map gw x gh x gc), gc = 1 or 3 */
+SO_API void so_gain_apply_blocks(uint8_t *img, size_t pitch, int w, int h, const float *gain, int gw, int gh, int gc)
+{
+    float *g = (float *)malloc(sizeof(float) * (size_t)w * h * gc);
+    so_resize_linear_f32(gain, gw, gh, gc, w, h, g);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) {
+                const float gv = g[((size_t)y * w + x) * gc + (gc == 3 ? c : 0)];
+                const float p = (float)img[y * pitch + 3 * (size_t)x + c] * gv; /* float32 product */
+                img[y * pitch + 3 * (size_t)x + c] = sat_round_u8((double)p);
+            }
+    free(g);
+}
+
+/* GainCompensator / ChannelsCompensator::apply: one double gain per channel */
+SO_API void so_gain_apply_scalar(uint8_t *img, size_t pitch, int w, int h, const double gain[3])
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) img[y * pitch + 3 * (size_t)x + c] = sat_round_u8((double)img[y * pitch + 3 * (size_t)x + c] * gain[c]);
+}

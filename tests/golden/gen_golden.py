@@ -229,6 +229,40 @@ def gen_seam():
     print("seam cases", len(cases))
 
 
+def gen_gain():
+    """ExposureErrorCompensator.apply (stitching/exposure_error_compensator.py:43-45) of the unmodified reference: the
+    compensator estimates its gains with its own feed() on LOW-resolution views (stitcher.py:211), apply() then runs on
+    FINAL-resolution images (stitcher.py:219-221).  Stored: the gains (getMatGains), the inputs and apply()'s outputs."""
+    from stitching.exposure_error_compensator import ExposureErrorCompensator as RefCompensator
+
+    rng = np.random.default_rng(20260924)
+    lh, lw = 90, 120
+    base = cv.resize(rng.integers(40, 200, (8, 12, 3), dtype=np.uint8), (lw + 60, lh), interpolation=cv.INTER_CUBIC).astype(np.float32)
+    low = [np.clip(base[:, 0:lw] * 0.8, 0, 255).astype(np.uint8),
+           np.clip(base[:, 30:30 + lw] * 1.2 + rng.normal(0, 2, (lh, lw, 3)), 0, 255).astype(np.uint8),
+           np.clip(base[:, 60:60 + lw] * np.array([1.0, 0.85, 1.25]), 0, 255).astype(np.uint8)]
+    corners = [(0, 0), (30, 0), (60, 0)]
+    masks = [np.full((lh, lw), 255, np.uint8)] * 3
+    out = {}
+    k = 0
+    for name in ("gain_blocks", "channel_blocks", "gain", "channel", "no"):
+        comp = RefCompensator(name, 1, 32)
+        comp.feed(corners, low, masks)
+        gains = [np.asarray(g) for g in comp.compensator.getMatGains()] if name != "no" else [None] * 3
+        for idx in range(3):
+            h, w = int(rng.integers(50, 110)), int(rng.integers(70, 150))  # small fixtures: the arithmetic is per pixel
+            img = rigs.noise_image(h, w, 700 + k) if idx % 2 else rigs.synth_image(h, w, 700 + k)
+            got = comp.apply(idx, (0, 0), img.copy(), np.full((h, w), 255, np.uint8))
+            out[f"kind_{k}"] = name
+            out[f"img_{k}"] = img
+            out[f"gain_{k}"] = gains[idx] if gains[idx] is not None else np.zeros((0,), np.float32)
+            out[f"out_{k}"] = got.get() if hasattr(got, "get") else np.asarray(got)
+            k += 1
+    out["n"] = k
+    np.savez_compressed(os.path.join(HERE, "golden_gain.npz"), **out)
+    print("gain cases", k)
+
+
 if __name__ == "__main__":
     print("cv2", cv.__version__)
     gen_warp()
@@ -236,6 +270,7 @@ if __name__ == "__main__":
     gen_pyr()
     gen_e2e()
     gen_seam()
+    gen_gain()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

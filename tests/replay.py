@@ -199,3 +199,12 @@ def seam_masks_low(ref_masks, ratio=3.17, seed=0):
             s[max(0, y - 2) : y + 3, sw // 2 - 4 : sw // 2 + 5] = 255 * int(rng.integers(0, 2))
         out.append(s if i % 2 else 255 - s)
     return out
+
+
+def run_gain_goldens(apply_fn):
+    """ExposureErrorCompensator.apply goldens (tests/golden/golden_gain.npz): apply_fn(img, gain) -> image."""
+    g = load("golden_gain.npz")
+    for i in range(int(g["n"])):
+        gain = g[f"gain_{i}"]
+        got = g[f"img_{i}"] if gain.size == 0 else np.asarray(apply_fn(g[f"img_{i}"], gain))  # compensator "no": identity
+        assert_exact(got, g[f"out_{i}"], f"compensator apply case {i} ({g[f'kind_{i}']})")

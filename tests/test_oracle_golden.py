@@ -33,3 +33,8 @@ def test_oracle_seam_resize_goldens(oracle):
     g = replay.load("golden_seam.npz")
     for i in range(int(g["n"])):
         replay.assert_exact(oracle.seam_resize(g[f"seam_{i}"], g[f"mask_{i}"]), g[f"out_{i}"], f"seam resize case {i}")
+
+
+def test_oracle_gain_apply_goldens(oracle):
+    """ExposureErrorCompensator.apply of the reference (all five compensators) == the oracle's restatement."""
+    replay.run_gain_goldens(oracle.gain_apply)
