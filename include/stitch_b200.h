@@ -61,6 +61,16 @@ SB_API unsigned long long sb_launch_count(void);
 SB_API int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h,
                        int out_rect[4]);
 
+/* exposure_error_compensator.py:43-45 ExposureErrorCompensator.apply(index, corner, image, mask) -> cv.detail
+ * {Gain,Channels,BlocksGain,BlocksChannels}Compensator::apply, in place on a uint8 h x w x 3 host image, with the
+ * compensator's gain for that image (getMatGains()[index]):
+ *   gain_map    float32 gh x gw x gc, gc = 1 (gain_blocks) or 3 (channel_blocks): resized to w x h as cv::resize
+ *               (INTER_LINEAR) does in the reference's wheel, then saturate(cvRound(float(value) * gain));
+ *   gain_scalar three doubles (gain: the value three times; channel): saturate(cvRound(double(value) * gain)).
+ * Exactly one of the two is non-NULL; both NULL is the identity (compensator "no"). */
+SB_API int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_map, int gw, int gh, int gc,
+                         const double *gain_scalar);
+
 /* seam_finder.py:38-43 SeamFinder.resize(seam_mask, mask) with host buffers:
  *   dst = cv.bitwise_and(cv.resize(cv.dilate(seam_mask, None), (w, h), 0, 0, cv.INTER_LINEAR_EXACT), mask)
  * (the positional arguments of that cv.resize call select its default INTER_LINEAR; reproduced bit for bit).
@@ -137,6 +147,10 @@ SB_API int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, 
  * performs SeamFinder.resize (seam_finder.py:38-43, called at stitcher.py:223-225) -- cv.dilate 3x3, cv.resize to the
  * warped size, AND with the warped mask -- and uses the result as blend mask from the next run on */
 SB_API int sb_compositor_set_seam_mask(sb_compositor *c, int i, const uint8_t *seam, size_t seam_pitch, int sw, int sh);
+/* exposure compensation of image i, fused into the warp: what ExposureErrorCompensator.apply(i, corner, warped, mask)
+ * (exposure_error_compensator.py:43-45, stitcher.py:219-221) does to the warped image, with the compensator's gain for
+ * image i -- cv.detail ...Compensator.getMatGains()[i] -- passed as in sb_gain_apply.  Both NULL: no compensation. */
+SB_API int sb_compositor_set_gain(sb_compositor *c, int i, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar);
 /* enqueue warp + blend on the compositor stream (no host sync) */
 SB_API int sb_compositor_run(sb_compositor *c);
 /* device -> host copy of the panorama (uint8 HxWx3 + uint8 mask); synchronises */

@@ -97,6 +97,17 @@ class Compositor:
         _lib.check(_lib.lib().sb_compositor_set_mask(self._c, i, mask.ctypes.data_as(C.c_void_p), mask.strides[0]),
                    "sb_compositor_set_mask")
 
+    def set_gain(self, i, gain):
+        """Exposure gain of image i (one entry of a fed cv.detail compensator's getMatGains(): float32 map of 1 or 3
+        channels, float64 scalar or vector; None removes it): ExposureErrorCompensator.apply (stitcher.py:219-221)
+        fused into the warp kernel's epilogue from the next run on."""
+        from .exposure_error_compensator import gain_arguments
+
+        gmap, gw, gh, gc, gscalar = gain_arguments(gain)
+        _lib.check(_lib.lib().sb_compositor_set_gain(self._c, i, gmap.ctypes.data_as(C.c_void_p) if gmap is not None else None, gw, gh, gc,
+                                                     gscalar.ctypes.data_as(C.c_void_p) if gscalar is not None else None),
+                   "sb_compositor_set_gain")
+
     def set_seam_mask(self, i, seam_mask):
         """Blend mask of image i from its LOW-resolution seam mask (what SeamFinder.find returns): SeamFinder.resize
         (seam_finder.py:38-43) runs on the device -- dilate, resize to the warped size, AND with the warped mask."""

@@ -155,7 +155,96 @@ int seam_resize_device(const uint8_t *seam_host, size_t seam_pitch, int sw, int 
 }
 }  // namespace sb
 
+namespace sb {
+void gain_free(GainData *gd, cudaStream_t s)
+{
+    dev_free(gd->map, s);
+    dev_free(gd->fx, s);
+    dev_free(gd->fy, s);
+    dev_free(gd->tx, s);
+    dev_free(gd->ty, s);
+    dev_free(gd->lut, s);
+    *gd = GainData{};
+}
+
+// ExposureErrorCompensator.apply's per-image data on the device: either the float32 gain map (gc = 1 or 3 channels) with
+// the resize taps for a w x h image, or the three 256-entry tables of scalar gains
+int gain_upload(WarpJob *job, GainData *gd, int w, int h, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar,
+                cudaStream_t s)
+{
+    gain_free(gd, s);
+    job->gain_mode = 0;
+    if (gain_scalar) {
+        uint8_t lut[768];
+        gain_scalar_lut(gain_scalar, lut);
+        SB_TRY(dev_alloc((void **)&gd->lut, sizeof lut, s));
+        SB_CUDA(cudaMemcpyAsync(gd->lut, lut, sizeof lut, cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        job->gain_lut = gd->lut;
+        job->gain_mode = 2;
+        return SB_OK;
+    }
+    if (!gain_map) return SB_OK;  // no gain: compensator "no"
+    std::vector<int> tx((size_t)2 * w), ty((size_t)2 * h);
+    std::vector<float> fx((size_t)w), fy((size_t)h);
+    resize_f32_taps(gw, w, tx.data(), fx.data());
+    resize_f32_taps(gh, h, ty.data(), fy.data());
+    SB_TRY(dev_alloc((void **)&gd->map, sizeof(float) * (size_t)gw * gh * gc, s));
+    SB_TRY(dev_alloc((void **)&gd->tx, sizeof(int) * tx.size(), s));
+    SB_TRY(dev_alloc((void **)&gd->ty, sizeof(int) * ty.size(), s));
+    SB_TRY(dev_alloc((void **)&gd->fx, sizeof(float) * fx.size(), s));
+    SB_TRY(dev_alloc((void **)&gd->fy, sizeof(float) * fy.size(), s));
+    SB_CUDA(cudaMemcpyAsync(gd->map, gain_map, sizeof(float) * (size_t)gw * gh * gc, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(gd->tx, tx.data(), sizeof(int) * tx.size(), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(gd->ty, ty.data(), sizeof(int) * ty.size(), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(gd->fx, fx.data(), sizeof(float) * fx.size(), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(gd->fy, fy.data(), sizeof(float) * fy.size(), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    job->gain_map = gd->map;
+    job->gain_tx = gd->tx;
+    job->gain_ty = gd->ty;
+    job->gain_fx = gd->fx;
+    job->gain_fy = gd->fy;
+    job->gain_gw = gw;
+    job->gain_gc = gc;
+    job->gain_mode = 1;
+    return SB_OK;
+}
+}  // namespace sb
+
+static bool valid_gain_args(const float *gain_map, int gw, int gh, int gc, const double *gain_scalar)
+{
+    if (gain_map && gain_scalar) return false;
+    if (gain_map && (gw <= 0 || gh <= 0 || (gc != 1 && gc != 3))) return false;
+    return true;
+}
+
 extern "C" {
+
+int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar)
+{
+    if (!img || w <= 0 || h <= 0 || pitch < (size_t)w * 3 || !valid_gain_args(gain_map, gw, gh, gc, gain_scalar)) {
+        set_error("sb_gain_apply: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    if (!gain_map && !gain_scalar) return SB_OK;  // compensator "no": identity
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    uint8_t *d_img = nullptr;
+    SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
+    SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * 3, img, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, s));
+    WarpJob job;
+    std::memset(&job, 0, sizeof job);
+    GainData gd;
+    int rc = gain_upload(&job, &gd, w, h, gain_map, gw, gh, gc, gain_scalar, s);
+    if (rc == SB_OK) rc = launch_gain_apply(d_img, (long long)w * 3, w, h, job, s);
+    if (rc == SB_OK && cudaMemcpy2DAsync(img, pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        rc = SB_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = SB_ERR_CUDA;
+    gain_free(&gd, s);
+    return rc;
+}
 
 int sb_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const uint8_t *mask, size_t mask_pitch, int w, int h,
                    uint8_t *dst, size_t dst_pitch)

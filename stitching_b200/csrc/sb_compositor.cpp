@@ -44,6 +44,7 @@ struct sb_compositor {
     std::vector<uint32_t *> rgbm_dev;  // warped, packed; row pitch = width rounded up to 32 pixels (128-byte rows)
     std::vector<float *> tab_dev;
     std::vector<uint8_t *> usermask_dev;
+    std::vector<GainData> gain;        // exposure gains per image (sb_compositor_set_gain)
     int max_w = 0, max_h = 0;
     BlendPlan plan;
     PanoOut out{};                     // device outputs
@@ -83,6 +84,7 @@ static void compositor_free(sb_compositor *c)
     for (auto p : c->rgbm_dev) dev_free(p, s);
     for (auto p : c->tab_dev) dev_free(p, s);
     for (auto p : c->usermask_dev) dev_free(p, s);
+    for (auto &g : c->gain) gain_free(&g, s);
     dev_free(c->out.rgb, s);
     dev_free(c->out.mask, s);
     dev_free(c->flush_buf, s);
@@ -153,6 +155,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
     c->rgbm_dev.assign(n, nullptr);
     c->tab_dev.assign(n, nullptr);
     c->usermask_dev.assign(n, nullptr);
+    c->gain.assign(n, GainData{});
     std::vector<int> corners(2 * n), sizes(2 * n);
     std::vector<float> host_tab;
     for (int i = 0; i < n; ++i) {
@@ -571,6 +574,42 @@ int sb_compositor_set_seam_mask(sb_compositor *c, int i, const uint8_t *seam, si
             jx[i].blend_mask_pitch = w;
             jx[i].blend_mask_and = 1;
         }
+#ifndef SB_EMU
+    for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture
+        if (g) {
+            (void)cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+#endif
+    return SB_OK;
+}
+
+int sb_compositor_set_gain(sb_compositor *c, int i, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar)
+{
+    if (!c || i < 0 || i >= c->n || !c->rgbm_dev[i] || (gain_map && gain_scalar) ||
+        (gain_map && (gw <= 0 || gh <= 0 || (gc != 1 && gc != 3)))) {
+        set_error("sb_compositor_set_gain: invalid argument (or an image of another rank)");
+        return SB_ERR_INVALID;
+    }
+    // ExposureErrorCompensator.apply(i, corner, warped image, mask) (exposure_error_compensator.py:43-45,
+    // stitcher.py:219-221) fused into the warp's epilogue: the warped image never exists uncompensated
+    SB_CUDA(cudaStreamSynchronize(c->stream));  // the previous run may still read the old gain buffers
+    WarpJob fields = c->jobs[i];
+    SB_TRY(gain_upload(&fields, &c->gain[i], c->rects[i].w, c->rects[i].h, gain_map, gw, gh, gc, gain_scalar, c->stream));
+    auto copy_gain = [&](WarpJob &j) {
+        j.gain_mode = fields.gain_mode;
+        j.gain_gw = fields.gain_gw;
+        j.gain_gc = fields.gain_gc;
+        j.gain_map = fields.gain_map;
+        j.gain_tx = fields.gain_tx;
+        j.gain_ty = fields.gain_ty;
+        j.gain_fx = fields.gain_fx;
+        j.gain_fy = fields.gain_fy;
+        j.gain_lut = fields.gain_lut;
+    };
+    copy_gain(c->jobs[i]);
+    for (auto &jx : c->jobsx)
+        if (!jx.empty()) copy_gain(jx[i]);
 #ifndef SB_EMU
     for (auto &g : c->graph_exec)  // the jobs are baked into the captured launches: re-capture
         if (g) {

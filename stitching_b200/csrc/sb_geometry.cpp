@@ -266,4 +266,32 @@ void resize_linear_taps(int n_src, int n_dst, bool columns, int *t)
     }
 }
 
+// Taps of cv::resize(float32, INTER_LINEAR) as the reference's wheel computes it for the exposure compensator's gain
+// maps (IPP's kernel; found by hypothesis testing, see oracle/stitch_oracle.c): coordinate in double, fraction rounded
+// to float, zero where the index is clamped.
+void resize_f32_taps(int n_src, int n_dst, int *i0i1, float *fr)
+{
+    const double scale = (double)n_src / (double)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        const double f = ((double)d + 0.5) * scale - 0.5;
+        const int s = (int)std::floor(f);
+        float t = (float)(f - (double)s);
+        if (s < 0 || s >= n_src - 1) t = 0.f;
+        i0i1[d] = std::min(std::max(s, 0), n_src - 1);
+        i0i1[n_dst + d] = std::min(std::max(s + 1, 0), n_src - 1);
+        fr[d] = t;
+    }
+}
+
+// GainCompensator / ChannelsCompensator::apply multiply by a double scalar: saturate_cast<uchar>(cvRound(v * gain)),
+// tabulated for the 256 byte values of each channel
+void gain_scalar_lut(const double gain[3], uint8_t lut[768])
+{
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < 256; ++v) {
+            const double r = std::nearbyint((double)v * gain[c]);
+            lut[c * 256 + v] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+}
+
 }  // namespace sb

@@ -76,6 +76,14 @@ struct WarpJob {
     float k[9];
     int always_divide;  // plane / affine: x/z, y/z unconditionally
     float xin_hi, yin_hi;  // 32 (sw-1) - 0.5, 32 (sh-1) - 0.5: upper limits of x*32, y*32 for a footprint inside the image
+    // exposure compensation of the warped image (ExposureErrorCompensator.apply, stitcher.py:219-221), fused into the
+    // warp's epilogue.  gain_mode 0: none; 1: float32 gain map (gain_gc = 1 or 3 channels) resized to dw x dh through
+    // the per-axis taps below (resize_f32_taps); 2: scalar gains as three 256-entry tables (gain_lut[c * 256 + value])
+    int gain_mode, gain_gw, gain_gc, gain_pad;
+    const float *gain_map;
+    const int *gain_tx, *gain_ty;    // [i0 | i1], dw / dh entries each
+    const float *gain_fx, *gain_fy;  // fractions
+    const uint8_t *gain_lut;
 };
 
 // floats in the device tables of a w x h warp: colX, colZ (each padded to a multiple of 4), rowA, rowY
@@ -189,6 +197,20 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
+// ExposureErrorCompensator.apply: taps of the float32 bilinear resize of a gain map (sb_geometry.cpp), the 256-entry
+// table of a scalar gain, and the host-buffer entry's kernel (sb_warp.cu)
+void resize_f32_taps(int n_src, int n_dst, int *i0i1, float *fr);  // i0i1: 2 * n_dst ints
+void gain_scalar_lut(const double gain[3], uint8_t lut[768]);
+int launch_gain_apply(uint8_t *img, long long pitch, int w, int h, const WarpJob &gain_fields, cudaStream_t s);
+// device copies of one image's gain (map + taps for a w x h target, or the scalar tables) and the WarpJob fields for them
+struct GainData {
+    float *map = nullptr, *fx = nullptr, *fy = nullptr;
+    int *tx = nullptr, *ty = nullptr;
+    uint8_t *lut = nullptr;
+};
+int gain_upload(WarpJob *job, GainData *gd, int w, int h, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar,
+                cudaStream_t s);  // synchronises s
+void gain_free(GainData *gd, cudaStream_t s);
 // SeamFinder.resize (sb_seam.cu, sb_geometry.cpp)
 void resize_linear_taps(int n_src, int n_dst, bool columns, int *t);  // t: 4 * n_dst ints
 int launch_seam_resize(const uint8_t *seam, int sw, int sh, uint8_t *scratch, const int *tx, const int *ty, const uint8_t *mask,

@@ -45,8 +45,43 @@ __device__ __forceinline__ void project(const WarpJob &j, int u, int v, float &x
     }
 }
 
+// ExposureErrorCompensator.apply on one warped pixel (stitching/exposure_error_compensator.py:43-45 -> cv.detail
+// compensators, stitcher.py:219-221), see oracle/stitch_oracle.c for the pinned arithmetic:
+//   mode 1 (gain_blocks / channel_blocks): the float32 gain map resized to the warped size -- horizontal pass first, each
+//     pass a + (b - a) t as ONE fused multiply-add -- then saturate(cvRound(float(value) * gain)) with a float32 product;
+//   mode 2 (gain / channel): saturate(cvRound(double(value) * gain)), tabulated per channel on the host.
+__device__ __forceinline__ void apply_gain(const WarpJob &j, int u, int v, unsigned &r, unsigned &g, unsigned &b)
+{
+    if (j.gain_mode == 2) {
+        r = j.gain_lut[r];
+        g = j.gain_lut[256 + g];
+        b = j.gain_lut[512 + b];
+        return;
+    }
+    const int x0 = j.gain_tx[u], x1 = j.gain_tx[j.dw + u], y0 = j.gain_ty[v], y1 = j.gain_ty[j.dh + v];
+    const float fx = j.gain_fx[u], fy = j.gain_fy[v];
+    const int gc = j.gain_gc;
+    const float *r0 = j.gain_map + (long long)y0 * j.gain_gw * gc, *r1 = j.gain_map + (long long)y1 * j.gain_gw * gc;
+    unsigned c[3] = {r, g, b};
+    float gain = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k == 0 || gc == 3) {
+            const float a0 = r0[x0 * gc + k], b0 = r0[x1 * gc + k], a1 = r1[x0 * gc + k], b1 = r1[x1 * gc + k];
+            const float h0 = fmaf(fadd(b0, -a0), fx, a0), h1 = fmaf(fadd(b1, -a1), fx, a1);
+            gain = fmaf(fadd(h1, -h0), fy, h0);
+        }
+        const int q = __float2int_rn(fmul((float)c[k], gain));  // |value * gain| is far below 2^31
+        c[k] = (unsigned)sat_u8(q);
+    }
+    r = c[0];
+    g = c[1];
+    b = c[2];
+}
+
 __device__ __forceinline__ void store_pixel(const WarpJob &j, int u, int v, unsigned r, unsigned g, unsigned b, unsigned m)
 {
+    if (j.gain_mode) apply_gain(j, u, v, r, g, b);
     if (j.dst_rgb) {
         uint8_t *d = j.dst_rgb + (long long)v * j.dst_pitch + 3 * u;
         d[0] = (uint8_t)r;
@@ -293,15 +328,26 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_
 #pragma unroll
         for (int p = 0; p < 2; ++p) out[p] = sample_general(j.src, j.sw, j.sh, pitch, xn[p], yn[p], zn[p], j.always_divide);
     }
-    if (HAS_BM) {
-        const uint8_t *bm = j.blend_mask + (unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u;
-        // a user blend mask replaces the validity byte; a seam mask (sb_compositor_set_seam_mask) is ANDed with it
+    if (HAS_BM) {  // the batch has per-pixel extras: exposure gains and / or blend masks (each optional per image)
+        if (j.gain_mode) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
-            if (p == 0 || u + 1 < j.dw) {
-                const unsigned b = (unsigned)bm[p] << 24;
-                out[p] = j.blend_mask_and ? (out[p] & (b | 0x00ffffffu)) : ((out[p] & 0x00ffffffu) | b);
-            }
+            for (int p = 0; p < 2; ++p)
+                if (p == 0 || u + 1 < j.dw) {
+                    unsigned r = out[p] & 255u, g = (out[p] >> 8) & 255u, b = (out[p] >> 16) & 255u;
+                    apply_gain(j, u + p, v, r, g, b);
+                    out[p] = (out[p] & 0xff000000u) | r | (g << 8) | (b << 16);
+                }
+        }
+        if (j.blend_mask) {
+            const uint8_t *bm = j.blend_mask + (unsigned)v * (unsigned)j.blend_mask_pitch + (unsigned)u;
+            // a user blend mask replaces the validity byte; a seam mask (sb_compositor_set_seam_mask) is ANDed with it
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+                if (p == 0 || u + 1 < j.dw) {
+                    const unsigned b = (unsigned)bm[p] << 24;
+                    out[p] = j.blend_mask_and ? (out[p] & (b | 0x00ffffffu)) : ((out[p] & 0x00ffffffu) | b);
+                }
+        }
     }
     uint32_t *d = j.dst_rgbm + (unsigned)v * (unsigned)j.rgbm_pitch + (unsigned)u;  // pitch is a multiple of 64: 8-byte aligned
     if (u + 1 < j.dw)
@@ -344,9 +390,8 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
             for (int i = 0; i < cnt; ++i) {
                 rgbm_only = rgbm_only && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767 &&
                             B.j[i].sw >= 2 && B.j[i].sh >= 2 && B.j[i].rgbm_pitch % 2 == 0;
-                has_bm = has_bm || B.j[i].blend_mask;
+                has_bm = has_bm || B.j[i].blend_mask || B.j[i].gain_mode;  // per-pixel extras anywhere in the batch
             }
-            for (int i = 0; i < cnt; ++i) rgbm_only = rgbm_only && (!has_bm || B.j[i].blend_mask);  // all or none
             if (rgbm_only) {
                 dim3 grid2(div_up(max_w, 2 * WARP_BX), div_up(max_h, WARP_BY), cnt);
                 if (has_bm)
@@ -364,6 +409,29 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         SB_TRY(launch_check("k_warp_gather"));
     }
     return SB_OK;
+}
+
+// ExposureErrorCompensator.apply on an image in device memory (the host-buffer entry sb_gain_apply): `g` carries the gain
+// fields of a WarpJob with dw x dh = the image size
+__global__ void k_gain_apply(uint8_t *__restrict__ img, long long pitch, const __grid_constant__ WarpJob g)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.dw || y >= g.dh) return;
+    uint8_t *p = img + y * pitch + 3 * (long long)x;
+    unsigned r = p[0], gg = p[1], b = p[2];
+    apply_gain(g, x, y, r, gg, b);
+    p[0] = (uint8_t)r;
+    p[1] = (uint8_t)gg;
+    p[2] = (uint8_t)b;
+}
+
+int launch_gain_apply(uint8_t *img, long long pitch, int w, int h, const WarpJob &gain_fields, cudaStream_t s)
+{
+    WarpJob g = gain_fields;
+    g.dw = w;
+    g.dh = h;
+    launch(k_gain_apply, dim3(div_up(w, 32), div_up(h, 8)), dim3(32, 8), 0, s, img, pitch, g);
+    return launch_check("k_gain_apply");
 }
 
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,

@@ -208,3 +208,43 @@ def run_gain_goldens(apply_fn):
         gain = g[f"gain_{i}"]
         got = g[f"img_{i}"] if gain.size == 0 else np.asarray(apply_fn(g[f"img_{i}"], gain))  # compensator "no": identity
         assert_exact(got, g[f"out_{i}"], f"compensator apply case {i} ({g[f'kind_{i}']})")
+
+
+def fused_gain_case(oracle, Warper, Blender, Compositor, rigs, scale_down, kinds=("gain_blocks", "channel_blocks", "gain", "channel")):
+    """Compositor.set_gain (gain applied in the warp kernel) against the reference order of operations done with the
+    drop-in classes and the ORACLE's apply in between: warp -> ExposureErrorCompensator.apply -> Blender.feed
+    (stitcher.py:219-221, 254).  One synthetic gain of each kind, cycling over the images."""
+    cfg = rigs.config("cfg2", scale_down)
+    cams = cfg["cameras"]
+    n = len(cams)
+    sizes_in = [(cfg["w"], cfg["h"])] * n
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 80 + i) for i in range(n)]
+    rng = np.random.default_rng(17)
+    gains = []
+    for i in range(n):
+        kind = kinds[i % len(kinds)]
+        if kind == "gain_blocks":
+            gains.append(rng.uniform(0.7, 1.5, (5 + i, 7)).astype(np.float32))
+        elif kind == "channel_blocks":
+            gains.append(rng.uniform(0.7, 1.5, (4, 6 + i, 3)).astype(np.float32))
+        elif kind == "gain":
+            gains.append(np.array([[rng.uniform(0.7, 1.5)]], np.float64))
+        else:
+            gains.append(np.array([[rng.uniform(0.7, 1.5)], [rng.uniform(0.7, 1.5)], [rng.uniform(0.7, 1.5)], [0.0]], np.float64))
+    w = Warper(cfg["warper"])
+    w.set_scale(cams)
+    corners, sizes = w.warp_rois(sizes_in, cams)
+    b = Blender(cfg["blender"], cfg["strength"])
+    b.prepare(corners, sizes)
+    for i in range(n):
+        wi, wm = w.warp_image_and_mask(imgs[i], cams[i])
+        b.feed(oracle.gain_apply(wi, gains[i]), wm, corners[i])
+    ref_pano, ref_mask = b.blend()
+    c = Compositor(cams, sizes_in, cfg["warper"], cfg["blender"], cfg["strength"])
+    for i in range(n):
+        c.set_gain(i, gains[i])
+    pano, mask = c.composite(imgs)
+    c.set_gain(0, None)  # and it can be removed again
+    pano0, _ = c.composite(imgs)
+    c.close()
+    return (pano, mask), (ref_pano, ref_mask), pano0

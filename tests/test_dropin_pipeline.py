@@ -53,6 +53,9 @@ def synthetic_views(cv):
         R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
         H = K @ R @ np.linalg.inv(Ks)
         views.append(cv.warpPerspective(scene, H, (w, h)))
+    # different exposures, so that the exposure compensator has something to do
+    views[0] = np.clip(views[0].astype(np.float32) * 0.82, 0, 255).astype(np.uint8)
+    views[2] = np.clip(views[2].astype(np.float32) * 1.12, 0, 255).astype(np.uint8)
     return views
 
 
@@ -107,15 +110,31 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
         log.append(("seam_resize", seam_mask, np.array(mask).copy(), out.get() if hasattr(out, "get") else np.array(out)))
         return out
 
+    from stitching.exposure_error_compensator import ExposureErrorCompensator as RefCompensator
+
+    ref_apply = RefCompensator.apply
+
+    def rec_apply(self, *args):
+        idx, _corner, img, _mask = args
+        before = np.array(img).copy()
+        gain = np.array(self.compensator.getMatGains()[idx]).copy()
+        out = ref_apply(self, *args)
+        log.append(("gain_apply", gain, before, np.array(out.get() if hasattr(out, "get") else out).copy()))
+        return out
+
     stitching.stitcher.Warper, stitching.stitcher.Blender = RecWarper, RecBlender
     RefSeamFinder.resize = staticmethod(rec_resize)
+    RefCompensator.apply = rec_apply
     try:
         stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in synthetic_views(cv)])
     finally:
         RefSeamFinder.resize = staticmethod(ref_resize)
+        RefCompensator.apply = ref_apply
     kinds = [e[0] for e in log]
     assert kinds.count("warp_image") >= 6 and kinds.count("feed") == 3 and kinds.count("blend") == 1
     assert kinds.count("seam_resize") == 3, "stitcher.py:223-225 resizes one seam mask per image"
+    applied = [e for e in log if e[0] == "gain_apply"]
+    assert len(applied) == 3 and any(not np.array_equal(e[2], e[3]) for e in applied), "stitcher.py:219-221 compensates every image"
     assert any(type(e[2]).__name__ == "UMat" for e in log if e[0] == "feed"), "the pipeline hands cv.UMat masks to feed"
 
     blender = None
@@ -129,6 +148,10 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
                 assert tuple(got) == e[6]
             else:
                 assert got.shape == e[6].shape and np.array_equal(got, e[6]), f"{e[0]}: {int((got != e[6]).sum())} values differ"
+            checked += 1
+        elif e[0] == "gain_apply":  # the default compensator (gain_blocks) with the gains its own feed() estimated
+            got = stitching_b200.exposure_error_compensator.apply_gain(e[2].copy(), e[1])
+            assert np.array_equal(got, e[3]), f"ExposureErrorCompensator.apply: {int((got != e[3]).sum())} values differ"
             checked += 1
         elif e[0] == "seam_resize":  # the LOW-resolution seam mask arrives as cv.UMat, the warped mask as ndarray
             got = stitching_b200.seam_finder.resize(e[1], e[2])
@@ -145,7 +168,7 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
             d = np.abs(pano.astype(np.int32) - e[1].astype(np.int32))
             assert d.max() == 0, f"panorama: max |diff| {int(d.max())}, {int((d != 0).sum())} values"
             checked += 1
-    assert checked >= 16
+    assert checked >= 19
 
 
 def test_stitcher_runs_end_to_end_on_the_swapped_classes(reference_stitching, use_emu):

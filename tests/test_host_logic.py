@@ -235,3 +235,21 @@ def test_seam_resize_drop_in_and_fused(use_emu, oracle):
     assert not np.array_equal(pb, plain), "the seam masks must change the blend"
     a.close()
     b.close()
+
+
+def test_exposure_gain_drop_in_and_fused(use_emu, oracle):
+    """ExposureErrorCompensator.apply through the C ABI == the reference's goldens == the oracle; the fused
+    Compositor.set_gain == warp -> apply -> feed."""
+    from stitching_b200 import exposure_error_compensator as ec
+
+    replay.run_gain_goldens(lambda img, gain: ec.apply_gain(img.copy(), gain))
+    rng = np.random.default_rng(21)
+    for t in range(8):
+        h, w = int(rng.integers(20, 160)), int(rng.integers(20, 200))
+        img = rigs.noise_image(h, w, 300 + t)
+        gain = rng.uniform(0.5, 2.5, (int(rng.integers(1, 9)), int(rng.integers(1, 9))) + ((3,) if t % 2 else ())).astype(np.float32)
+        replay.assert_exact(ec.apply_gain(img.copy(), gain), oracle.gain_apply(img, gain), f"gain map fuzz {t}")
+    got, ref, pano0 = replay.fused_gain_case(oracle, Warper, Blender, Compositor, rigs, 25)
+    replay.assert_exact(got[0], ref[0], "pano with fused exposure gains")
+    replay.assert_exact(got[1], ref[1], "mask with fused exposure gains")
+    assert not np.array_equal(got[0], pano0), "removing a gain must change the panorama back"

@@ -1,0 +1,30 @@
+"""ExposureErrorCompensator.apply on the device: the reference's goldens, fuzz against the oracle and the
+fused Compositor.set_gain, through the real library.  Kept in its own file, last in collection order."""
+import numpy as np
+import pytest
+
+import replay
+from stitching_b200 import Blender, Compositor, Warper, rigs
+from stitching_b200 import exposure_error_compensator as ec
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gain_apply_goldens_and_fuzz(cuda_lib, oracle):
+    replay.run_gain_goldens(lambda img, gain: ec.apply_gain(img.copy(), gain))
+    rng = np.random.default_rng(22)
+    for t in range(12):
+        h, w = int(rng.integers(20, 900)), int(rng.integers(20, 1200))
+        img = rigs.noise_image(h, w, 400 + t)
+        if t % 3 == 2:
+            gain = np.array([[rng.uniform(0.4, 2.5)]], np.float64)
+        else:
+            gain = rng.uniform(0.5, 2.5, (int(rng.integers(1, 40)), int(rng.integers(1, 50))) + ((3,) if t % 3 else ())).astype(np.float32)
+        replay.assert_exact(ec.apply_gain(img.copy(), gain), oracle.gain_apply(img, gain), f"gain fuzz {t}")
+
+
+def test_fused_gain_in_the_compositor(cuda_lib, oracle):
+    got, ref, pano0 = replay.fused_gain_case(oracle, Warper, Blender, Compositor, rigs, 4)
+    replay.assert_exact(got[0], ref[0], "pano with fused exposure gains")
+    replay.assert_exact(got[1], ref[1], "mask with fused exposure gains")
+    assert not np.array_equal(got[0], pano0)
