@@ -71,6 +71,12 @@ SB_API int sb_warp_roi(int warp_type, float scale, const float K[9], const float
 SB_API int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_map, int gw, int gh, int gc,
                          const double *gain_scalar);
 
+/* images.py:120-123 Images.resize_img_by_scaler -> cv.resize(img, (dw, dh), interpolation=cv.INTER_LINEAR_EXACT) on a
+ * uint8 image of 1 or 3 channels with host buffers (the step that produces the MEDIUM / LOW / FINAL resolution inputs
+ * of the pipeline; OpenCV's bit-exact fixed-point bilinear, any scale). */
+SB_API int sb_resize_exact(const uint8_t *src, size_t src_pitch, int sw, int sh, int channels, uint8_t *dst, size_t dst_pitch,
+                           int dw, int dh);
+
 /* seam_finder.py:38-43 SeamFinder.resize(seam_mask, mask) with host buffers:
  *   dst = cv.bitwise_and(cv.resize(cv.dilate(seam_mask, None), (w, h), 0, 0, cv.INTER_LINEAR_EXACT), mask)
  * (the positional arguments of that cv.resize call select its default INTER_LINEAR; reproduced bit for bit).

@@ -64,6 +64,7 @@ def lib():
         L.so_sb_blend.argtypes = [C.c_void_p, s16p, u8p]
         L.so_convert_scale_abs_s16.argtypes = [s16p, C.c_size_t, u8p]
         L.so_resize_linear_f32.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+        L.so_resize_linear_exact_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.so_gain_apply_blocks.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int]
         L.so_gain_apply_scalar.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.so_dilate3x3_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
@@ -206,6 +207,17 @@ def seam_resize(seam_mask, mask):
     out = np.empty((h, w), np.uint8)
     lib().so_seam_resize(_p(seam_mask, C.c_uint8), seam_mask.strides[0], sw, sh, _p(mask, C.c_uint8), mask.strides[0], w, h,
                          _p(out, C.c_uint8))
+    return out
+
+
+def resize_linear_exact(a, size):
+    """cv.resize(a, size, interpolation=cv.INTER_LINEAR_EXACT) for a uint8 image of 1 or 3 channels (images.py:120-123);
+    size = (w, h)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    h, w = a.shape[:2]
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    out = np.empty((int(size[1]), int(size[0])) + (() if a.ndim == 2 else (cn,)), np.uint8)
+    lib().so_resize_linear_exact_u8(_p(a, C.c_uint8), a.strides[0], w, h, cn, int(size[0]), int(size[1]), _p(out, C.c_uint8))
     return out
 
 

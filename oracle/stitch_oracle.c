@@ -873,6 +873,51 @@ SO_API void so_gain_apply_blocks(uint8_t *img, size_t pitch, int w, int h, const
     free(g);
 }
 
+/* ----------------------------------------------------------------------------------------
+ * Images.resize_img_by_scaler (stitching/images.py:120-123): cv.resize(img, size, interpolation=cv.INTER_LINEAR_EXACT)
+ * on uint8 images (here the constant IS passed by keyword).  OpenCV's bit-exact fixed-point path: per axis
+ *   f = (d + 0.5) * (n_src / n_dst) - 0.5 in double, i0 = floor(f), weight c1 = cvRound((f - i0) * 256) in 8.8 fixed
+ *   point, c0 = 256 - c1; a clamped index takes the edge sample with weight 256;
+ *   horizontal pass in 8.8 (exact), vertical pass in 16.16, result (v + 2^15) >> 16.  Any scale, any channel count
+ *   (an exact 2x reduction comes out as the 2x2 box average by itself).
+ * 0 mismatches against cv2 4.13 over random sizes / scales 0.08 .. 3 / 1 and 3 channels; pinned against the reference
+ * function by tests/golden/gen_golden.py -> golden_resize.npz.
+ * ---------------------------------------------------------------------------------------- */
+static void resize_exact_taps(int n_src, int n_dst, int *i0, int *i1, int *c1)
+{
+    const double scale = (double)n_src / (double)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        const double f = ((double)d + 0.5) * scale - 0.5;
+        int a = (int)floor(f);
+        int w1 = (int)nearbyint((f - (double)a) * 256.0);
+        if (a < 0 || a >= n_src - 1) w1 = 0;
+        i0[d] = a < 0 ? 0 : (a > n_src - 1 ? n_src - 1 : a);
+        i1[d] = a + 1 < 0 ? 0 : (a + 1 > n_src - 1 ? n_src - 1 : a + 1);
+        c1[d] = w1;
+    }
+}
+
+SO_API void so_resize_linear_exact_u8(const uint8_t *src, size_t pitch, int sw, int sh, int cn, int dw, int dh, uint8_t *dst)
+{
+    int *tx = (int *)malloc(sizeof(int) * 3 * (size_t)dw), *ty = (int *)malloc(sizeof(int) * 3 * (size_t)dh);
+    resize_exact_taps(sw, dw, tx, tx + dw, tx + 2 * dw);
+    resize_exact_taps(sh, dh, ty, ty + dh, ty + 2 * dh);
+    for (int y = 0; y < dh; ++y) {
+        const uint8_t *r0 = src + (size_t)ty[y] * pitch, *r1 = src + (size_t)ty[dh + y] * pitch;
+        const unsigned cy1 = (unsigned)ty[2 * dh + y], cy0 = 256u - cy1;
+        for (int x = 0; x < dw; ++x) {
+            const unsigned cx1 = (unsigned)tx[2 * dw + x], cx0 = 256u - cx1;
+            for (int c = 0; c < cn; ++c) {
+                const unsigned h0 = r0[tx[x] * cn + c] * cx0 + r0[tx[dw + x] * cn + c] * cx1; /* 8.8 */
+                const unsigned h1 = r1[tx[x] * cn + c] * cx0 + r1[tx[dw + x] * cn + c] * cx1;
+                dst[((size_t)y * dw + x) * cn + c] = (uint8_t)((h0 * cy0 + h1 * cy1 + (1u << 15)) >> 16);
+            }
+        }
+    }
+    free(tx);
+    free(ty);
+}
+
 /* GainCompensator / ChannelsCompensator::apply: one double gain per channel */
 SO_API void so_gain_apply_scalar(uint8_t *img, size_t pitch, int w, int h, const double gain[3])
 {

@@ -5,7 +5,7 @@ interface) backed by hand-written CUDA kernels behind a C ABI (include/stitch_b2
 `install()` swaps them into an installed `stitching` package so that Stitcher / AffineStitcher / the CLI run
 unchanged.
 """
-from . import exposure_error_compensator, seam_finder  # noqa: F401
+from . import exposure_error_compensator, images, seam_finder  # noqa: F401
 from .blender import Blender  # noqa: F401
 from .compositor import Compositor  # noqa: F401
 from .stitching_error import StitchingError, StitchingWarning  # noqa: F401
@@ -40,6 +40,12 @@ def install(stitching_module=None):
     try:
         sf = importlib.import_module(f"{pkg}.seam_finder")
         sf.SeamFinder.resize = staticmethod(seam_finder.resize)
+    except Exception:
+        pass
+    # the resampling to MEDIUM / LOW / FINAL resolution (images.py:120-123)
+    try:
+        im = importlib.import_module(f"{pkg}.images")
+        im.Images.resize_img_by_scaler = staticmethod(images.resize_img_by_scaler)
     except Exception:
         pass
     # the FINAL-resolution step of the exposure compensator (exposure_error_compensator.py:43-45)

@@ -246,6 +246,36 @@ int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_ma
     return rc;
 }
 
+int sb_resize_exact(const uint8_t *src, size_t src_pitch, int sw, int sh, int channels, uint8_t *dst, size_t dst_pitch, int dw, int dh)
+{
+    if (!src || !dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || (channels != 1 && channels != 3) ||
+        src_pitch < (size_t)sw * channels || dst_pitch < (size_t)dw * channels || (long long)sw * sh * channels > (1ll << 31) ||
+        (long long)dw * dh * channels > (1ll << 31)) {
+        set_error("sb_resize_exact: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    int *d_tx = nullptr, *d_ty = nullptr;
+    const size_t srow = (size_t)sw * channels, drow = (size_t)dw * channels;
+    SB_TRY(tmp.get(&d_src, srow * sh));
+    SB_TRY(tmp.get(&d_dst, drow * dh));
+    SB_TRY(tmp.get(&d_tx, (size_t)3 * dw));
+    SB_TRY(tmp.get(&d_ty, (size_t)3 * dh));
+    std::vector<int> tx((size_t)3 * dw), ty((size_t)3 * dh);
+    resize_exact_taps(sw, dw, tx.data());
+    resize_exact_taps(sh, dh, ty.data());
+    SB_CUDA(cudaMemcpy2DAsync(d_src, srow, src, src_pitch, srow, sh, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(d_tx, tx.data(), tx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(d_ty, ty.data(), ty.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    SB_TRY(launch_resize_exact(d_src, (long long)srow, channels, d_tx, d_ty, d_dst, (long long)drow, dw, dh, s));
+    SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d_dst, drow, drow, dh, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
+}
+
 int sb_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const uint8_t *mask, size_t mask_pitch, int w, int h,
                    uint8_t *dst, size_t dst_pitch)
 {

@@ -283,6 +283,23 @@ void resize_f32_taps(int n_src, int n_dst, int *i0i1, float *fr)
     }
 }
 
+// Taps of cv::resize(uint8, INTER_LINEAR_EXACT) (Images.resize_img_by_scaler, images.py:120-123): OpenCV's bit-exact
+// path -- coordinate in double, weight cvRound(fraction * 256) in 8.8 fixed point, a clamped index takes the edge sample
+// with full weight.  t = [i0 | i1 | c1], n_dst entries each (c0 = 256 - c1).
+void resize_exact_taps(int n_src, int n_dst, int *t)
+{
+    const double scale = (double)n_src / (double)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        const double f = ((double)d + 0.5) * scale - 0.5;
+        const int a = (int)std::floor(f);
+        int w1 = (int)std::nearbyint((f - (double)a) * 256.0);
+        if (a < 0 || a >= n_src - 1) w1 = 0;
+        t[d] = std::min(std::max(a, 0), n_src - 1);
+        t[n_dst + d] = std::min(std::max(a + 1, 0), n_src - 1);
+        t[2 * (size_t)n_dst + d] = w1;
+    }
+}
+
 // GainCompensator / ChannelsCompensator::apply multiply by a double scalar: saturate_cast<uchar>(cvRound(v * gain)),
 // tabulated for the 256 byte values of each channel
 void gain_scalar_lut(const double gain[3], uint8_t lut[768])

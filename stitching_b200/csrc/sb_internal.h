@@ -211,6 +211,10 @@ struct GainData {
 int gain_upload(WarpJob *job, GainData *gd, int w, int h, const float *gain_map, int gw, int gh, int gc, const double *gain_scalar,
                 cudaStream_t s);  // synchronises s
 void gain_free(GainData *gd, cudaStream_t s);
+// Images.resize_img_by_scaler: cv.resize(uint8, INTER_LINEAR_EXACT) (sb_seam.cu, sb_geometry.cpp)
+void resize_exact_taps(int n_src, int n_dst, int *t);  // t: 3 * n_dst ints
+int launch_resize_exact(const uint8_t *src, long long spitch, int cn, const int *tx, const int *ty, uint8_t *dst, long long dpitch, int w,
+                        int h, cudaStream_t s);
 // SeamFinder.resize (sb_seam.cu, sb_geometry.cpp)
 void resize_linear_taps(int n_src, int n_dst, bool columns, int *t);  // t: 4 * n_dst ints
 int launch_seam_resize(const uint8_t *seam, int sw, int sh, uint8_t *scratch, const int *tx, const int *ty, const uint8_t *mask,

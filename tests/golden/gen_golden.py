@@ -263,6 +263,28 @@ def gen_gain():
     print("gain cases", k)
 
 
+def gen_resize():
+    """Images.resize_img_by_scaler (stitching/images.py:120-123) of the unmodified reference with its own scalers
+    (megapix_scaler.py): full-size views down to MEDIUM / LOW / FINAL-like resolutions, plus an upscale."""
+    from stitching.images import Images as RefImages
+    from stitching.megapix_scaler import MegapixDownscaler, MegapixScaler
+
+    out = {}
+    k = 0
+    for (h, w, mp, up) in ((150, 200, 0.015, False), (129, 195, 0.003, False), (150, 200, 0.0075, False), (64, 48, 0.000768, False),
+                           (60, 45, 0.005, True), (100, 150, -1, False)):
+        img = rigs.noise_image(h, w, 800 + k) if k % 2 else rigs.synth_image(h, w, 800 + k)
+        scaler = (MegapixScaler if up else MegapixDownscaler)(mp)
+        scaler.set_scale_by_img_size((w, h))
+        out[f"img_{k}"] = img
+        out[f"size_{k}"] = np.array(scaler.get_scaled_img_size((w, h)), np.int64)
+        out[f"out_{k}"] = RefImages.resize_img_by_scaler(scaler, (w, h), img)
+        k += 1
+    out["n"] = k
+    np.savez_compressed(os.path.join(HERE, "golden_resize.npz"), **out)
+    print("resize cases", k, [tuple(out[f"size_{i}"]) for i in range(k)])
+
+
 if __name__ == "__main__":
     print("cv2", cv.__version__)
     gen_warp()
@@ -271,6 +293,7 @@ if __name__ == "__main__":
     gen_e2e()
     gen_seam()
     gen_gain()
+    gen_resize()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

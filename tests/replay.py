@@ -201,6 +201,14 @@ def seam_masks_low(ref_masks, ratio=3.17, seed=0):
     return out
 
 
+def run_resize_goldens(resize_fn):
+    """Images.resize_img_by_scaler goldens (tests/golden/golden_resize.npz): resize_fn(img, (w, h)) -> image."""
+    g = load("golden_resize.npz")
+    for i in range(int(g["n"])):
+        size = tuple(int(v) for v in g[f"size_{i}"])
+        assert_exact(np.asarray(resize_fn(g[f"img_{i}"], size)), g[f"out_{i}"], f"Images.resize case {i} -> {size}")
+
+
 def run_gain_goldens(apply_fn):
     """ExposureErrorCompensator.apply goldens (tests/golden/golden_gain.npz): apply_fn(img, gain) -> image."""
     g = load("golden_gain.npz")

@@ -122,17 +122,29 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
         log.append(("gain_apply", gain, before, np.array(out.get() if hasattr(out, "get") else out).copy()))
         return out
 
+    from stitching.images import Images as RefImages
+
+    ref_img_resize = RefImages.resize_img_by_scaler
+
+    def rec_img_resize(scaler, size, img):
+        out = ref_img_resize(scaler, size, img)
+        log.append(("img_resize", np.array(img).copy(), scaler.get_scaled_img_size(size), np.array(out).copy()))
+        return out
+
     stitching.stitcher.Warper, stitching.stitcher.Blender = RecWarper, RecBlender
     RefSeamFinder.resize = staticmethod(rec_resize)
     RefCompensator.apply = rec_apply
+    RefImages.resize_img_by_scaler = staticmethod(rec_img_resize)
     try:
         stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in synthetic_views(cv)])
     finally:
         RefSeamFinder.resize = staticmethod(ref_resize)
         RefCompensator.apply = ref_apply
+        RefImages.resize_img_by_scaler = staticmethod(ref_img_resize)
     kinds = [e[0] for e in log]
     assert kinds.count("warp_image") >= 6 and kinds.count("feed") == 3 and kinds.count("blend") == 1
     assert kinds.count("seam_resize") == 3, "stitcher.py:223-225 resizes one seam mask per image"
+    assert kinds.count("img_resize") >= 6, "images.py:120-123 resamples every image to the working resolutions"
     applied = [e for e in log if e[0] == "gain_apply"]
     assert len(applied) == 3 and any(not np.array_equal(e[2], e[3]) for e in applied), "stitcher.py:219-221 compensates every image"
     assert any(type(e[2]).__name__ == "UMat" for e in log if e[0] == "feed"), "the pipeline hands cv.UMat masks to feed"
@@ -148,6 +160,10 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
                 assert tuple(got) == e[6]
             else:
                 assert got.shape == e[6].shape and np.array_equal(got, e[6]), f"{e[0]}: {int((got != e[6]).sum())} values differ"
+            checked += 1
+        elif e[0] == "img_resize":  # images.py:120-123: the MEDIUM / LOW / FINAL resolution inputs
+            got = stitching_b200.images.resize_exact(e[1], e[2])
+            assert got.shape == e[3].shape and np.array_equal(got, e[3]), f"Images.resize: {int((got != e[3]).sum())} values differ"
             checked += 1
         elif e[0] == "gain_apply":  # the default compensator (gain_blocks) with the gains its own feed() estimated
             got = stitching_b200.exposure_error_compensator.apply_gain(e[2].copy(), e[1])

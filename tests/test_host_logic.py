@@ -237,6 +237,27 @@ def test_seam_resize_drop_in_and_fused(use_emu, oracle):
     b.close()
 
 
+def test_image_resize_drop_in(use_emu, oracle):
+    """Images.resize_img_by_scaler through the C ABI == the reference's goldens == the oracle."""
+    from stitching_b200 import images
+
+    replay.run_resize_goldens(images.resize_exact)
+    rng = np.random.default_rng(31)
+    for t in range(10):
+        sh, sw = int(rng.integers(2, 120)), int(rng.integers(2, 160))
+        sc = rng.uniform(0.1, 1.0) if t % 3 else rng.uniform(1.0, 3.0)
+        size = (max(1, int(round(sw * sc))), max(1, int(round(sh * sc))))
+        src = rng.integers(0, 256, (sh, sw, 3) if t % 2 else (sh, sw), dtype=np.uint8)
+        replay.assert_exact(images.resize_exact(src, size), oracle.resize_linear_exact(src, size), f"resize fuzz {t}")
+
+    class Scaler:  # what megapix_scaler.py's scalers offer to images.py:120-123
+        def get_scaled_img_size(self, size):
+            return (size[0] // 3, size[1] // 3)
+
+    img = rigs.synth_image(90, 120, 1)
+    assert images.resize_img_by_scaler(Scaler(), (120, 90), img).shape == (30, 40, 3)
+
+
 def test_exposure_gain_drop_in_and_fused(use_emu, oracle):
     """ExposureErrorCompensator.apply through the C ABI == the reference's goldens == the oracle; the fused
     Compositor.set_gain == warp -> apply -> feed."""

@@ -35,6 +35,11 @@ def test_oracle_seam_resize_goldens(oracle):
         replay.assert_exact(oracle.seam_resize(g[f"seam_{i}"], g[f"mask_{i}"]), g[f"out_{i}"], f"seam resize case {i}")
 
 
+def test_oracle_image_resize_goldens(oracle):
+    """Images.resize_img_by_scaler of the reference (cv.resize INTER_LINEAR_EXACT) == the oracle's restatement."""
+    replay.run_resize_goldens(oracle.resize_linear_exact)
+
+
 def test_oracle_gain_apply_goldens(oracle):
     """ExposureErrorCompensator.apply of the reference (all five compensators) == the oracle's restatement."""
     replay.run_gain_goldens(oracle.gain_apply)

@@ -23,6 +23,20 @@ def test_gain_apply_goldens_and_fuzz(cuda_lib, oracle):
         replay.assert_exact(ec.apply_gain(img.copy(), gain), oracle.gain_apply(img, gain), f"gain fuzz {t}")
 
 
+def test_image_resize_goldens_and_fuzz(cuda_lib, oracle):
+    """Images.resize_img_by_scaler (cv.resize INTER_LINEAR_EXACT) on the device."""
+    from stitching_b200 import images
+
+    replay.run_resize_goldens(images.resize_exact)
+    rng = np.random.default_rng(32)
+    for t in range(12):
+        sh, sw = int(rng.integers(2, 1200)), int(rng.integers(2, 1600))
+        sc = rng.uniform(0.05, 1.0) if t % 3 else rng.uniform(1.0, 3.0)
+        size = (max(1, int(round(sw * sc))), max(1, int(round(sh * sc))))
+        src = rng.integers(0, 256, (sh, sw, 3) if t % 2 else (sh, sw), dtype=np.uint8)
+        replay.assert_exact(images.resize_exact(src, size), oracle.resize_linear_exact(src, size), f"resize fuzz {t}")
+
+
 def test_fused_gain_in_the_compositor(cuda_lib, oracle):
     got, ref, pano0 = replay.fused_gain_case(oracle, Warper, Blender, Compositor, rigs, 4)
     replay.assert_exact(got[0], ref[0], "pano with fused exposure gains")
