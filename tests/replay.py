@@ -218,6 +218,40 @@ def run_gain_goldens(apply_fn):
         assert_exact(got, g[f"out_{i}"], f"compensator apply case {i} ({g[f'kind_{i}']})")
 
 
+def fused_chain_case(oracle, Warper, Blender, Compositor, rigs, scale_down):
+    """The whole FINAL-resolution chain fused in the compositor -- warp, exposure gain, seam mask, blend -- against the
+    reference order of operations with the drop-in classes and the oracle's apply / SeamFinder.resize in between
+    (stitcher.py:219-225, 254)."""
+    cfg = rigs.config("cfg2", scale_down)
+    cams = cfg["cameras"]
+    n = len(cams)
+    sizes_in = [(cfg["w"], cfg["h"])] * n
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 90 + i) if i % 2 else rigs.synth_image(cfg["h"], cfg["w"], 90 + i) for i in range(n)]
+    rng = np.random.default_rng(19)
+    gains = [rng.uniform(0.75, 1.4, (4 + i % 3, 6)).astype(np.float32) if i % 3 else None for i in range(n)]  # some images without
+    w = Warper(cfg["warper"])
+    w.set_scale(cams)
+    corners, sizes = w.warp_rois(sizes_in, cams)
+    warped = [w.warp_image_and_mask(imgs[i], cams[i]) for i in range(n)]
+    seams = seam_masks_low([m for _, m in warped], seed=3)
+    b = Blender(cfg["blender"], cfg["strength"])
+    b.prepare(corners, sizes)
+    for i in range(n):
+        wi, wm = warped[i]
+        if gains[i] is not None:
+            wi = oracle.gain_apply(wi, gains[i])
+        b.feed(wi, oracle.seam_resize(seams[i], wm) if i != 1 else wm, corners[i])  # image 1 keeps its validity mask
+    ref = b.blend()
+    c = Compositor(cams, sizes_in, cfg["warper"], cfg["blender"], cfg["strength"])
+    for i in range(n):
+        c.set_gain(i, gains[i])
+        if i != 1:
+            c.set_seam_mask(i, seams[i])
+    got = c.composite(imgs)
+    c.close()
+    return got, ref
+
+
 def fused_gain_case(oracle, Warper, Blender, Compositor, rigs, scale_down, kinds=("gain_blocks", "channel_blocks", "gain", "channel")):
     """Compositor.set_gain (gain applied in the warp kernel) against the reference order of operations done with the
     drop-in classes and the ORACLE's apply in between: warp -> ExposureErrorCompensator.apply -> Blender.feed

@@ -237,6 +237,13 @@ def test_seam_resize_drop_in_and_fused(use_emu, oracle):
     b.close()
 
 
+def test_fused_final_resolution_chain(use_emu, oracle):
+    """Gains and seam masks together (some images with neither): compositor == warp -> apply -> SeamFinder.resize -> feed."""
+    got, ref = replay.fused_chain_case(oracle, Warper, Blender, Compositor, rigs, 25)
+    replay.assert_exact(got[0], ref[0], "pano of the fused chain")
+    replay.assert_exact(got[1], ref[1], "mask of the fused chain")
+
+
 def test_image_resize_drop_in(use_emu, oracle):
     """Images.resize_img_by_scaler through the C ABI == the reference's goldens == the oracle."""
     from stitching_b200 import images

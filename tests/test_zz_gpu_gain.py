@@ -23,6 +23,13 @@ def test_gain_apply_goldens_and_fuzz(cuda_lib, oracle):
         replay.assert_exact(ec.apply_gain(img.copy(), gain), oracle.gain_apply(img, gain), f"gain fuzz {t}")
 
 
+def test_fused_final_resolution_chain(cuda_lib, oracle):
+    """Gains and seam masks together in the fast warp kernel's extras path."""
+    got, ref = replay.fused_chain_case(oracle, Warper, Blender, Compositor, rigs, 4)
+    replay.assert_exact(got[0], ref[0], "pano of the fused chain")
+    replay.assert_exact(got[1], ref[1], "mask of the fused chain")
+
+
 def test_image_resize_goldens_and_fuzz(cuda_lib, oracle):
     """Images.resize_img_by_scaler (cv.resize INTER_LINEAR_EXACT) on the device."""
     from stitching_b200 import images
