@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY) k_warp_gather(const __grid_c
     store_pixel(j, u, v, out[0], out[1], out[2], m);
 }
 
-#ifndef SB_EMU
 // Fast variant: the two horizontally adjacent source pixels of a bilinear footprint are 6 contiguous bytes;
 // fetch them with one (or two) aligned 8-byte loads instead of six byte loads.  Callers allocate the source
 // with SB_SRC_PAD spare bytes so that the second aligned word may straddle the end of the image.
@@ -257,7 +256,7 @@ __device__ __forceinline__ unsigned lerp6(unsigned l0, unsigned h0, unsigned l1,
 // the general rule for one pixel, from the projected numerators: exact division, x86 rounding, int16 saturation,
 // BORDER_REFLECT, validity from the nearest-neighbour test.  Called for the few pixels the streamlined path of
 // k_warp_rgbm does not cover (footprint on the border or outside, z <= 0, values outside the shortcut's ranges).
-__device__ __noinline__ unsigned sample_general(const uint8_t *__restrict__ src, int sw, int sh, unsigned pitch, float x, float y,
+__device__ SB_NOINLINE unsigned sample_general(const uint8_t *__restrict__ src, int sw, int sh, unsigned pitch, float x, float y,
                                                 float z, int always_divide)
 {
     if (always_divide || z > 0.f) {
@@ -355,7 +354,6 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_
     else
         d[0] = out[0];
 }
-#endif  // SB_EMU
 
 __global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch, const uint8_t *__restrict__ mask,
                             long long mask_pitch, uint32_t *__restrict__ dst, long long dst_pitch, int w, int h)
@@ -384,7 +382,6 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         for (int i = cnt; i < SB_WARP_BATCH; ++i) B.j[i] = B.j[0];
         if (max_w <= 0 || max_h <= 0) continue;
         dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), cnt);
-#ifndef SB_EMU
         if (!use_simple_kernels()) {
             bool rgbm_only = true, has_bm = false;
             for (int i = 0; i < cnt; ++i) {
@@ -404,7 +401,6 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
             SB_TRY(launch_check("k_warp_wide"));
             continue;
         }
-#endif
         launch(k_warp_gather, grid, block, 0, s, B);
         SB_TRY(launch_check("k_warp_gather"));
     }
