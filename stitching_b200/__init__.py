@@ -59,3 +59,12 @@ def install(stitching_module=None):
     except Exception:
         pass
     return stitching_module
+
+
+def __getattr__(name):
+    """`stitching_b200.Stitcher` / `stitching_b200.AffineStitcher` (stitching/__init__.py:1): the reference's pipeline
+    classes -- same DEFAULT_SETTINGS, same CLI -- running on the B200 classes.  They live in the reference package
+    (registration, seam estimation, cropping ... are its control plane); install() routes their hot path here."""
+    if name in ("Stitcher", "AffineStitcher"):
+        return getattr(install(), name)
+    raise AttributeError(f"module 'stitching_b200' has no attribute {name!r}")

@@ -195,6 +195,9 @@ def test_stitcher_runs_end_to_end_on_the_swapped_classes(reference_stitching, us
     ref_pano = stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in views])
     stitching_b200.install(stitching)
     assert stitching.stitcher.Warper is stitching_b200.Warper and stitching.stitcher.Blender is stitching_b200.Blender
+    # the package surface of stitching/__init__.py:1, with the reference's own settings
+    assert stitching_b200.Stitcher is stitching.Stitcher and stitching_b200.AffineStitcher is stitching.AffineStitcher
+    assert stitching_b200.Stitcher.DEFAULT_SETTINGS["warper_type"] == "spherical"
     pano = stitching.Stitcher(**SETTINGS).stitch([v.copy() for v in views])
     # registration is re-estimated (RANSAC): same geometry up to a few pixels, same kind of picture
     assert pano.ndim == 3 and pano.dtype == np.uint8
