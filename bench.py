@@ -234,6 +234,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def set_extras(comp):
+    """--extras: the other two FINAL-resolution steps of the pipeline fused into the step: a
+    synthetic exposure gain map (one sample per 32x32 block, as gain_blocks estimates) and a LOW-resolution seam mask
+    (keeps the middle three quarters of every image; the overlaps of the ring stay covered) per image."""
+    rng = np.random.default_rng(5)
+    for i, (_x, _y, w, h) in enumerate(comp.rects):
+        comp.set_gain(i, rng.uniform(0.9, 1.1, (max(1, h // 32), max(1, w // 32))).astype(np.float32))
+        sh, sw = max(2, int(round(h / 3.2))), max(2, int(round(w / 3.2)))
+        seam = np.zeros((sh, sw), np.uint8)
+        seam[:, sw // 8: sw - sw // 8] = 255
+        comp.set_seam_mask(i, seam)
+
+
 def run_ours(args, rank, local_rank, world):
     from stitching_b200 import Compositor, _lib
 
@@ -247,6 +260,8 @@ def run_ours(args, rank, local_rank, world):
     comp = Compositor(cfg["cameras"], sizes, cfg["warper"], cfg["blender"], cfg["strength"])
     plan_ms = 1e3 * (time.perf_counter() - t0)
     mpix_rank = n * w * h / 1e6
+    if args.extras:
+        set_extras(comp)
 
     # ---- device-resident throughput (`value`) -----------------------------------------------------
     comp.upload(imgs)
@@ -260,6 +275,8 @@ def run_ours(args, rank, local_rank, world):
     extra = []
     for k in range(1, args.inflight):
         c2 = Compositor(cfg["cameras"], sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+        if args.extras:
+            set_extras(c2)
         c2.upload(imgs)
         for _ in range(args.warmup):
             c2.run()
@@ -370,7 +387,8 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {WORKLOADS[args.workload]}" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""),
+                "workload": f"{args.workload}: {WORKLOADS[args.workload]}" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else "") +
+                            (" + fused exposure gains and seam masks (--extras; not the BASELINE metric's step)" if args.extras else ""),
                 "images_per_gpu": n, "pano": [pw, ph],
                 "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
                 "batches_in_flight": args.inflight, "one_batch_at_a_time_ms_per_step": round(single_ms, 4),
@@ -509,6 +527,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring used for the CPU baseline (default 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one independent panorama per GPU instead of one sharded panorama")
+    ap.add_argument("--extras", action="store_true", help="also fuse exposure gains and seam masks into the step (SURVEY 8f f1, f2)")
     ap.add_argument("--scale-down", type=int, default=1, help="debug: shrink the workload (not a valid measurement)")
     args = ap.parse_args()
     global SCALE_DOWN
