@@ -15,12 +15,24 @@ inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, cudaSt
     count_launch();
     sb_emu_run(grid, block, [&]() { kern(args...); });
 }
+// kernels whose lanes exchange values (warp shuffles): the emulation runs the 32 lanes of a warp concurrently
+template <typename... KArgs, typename... Args>
+inline void launch_lanes(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args &&...args)
+{
+    count_launch();
+    sb_emu_run_lanes(grid, block, [&]() { kern(args...); });
+}
 #else
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
 {
     count_launch();
     kern<<<grid, block, smem, s>>>(std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_lanes(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    launch(kern, grid, block, smem, s, std::forward<Args>(args)...);
 }
 #endif
 

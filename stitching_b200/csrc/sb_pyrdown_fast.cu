@@ -24,7 +24,6 @@
 
 namespace sb {
 
-#ifndef SB_EMU
 namespace {
 
 constexpr int WK_WARPS = 4;  // warps per block: consecutive row chunks of the same strip
@@ -208,17 +207,14 @@ int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int coun
         if (l == 0) near = near && im.top <= im.h && im.ph - im.top - im.h <= im.h;
     }
     if (l == 0 && near)
-        launch(k_pyrdown_walk<true, true>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<true, true>, grid, block, 0, s, pyr, rows);
     else if (l == 0)
-        launch(k_pyrdown_walk<true, false>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<true, false>, grid, block, 0, s, pyr, rows);
     else if (near)
-        launch(k_pyrdown_walk<false, true>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<false, true>, grid, block, 0, s, pyr, rows);
     else
-        launch(k_pyrdown_walk<false, false>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<false, false>, grid, block, 0, s, pyr, rows);
     return launch_check("k_pyrdown_walk");
 }
-#else
-int launch_pyrdown_fast(const PyrDesc *, const FeedImage *, int, int, int, int, cudaStream_t) { return SB_ERR_INVALID; }
-#endif
 
 }  // namespace sb

@@ -1,15 +1,20 @@
 // tests/emu/cuda_runtime.h -- TEST INFRASTRUCTURE ONLY.
-// A serial CPU stand-in for the few CUDA runtime calls and device builtins libstitch_b200 uses, so that
-// the product's host logic (plans, geometry, C ABI) and the index/rounding arithmetic of its
-// synchronisation-free kernels can be exercised on a GPU-less box (pytest -m "not gpu").
+// A CPU stand-in for the few CUDA runtime calls and device builtins libstitch_b200 uses, so that the product's
+// host logic (plans, geometry, C ABI) and the arithmetic of its kernels can be exercised on a GPU-less box
+// (pytest -m "not gpu"): synchronisation-free kernels run as serial loops over the grid (sb_emu_run), kernels whose
+// lanes exchange values through warp shuffles run with 32 host threads as the lanes of a warp (sb_emu_run_lanes).
 // The product build never sees this header (it is only on the include path of tests/emu/Makefile, which
 // defines SB_EMU), the product loader (stitching_b200/_lib.py) never loads the emu library, and nothing
 // measured or shipped runs through it.
 #pragma once
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
@@ -97,6 +102,67 @@ static inline int __float2int_rn(float v) { return (int)nearbyintf(v); }
 static inline int __float2int_rz(float v) { return (int)v; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+
+// ---- kernels whose lanes talk to each other (warp shuffles) -----------------------------------------------------
+// 32 host threads play the 32 lanes; every thread walks all warps of the grid in the same order and the lanes meet at
+// each collective (their control flow around collectives is warp-uniform, as CUDA requires for the *_sync forms).
+struct EmuWarpSync {
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long long generation = 0;
+    unsigned vals[32];
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned long long g = generation;
+        if (++waiting == 32) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != g; });
+        }
+    }
+    unsigned exchange(unsigned lane, unsigned v, int src)  // every lane publishes v and reads lane `src` (own value if out of range)
+    {
+        vals[lane] = v;
+        barrier();
+        const unsigned r = (src >= 0 && src < 32) ? vals[src] : v;
+        barrier();
+        return r;
+    }
+};
+extern thread_local EmuWarpSync *emu_warp;
+static inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x - (int)d); }
+static inline unsigned __shfl_down_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x + (int)d); }
+static inline float __shfl_up_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_up_sync(m, __float_as_uint(v), d)); }
+static inline float __shfl_down_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_down_sync(m, __float_as_uint(v), d)); }
+
+template <typename F>
+static inline void sb_emu_run_lanes(dim3 grid, dim3 block, F &&body)
+{
+    if (block.x != 32) std::abort();  // a warp is one row of the block in these kernels
+    EmuWarpSync sync;
+    std::vector<std::thread> lanes;
+    for (unsigned lane = 0; lane < 32; ++lane)
+        lanes.emplace_back([&, lane]() {
+            emu_warp = &sync;
+            gridDim = emuIdx{grid.x, grid.y, grid.z};
+            blockDim = emuIdx{block.x, block.y, block.z};
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
+                        blockIdx = emuIdx{bx, by, bz};
+                        for (unsigned tz = 0; tz < block.z; ++tz)
+                            for (unsigned ty = 0; ty < block.y; ++ty) {
+                                threadIdx = emuIdx{lane, ty, tz};
+                                body();
+                            }
+                    }
+        });
+    for (auto &t : lanes) t.join();
+}
 
 template <typename F>
 static inline void sb_emu_run(dim3 grid, dim3 block, F &&body)

@@ -237,6 +237,24 @@ def test_seam_resize_drop_in_and_fused(use_emu, oracle):
     b.close()
 
 
+def test_shuffle_pyrdown_kernel_under_lane_emulation(use_emu, oracle, monkeypatch):
+    """The warp-shuffle pyrDown kernel (sb_pyrdown_fast.cu) itself on the CPU: tests/emu plays the 32 lanes of a warp
+    with 32 host threads that meet at every shuffle.  Slow, hence one small rig (level-0 and level->=1 variants, virtual
+    halo lanes, both border-rule templates) against the oracle."""
+    monkeypatch.setenv("SB_EMU_LANES", "1")
+    for name, sd, ncap, strength in (("cfg2", 50, 3, 5), ("cfg3", 60, 3, 20)):
+        cfg = rigs.config(name, sd)
+        cams = cfg["cameras"][:ncap]
+        imgs = [rigs.noise_image(cfg["h"], cfg["w"], 500 + i) for i in range(len(cams))]
+        cfg = dict(cfg, strength=strength)
+        ref = replay.oracle_composite(oracle, cfg, cams, imgs)
+        c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], strength)
+        pano, mask = c.composite(imgs)
+        c.close()
+        replay.assert_exact(pano, ref["pano"], f"{name} pano through the shuffle pyrDown")
+        replay.assert_exact(mask, ref["pmask"], f"{name} mask through the shuffle pyrDown")
+
+
 def test_fused_final_resolution_chain(use_emu, oracle):
     """Gains and seam masks together (some images with neither): compositor == warp -> apply -> SeamFinder.resize -> feed."""
     got, ref = replay.fused_chain_case(oracle, Warper, Blender, Compositor, rigs, 25)
