@@ -226,9 +226,11 @@ int launch_feather_weights_fast(const FeedImage *imgs_dev, const FeedImage *imgs
 
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s)
 {
-#ifndef SB_EMU
-    if (!use_simple_kernels()) return launch_feather_weights_fast(imgs_dev, imgs_host, n, sharpness, s);
+    bool fast = !use_simple_kernels();
+#ifdef SB_EMU
+    if (!getenv("SB_EMU_LANES")) fast = false;  // the ballot-based row kernel needs the (slow) lane emulation: on request only
 #endif
+    if (fast) return launch_feather_weights_fast(imgs_dev, imgs_host, n, sharpness, s);
     for (int i = 0; i < n; ++i) {
         launch(k_dt_rows, dim3(div_up(imgs_host[i].h, 64)), dim3(64), 0, s, imgs_dev, i);
         launch(k_dt_cols, dim3(div_up(imgs_host[i].w, 64)), dim3(64), 0, s, imgs_dev, i, sharpness);

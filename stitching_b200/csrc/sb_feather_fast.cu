@@ -13,7 +13,6 @@
 
 namespace sb {
 
-#ifndef SB_EMU
 namespace {
 
 #define DT_INF (1 << 29)
@@ -86,12 +85,9 @@ int launch_feather_weights_fast(const FeedImage *imgs_dev, const FeedImage *imgs
         mh = mh > imgs_host[i].h ? mh : imgs_host[i].h;
     }
     if (n <= 0 || mw <= 0 || mh <= 0) return SB_OK;
-    launch(k_dt_rows_warp, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
+    launch_lanes(k_dt_rows_warp, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
     launch(k_dt_cols_batched, dim3(div_up(mw, 128), n), dim3(128), 0, s, imgs_dev, sharpness);
     return launch_check("k_dt_*");
 }
-#else
-int launch_feather_weights_fast(const FeedImage *, const FeedImage *, int, float, cudaStream_t) { return SB_ERR_INVALID; }
-#endif
 
 }  // namespace sb

@@ -134,6 +134,18 @@ struct EmuWarpSync {
     }
 };
 extern thread_local EmuWarpSync *emu_warp;
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+    emu_warp->vals[threadIdx.x] = pred ? 1u : 0u;
+    emu_warp->barrier();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= emu_warp->vals[i] << i;
+    emu_warp->barrier();
+    return m;
+}
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x - (int)d); }
 static inline unsigned __shfl_down_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x + (int)d); }
 static inline float __shfl_up_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_up_sync(m, __float_as_uint(v), d)); }

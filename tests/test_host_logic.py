@@ -237,12 +237,13 @@ def test_seam_resize_drop_in_and_fused(use_emu, oracle):
     b.close()
 
 
-def test_shuffle_pyrdown_kernel_under_lane_emulation(use_emu, oracle, monkeypatch):
-    """The warp-shuffle pyrDown kernel (sb_pyrdown_fast.cu) itself on the CPU: tests/emu plays the 32 lanes of a warp
-    with 32 host threads that meet at every shuffle.  Slow, hence one small rig (level-0 and level->=1 variants, virtual
-    halo lanes, both border-rule templates) against the oracle."""
+def test_warp_collective_kernels_under_lane_emulation(use_emu, oracle, monkeypatch):
+    """The kernels whose lanes talk to each other -- the warp-shuffle pyrDown (sb_pyrdown_fast.cu) and the ballot-based
+    distance transform (sb_feather_fast.cu) -- themselves on the CPU: tests/emu plays the 32 lanes of a warp with 32 host
+    threads that meet at every collective.  Slow, hence small rigs (level-0 and level->=1 variants, virtual halo lanes,
+    border-rule templates; feather weights) against the oracle."""
     monkeypatch.setenv("SB_EMU_LANES", "1")
-    for name, sd, ncap, strength in (("cfg2", 50, 3, 5), ("cfg3", 60, 3, 20)):
+    for name, sd, ncap, strength in (("cfg2", 50, 3, 5), ("cfg3", 60, 3, 20), ("cfg5", 20, 4, 5)):  # cfg5: ballot-based feather DT
         cfg = rigs.config(name, sd)
         cams = cfg["cameras"][:ncap]
         imgs = [rigs.noise_image(cfg["h"], cfg["w"], 500 + i) for i in range(len(cams))]
