@@ -169,8 +169,9 @@ def make_workload(name, rank):
     return cfg, imgs
 
 
-def cpu_reference_run(cfg, imgs, n_sample, threads=None):
-    """The reference's CPU path on the first n_sample images of the ring.  Returns (MPix/s, seconds, info)."""
+def cpu_reference_run(cfg, imgs, n_sample, threads=None, want_result=False):
+    """One pass of the reference's CPU path over the first n_sample images of the ring (n_sample = cfg['n']: the whole
+    configuration).  Returns (MPix/s, seconds, info[, pano, mask])."""
     from oracle import cv_path
 
     cams = cfg["cameras"][:n_sample]
@@ -178,19 +179,79 @@ def cpu_reference_run(cfg, imgs, n_sample, threads=None):
     mpix = sum(im.shape[0] * im.shape[1] for im in sub) / 1e6
     if cv_path.available():
         t0 = time.perf_counter()
-        _, _, stages = cv_path.composite(cfg, cams, sub, threads)
+        pano, mask, stages = cv_path.composite(cfg, cams, sub, threads)
         dt = time.perf_counter() - t0
         info = cv_path.describe()
-        return mpix / dt, dt, {"backend": f"cv2 {info['cv2']}", "cores": info["threads"], "stages_s": {k: round(v, 3) for k, v in stages.items()}}
+        out = (mpix / dt, dt, {"backend": f"cv2 {info['cv2']}", "cores": info["threads"], "parallel": info["parallel"],
+                               "stages_s": {k: round(v, 3) for k, v in stages.items()}})
+        if want_result:
+            if hasattr(mask, "get"):
+                mask = mask.get()
+            return out + (pano, mask)
+        return out
     # cv2 missing on this box: the scalar C restatement (1 core)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import replay
     from oracle import oracle as O
 
     t0 = time.perf_counter()
-    replay.oracle_composite(O, cfg, cams, sub)
+    ref = replay.oracle_composite(O, cfg, cams, sub)
     dt = time.perf_counter() - t0
-    return mpix / dt, dt, {"backend": "oracle/stitch_oracle.c (scalar)", "cores": 1, "stages_s": {}}
+    out = (mpix / dt, dt, {"backend": "oracle/stitch_oracle.c (scalar)", "cores": 1, "parallel": "", "stages_s": {}})
+    return out + (ref["pano"], ref["pmask"]) if want_result else out
+
+
+def compare_results(pano, mask, ref_pano, ref_mask):
+    """GPU result vs the CPU reference result of the same inputs: differing values and the largest difference."""
+    if pano.shape != ref_pano.shape or mask.shape != ref_mask.shape:
+        return {"shape_mismatch": [list(pano.shape), list(ref_pano.shape)]}
+    differing, max_abs = 0, 0
+    rows = 512
+    for y in range(0, pano.shape[0], rows):  # in bands: the int16 temporaries of a 160 MB panorama stay small
+        d = np.abs(pano[y:y + rows].astype(np.int16) - ref_pano[y:y + rows].astype(np.int16))
+        differing += int(np.count_nonzero(d))
+        max_abs = max(max_abs, int(d.max()) if d.size else 0)
+    mask_diff = int(np.count_nonzero(mask != ref_mask))
+    return {"differing": differing, "max_abs": max_abs, "mask_differing": mask_diff, "values": int(pano.size),
+            "against": "the reference's cv2 path on the same inputs (oracle/cv_path.py), whole panorama"}
+
+
+def cpu_baseline_block(cfg, imgs, gpu_pano=None, gpu_mask=None, budget_s=100.0):
+    """the WHOLE configuration through the reference's CPU path on this box's host cores, with
+    all cores (one warm-up + up to 3 timed repetitions, median) and with one core (one repetition, as the time budget
+    of a default bench run allows), plus the comparison of the GPU panorama with the CPU panorama."""
+    n = cfg["n"]
+    ncpu = os.cpu_count() or 1
+    t_start = time.perf_counter()
+    _, warm_dt, info, pano, mask = cpu_reference_run(cfg, imgs, n, threads=ncpu, want_result=True)
+    parity = None
+    if gpu_pano is not None:
+        parity = compare_results(gpu_pano, gpu_mask, pano, mask)
+    del pano, mask
+    times = []
+    reps = 3 if warm_dt * 3.2 < budget_s * 0.6 else 1
+    for _ in range(reps):
+        _, dt, info = cpu_reference_run(cfg, imgs, n, threads=ncpu)
+        times.append(dt)
+    mpix = n * cfg["w"] * cfg["h"] / 1e6
+    med = float(np.median(times))
+    block = {"value": mpix / med, "unit": UNIT, "cores": info["cores"], "kind": "port",
+             "sample": f"the whole configuration ({n} images at full resolution) per repetition: 1 warm-up + {reps} timed, median "
+                       f"{med:.2f} s, min {min(times):.2f} s ({info['backend']}, cv.setNumThreads({ncpu}); {info['parallel']})",
+             "stages_s": info["stages_s"], "host_cpus": ncpu, "warmup_s": round(warm_dt, 2), "reps_s": [round(t, 2) for t in times]}
+    # one core, if the remaining budget allows (the single-core pass of cfg 2 takes ~30-60 s)
+    left = budget_s - (time.perf_counter() - t_start)
+    if left > 45:
+        v1, dt1, _ = cpu_reference_run(cfg, imgs, n, threads=1)
+        block["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "seconds": round(dt1, 2), "sample": "the whole configuration, 1 cold repetition"}
+    else:
+        block["one_core"] = None
+    return block, parity
+
+
+def sharded_workload_name(n, w, h, world):
+    return (f"cfg3 family: {n}x{w}x{h} RGB, cylindrical warp + multiband blend, ONE panorama sharded over {world} GPUs "
+            f"(4 images per GPU; N=8 is BASELINE configs[2])" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""))
 
 
 def run_reference(args, rank, world):
@@ -201,33 +262,39 @@ def run_reference(args, rank, world):
 
         n, w, h = 4 * world, 4000 // SCALE_DOWN, 3000 // SCALE_DOWN
         cfg = dict(n=n, w=w, h=h, warper="cylindrical", cameras=rigs.yaw_ring(n, w, h, 8000 / SCALE_DOWN, 10), blender="multiband", strength=5)
-        imgs = [rigs.synth_image(h, w, i) for i in range(min(args.cpu_sample or 4, n))]
-        args.workload = "cfg3"
+        imgs = [rigs.synth_image(h, w, i) for i in range(n)]
+        workload = sharded_workload_name(n, w, h, world)
     else:
         cfg, imgs = make_workload(args.workload, 0)
-    n_sample = min(args.cpu_sample or 4, cfg["n"])
-    # bound the whole run to a few minutes: shrink the sample if one step is slow
-    v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
-    budget = 150.0
+        workload = f"{args.workload}: {WORKLOADS[args.workload]}"
+    ncpu = os.cpu_count() or 1
+    # the whole configuration per step with all host cores; only if that cannot finish the requested steps within a few
+    # minutes the step shrinks to the first images of the ring (and says so)
+    n_sample = min(args.cpu_sample or cfg["n"], cfg["n"])
+    v, dt, info = cpu_reference_run(cfg, imgs, n_sample, threads=ncpu)  # first (cold) pass = first warm-up step
+    budget = 330.0
     while n_sample > 2 and dt * (args.steps + args.warmup) > budget:
         n_sample = max(2, n_sample // 2)
-        v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+        v, dt, info = cpu_reference_run(cfg, imgs, n_sample, threads=ncpu)
     for _ in range(max(0, args.warmup - 1)):
-        cpu_reference_run(cfg, imgs, n_sample)
+        cpu_reference_run(cfg, imgs, n_sample, threads=ncpu)
     times = []
     for _ in range(args.steps):
-        _, dt, info = cpu_reference_run(cfg, imgs, n_sample)
+        _, dt, info = cpu_reference_run(cfg, imgs, n_sample, threads=ncpu)
         times.append(dt)
     mpix = n_sample * cfg["w"] * cfg["h"] / 1e6
     value = mpix * len(times) / sum(times)
-    sample = f"first {n_sample} of {cfg['n']} images of the ring at full resolution per step ({info['backend']})"
+    whole = n_sample == cfg["n"]
+    sample = (f"the whole configuration ({cfg['n']} images at full resolution) per step" if whole else
+              f"first {n_sample} of {cfg['n']} images of the ring at full resolution per step (bounded: the whole ring would not finish "
+              f"{args.steps + args.warmup} steps within a few minutes)") + f" ({info['backend']}, cv.setNumThreads({ncpu}))"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "sample": sample},
+        "config": {"workload": workload, "sample": sample, "whole_config": whole},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample,
-                         "stages_s": info["stages_s"]},
+                         "stages_s": info["stages_s"], "host_cpus": ncpu, "median_s": float(np.median(times)), "min_s": min(times)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -372,14 +439,10 @@ def run_ours(args, rank, local_rank, world):
     assert np.array_equal(pano, pano2), "pipelined slots disagree"
     checksum = int(pano[::97, ::89].astype(np.uint64).sum())  # the result was really produced and read back
 
-    # ---- CPU baseline: the reference's cv2 path on this box's host cores (rank 0, N = 1 only) ------
-    cpu = None
+    # ---- CPU baseline: the reference's cv2 path on this box's host cores (rank 0, N = 1 only), and parity ------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sample = min(args.cpu_sample or 4, n)
-        v, dt, info = cpu_reference_run(cfg, imgs, n_sample)
-        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
-               "sample": f"first {n_sample} of {n} images of the ring at full resolution, 1 cold run of {dt:.1f} s ({info['backend']})",
-               "stages_s": info["stages_s"], "host_cpus": os.cpu_count()}
+        cpu, parity = cpu_baseline_block(cfg, imgs, np.array(pano), np.array(pmask))
 
     if rank == 0:
         line = {
@@ -398,7 +461,7 @@ def run_ours(args, rank, local_rank, world):
                 "timed": "plan (roi detection, trig tables, buffers) built once outside the timed region; a step = warp + pyramids + collapse kernels",
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "roofline": roofline,
-            "cpu_baseline": cpu, "result_checksum": checksum,
+            "cpu_baseline": cpu, "parity": parity, "result_checksum": checksum,
         }
         print(json.dumps(line), flush=True)
     for p, _ in host_src:
@@ -419,7 +482,10 @@ def run_sharded(args, rank, local_rank, world):
     from stitching_b200 import Compositor, _lib, rigs
     from stitching_b200 import dist as sbdist
 
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep the one-JSON-line contract
+    # NCCL's own log lines (NCCL_DEBUG=INFO from the driver) go to stderr unless the caller chose a file: stdout
+    # carries the one JSON line
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     dist = Dist(world)
     L = _lib.lib()
 
@@ -524,7 +590,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--inflight", type=int, default=2, help="N = 1: independent batches in flight (own stream + buffers each)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring used for the CPU baseline (default 4)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring per step of the reference arm (default: the whole configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one independent panorama per GPU instead of one sharded panorama")
     ap.add_argument("--extras", action="store_true", help="also fuse exposure gains and seam masks into the step (SURVEY 8f f1, f2)")

@@ -110,6 +110,7 @@ class Blender:
         blend_width = np.sqrt(dst_sz[2] * dst_sz[3]) * self.blend_strength / 100
         if self.blender is not None:
             self.blender.close()
+            self.blender = None  # an unknown blender_type must fail on `None`, not on a closed handle
         if self.blender_type == "no" or blend_width < 1:
             self.blender = _NativeBlender("no")
         elif self.blender_type == "multiband":

@@ -393,11 +393,12 @@ int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_p
             im.mask_pitch = w;
         } else {
             uint32_t *d_rgbm = nullptr;
-            SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)w * h * 4, s));
+            const int rp = (w + 3) & ~3;  // 16-byte rows: the copy engine (TMA) stages windows of this buffer
+            SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)rp * h * 4, s));
             b->level0.push_back(d_rgbm);
-            SB_TRY(launch_pack_rgbm((const uint8_t *)d_img, (long long)w * 3, d_mask, w, d_rgbm, w, w, h, s));
+            SB_TRY(launch_pack_rgbm((const uint8_t *)d_img, (long long)w * 3, d_mask, w, d_rgbm, rp, w, h, s));
             im.rgbm = d_rgbm;
-            im.rgbm_pitch = w;
+            im.rgbm_pitch = rp;
         }
         // the caller's buffers may be reused as soon as we return
         SB_CUDA(cudaStreamSynchronize(s));

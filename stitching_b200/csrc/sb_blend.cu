@@ -197,7 +197,8 @@ __global__ void k_dt_cols(const FeedImage *__restrict__ imgs, int i, float sharp
 }  // namespace
 
 int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
-                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s)
+                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s, const TileDesc *tile,
+                    const void *maps, int map_c_up)
 {
     int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
     if (gw <= 0 || gh <= 0) return SB_OK;
@@ -215,6 +216,13 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
         A.rh = l == 0 ? (out.h + 1) / 2 * 2 : lh;
         A.out = out;
         A.out_hi = out.w;
+        A.tile = tile;
+        A.maps = maps;
+        A.map_c_up = map_c_up;
+        if (tile && l < nb) {  // TMA-staged tiles (sb_collapse_tile.cu) where the launch qualifies
+            const int rc = launch_collapse_tile(A, l, nb, s);
+            if (rc != SB_ERR_STATE) return rc;
+        }
         return launch_collapse_fast(A, l, nb, s);
     }
     dim3 block(CL_BX, CL_BY), grid(div_up(gw, CL_BX), div_up(gh, CL_BY));

@@ -80,7 +80,16 @@ static int init_locked(int ordinal)
 int ensure_device()
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device >= 0) return SB_OK;
+    if (g_device >= 0) {
+        // cudaSetDevice is per host thread: a caller on another thread than the one that initialised the library
+        // would otherwise run on device 0 with streams of device g_device
+        static thread_local int t_device = -1;
+        if (t_device != g_device) {
+            SB_CUDA(cudaSetDevice(g_device));
+            t_device = g_device;
+        }
+        return SB_OK;
+    }
     const char *env = getenv("SB_DEVICE");
     if (!env) env = getenv("LOCAL_RANK");
     return init_locked(env ? atoi(env) : 0);

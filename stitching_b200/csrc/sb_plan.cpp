@@ -181,6 +181,9 @@ int BlendPlan::allocate(cudaStream_t s)
     const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
     const size_t col_off = carve(sizeof(ColDesc) * (size_t)std::max(n, 1) * (nb + 1));
     const size_t pyr_off = carve(sizeof(PyrDesc) * (size_t)std::max(n, 1) * (nb + 1));
+    const size_t n_maps = (size_t)3 * std::max(n, 1) * (nb + 1) + (nb + 1);
+    const size_t tile_off = carve(sizeof(TileDesc) * (size_t)std::max(n, 1) * (nb + 1));
+    const size_t maps_off = carve(sizeof(TensorMap) * n_maps);
     arena_bytes_ = off;
     SB_TRY(dev_alloc(&arena_, arena_bytes_, s));
     char *base = (char *)arena_;
@@ -267,6 +270,61 @@ int BlendPlan::allocate(cudaStream_t s)
             SB_CUDA(cudaMemcpyAsync(col_dev, col.data(), sizeof(ColDesc) * col.size(), cudaMemcpyHostToDevice, s));
             SB_CUDA(cudaMemcpyAsync(pyr_dev, pyr.data(), sizeof(PyrDesc) * pyr.size(), cudaMemcpyHostToDevice, s));
         }
+        // TMA tile kernels: tensor maps of every window they stage + per-(level, image) descriptors.  Byte-fed images
+        // with storage on this device only; any geometry the copy engine refuses leaves tile_dev null (no error).
+        tile_dev = nullptr;
+        maps_dev = nullptr;
+        bool tiles = n > 0 && nb >= 1 && active_count < 0 && collapse_tile_enabled();
+        for (int i = 0; i < n && tiles; ++i) tiles = imgs[i].rgbm != nullptr;
+        if (tiles) {
+            std::vector<TensorMap> maps(n_maps);
+            std::vector<TileDesc> td((size_t)n * (nb + 1));
+            std::memset(td.data(), 0, sizeof(TileDesc) * td.size());
+            auto midx = [&](int l, int i, int kind) { return (int)(((size_t)l * n + i) * 3 + kind); };
+            map_pano_base = 3 * n * (nb + 1);
+            int rc = SB_OK;
+            for (int l = 0; l <= nb && rc == SB_OK; ++l)
+                for (int i = 0; i < n && rc == SB_OK; ++i) {
+                    const FeedImage &im = imgs[i];
+                    if (l == 0) {
+                        rc = tensor_map_encode(&maps[midx(0, i, 0)], TMA_U32, im.rgbm, im.w, im.h, im.rgbm_pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
+                    } else {
+                        const Level &L = im.lv[l];
+                        rc = tensor_map_encode(&maps[midx(l, i, 0)], TMA_U64, L.q, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
+                        if (rc == SB_OK) rc = tensor_map_encode(&maps[midx(l, i, 1)], TMA_F32, L.w, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
+                        if (rc == SB_OK) rc = tensor_map_encode(&maps[midx(l, i, 2)], TMA_U64, L.q, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_UPW, SB_TILE_UPH, 1);
+                    }
+                    TileDesc &t = td[(size_t)l * n + i];
+                    t.ox = im.px >> l;
+                    t.oy = im.py >> l;
+                    if (l == 0) {
+                        t.x0 = im.px + im.left;
+                        t.y0 = im.py + im.top;
+                        t.w = im.w;
+                        t.h = im.h;
+                    } else {
+                        t.x0 = t.ox;
+                        t.y0 = t.oy;
+                        t.w = im.pw >> l;
+                        t.h = im.ph >> l;
+                    }
+                    t.uw = im.pw >> (l + 1);
+                    t.uh = im.ph >> (l + 1);
+                    t.map_own = midx(l, i, 0);
+                    t.map_w = midx(l, i, 1);
+                    t.map_up = midx(l + 1 <= nb ? l + 1 : nb, i, 2);
+                }
+            for (int l = 1; l <= nb && rc == SB_OK; ++l)
+                rc = tensor_map_encode(&maps[map_pano_base + l], TMA_U16, pano[l].c, pano[l].w_px, pano[l].h_px, pano[l].pitch, 3, pano[l].plane,
+                                       SB_TILE_C1W, SB_TILE_UPH, 3);
+            if (rc == SB_OK) {
+                tile_dev = (TileDesc *)(base + tile_off);
+                maps_dev = base + maps_off;
+                SB_CUDA(cudaMemcpyAsync(tile_dev, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice, s));
+                SB_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), sizeof(TensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
+                SB_CUDA(cudaStreamSynchronize(s));  // `maps` / `td` are locals
+            }
+        }
     }
     if (n) SB_CUDA(cudaMemcpyAsync(imgs_dev, imgs.data(), sizeof(FeedImage) * n, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(pano_dev, pano, sizeof pano, cudaMemcpyHostToDevice, s));
@@ -284,6 +342,8 @@ void BlendPlan::release(cudaStream_t s)
     pano_dev = nullptr;
     col_dev = nullptr;
     pyr_dev = nullptr;
+    tile_dev = nullptr;
+    maps_dev = nullptr;
 }
 
 int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(const std::string &)> &mark)
@@ -301,7 +361,8 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
             SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
         for (int l = nb; l >= 0; --l) {
-            SB_TRY(launch_collapse(imgs_dev, imgs.data(), col_dev + (size_t)l * n, n, pano_dev, pano, l, nb, wp >> l, hp >> l, out, s));
+            SB_TRY(launch_collapse(imgs_dev, imgs.data(), col_dev + (size_t)l * n, n, pano_dev, pano, l, nb, wp >> l, hp >> l, out, s,
+                                   tile_dev ? tile_dev + (size_t)l * n : nullptr, maps_dev, map_pano_base + l + 1));
             SB_TRY(note("collapse_l" + std::to_string(l)));
         }
     } else {

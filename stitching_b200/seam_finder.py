@@ -15,12 +15,15 @@ from .stitching_error import StitchingError
 
 
 def resize(seam_mask, mask):
-    """SeamFinder.resize(seam_mask, mask): uint8 mask of `mask`'s size (the reference returns a cv.UMat; every
-    consumer -- Blender.feed, SeamFinder.draw_seam_mask via cv.UMat.get -- takes either)."""
+    """SeamFinder.resize(seam_mask, mask): uint8 mask of `mask`'s size.  Like the cv2 chain it replaces
+    (seam_finder.py:39-43: dilate -> resize -> bitwise_and) the result is a cv.UMat whenever an input was one -- the seam
+    finder hands out cv.UMat masks, and SeamFinder.draw_seam_mask (seam_finder.py:47) calls cv.UMat.get on the result --
+    and an ndarray when both inputs were ndarrays."""
+    was_umat = False
     if hasattr(seam_mask, "get") and not isinstance(seam_mask, np.ndarray):
-        seam_mask = seam_mask.get()  # cv.UMat from the seam finder
+        seam_mask, was_umat = seam_mask.get(), True  # cv.UMat from the seam finder
     if hasattr(mask, "get") and not isinstance(mask, np.ndarray):
-        mask = mask.get()
+        mask, was_umat = mask.get(), True
     seam_mask = np.ascontiguousarray(seam_mask, np.uint8)
     mask = np.ascontiguousarray(mask, np.uint8)
     if seam_mask.ndim != 2 or mask.ndim != 2:
@@ -34,4 +37,8 @@ def resize(seam_mask, mask):
         ),
         "sb_seam_resize",
     )
+    if was_umat:
+        import cv2  # a cv.UMat came in, so cv2 is importable
+
+        return cv2.UMat(out)
     return out

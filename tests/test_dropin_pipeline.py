@@ -107,7 +107,7 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
 
     def rec_resize(seam_mask, mask):
         out = ref_resize(seam_mask, mask)
-        log.append(("seam_resize", seam_mask, np.array(mask).copy(), out.get() if hasattr(out, "get") else np.array(out)))
+        log.append(("seam_resize", seam_mask, np.array(mask).copy(), out.get() if hasattr(out, "get") else np.array(out), type(out).__name__))
         return out
 
     from stitching.exposure_error_compensator import ExposureErrorCompensator as RefCompensator
@@ -171,6 +171,10 @@ def test_recorded_boundary_calls_replay_identically(reference_stitching, use_emu
             checked += 1
         elif e[0] == "seam_resize":  # the LOW-resolution seam mask arrives as cv.UMat, the warped mask as ndarray
             got = stitching_b200.seam_finder.resize(e[1], e[2])
+            # same container type as the reference's cv2 chain (cv.UMat in the pipeline): seam_finder.py:47 and
+            # verbose.py:149-156 call cv.UMat.get on it
+            assert type(got).__name__ == e[4], f"SeamFinder.resize returned {type(got).__name__}, the reference {e[4]}"
+            got = got.get() if hasattr(got, "get") else got
             assert got.shape == e[3].shape and np.array_equal(got, e[3]), f"SeamFinder.resize: {int((got != e[3]).sum())} values differ"
             checked += 1
         elif e[0] == "prepare":
