@@ -14,50 +14,63 @@ from .warper import Warper  # noqa: F401
 __version__ = "0.1.0"
 
 
+_installed = {}
+
+
 def install(stitching_module=None):
     """Route `stitching.Stitcher` (and cropper / seam finder / verbose callers) through the B200 classes.
 
     The reference modules bind the class names at import time (`from .warper import Warper` in
-    stitcher.py, cropper.py, seam_finder.py, verbose.py), so the names are patched in each of them.
+    stitcher.py, cropper.py, seam_finder.py, verbose.py), so the names are patched in each of them.  A reference
+    module that cannot be imported is reported with a StitchingWarning (the pipeline would otherwise run half on cv2
+    and half on the B200 classes without a sign); any other failure propagates.
     """
     import importlib
+    import warnings
 
     if stitching_module is None:
         stitching_module = importlib.import_module("stitching")
+    if _installed.get(id(stitching_module)) is stitching_module:
+        return stitching_module
     pkg = stitching_module.__name__
+    missing = []
+
+    def module(name):
+        try:
+            return importlib.import_module(f"{pkg}.{name}")
+        except ImportError as e:  # (ModuleNotFoundError included)
+            missing.append(f"{pkg}.{name} ({e})")
+            return None
+
     for mod, names in (
         ("warper", ("Warper",)), ("blender", ("Blender",)), ("stitcher", ("Warper", "Blender")),
         ("cropper", ("Blender",)), ("seam_finder", ("Blender",)), ("verbose", ("Warper", "Blender")),
     ):
-        try:
-            m = importlib.import_module(f"{pkg}.{mod}")
-        except Exception:
+        m = module(mod)
+        if m is None:
             continue
         for name in names:
             if hasattr(m, name):
                 setattr(m, name, {"Warper": Warper, "Blender": Blender}[name])
     # the FINAL-resolution step of the seam finder (seam_finder.py:38-43); stitcher.py calls it through the class
-    try:
-        sf = importlib.import_module(f"{pkg}.seam_finder")
+    sf = module("seam_finder")
+    if sf is not None:
         sf.SeamFinder.resize = staticmethod(seam_finder.resize)
-    except Exception:
-        pass
     # the resampling to MEDIUM / LOW / FINAL resolution (images.py:120-123)
-    try:
-        im = importlib.import_module(f"{pkg}.images")
+    im = module("images")
+    if im is not None:
         im.Images.resize_img_by_scaler = staticmethod(images.resize_img_by_scaler)
-    except Exception:
-        pass
     # the FINAL-resolution step of the exposure compensator (exposure_error_compensator.py:43-45)
-    try:
-        ec = importlib.import_module(f"{pkg}.exposure_error_compensator")
+    ec = module("exposure_error_compensator")
+    if ec is not None:
 
         def _apply(self, *args):
             return exposure_error_compensator.apply(self.compensator, *args)
 
         ec.ExposureErrorCompensator.apply = _apply
-    except Exception:
-        pass
+    if missing:
+        warnings.warn("stitching_b200.install(): not patched, these stay on the reference's cv2 path: " + "; ".join(missing), StitchingWarning)
+    _installed[id(stitching_module)] = stitching_module
     return stitching_module
 
 

@@ -396,6 +396,7 @@ int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_p
             const int rp = (w + 3) & ~3;  // 16-byte rows: the copy engine (TMA) stages windows of this buffer
             SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)rp * h * 4, s));
             b->level0.push_back(d_rgbm);
+            if (rp != w) SB_CUDA(cudaMemsetAsync(d_rgbm, 0, (size_t)rp * h * 4, s));  // zero row padding = weight 0
             SB_TRY(launch_pack_rgbm((const uint8_t *)d_img, (long long)w * 3, d_mask, w, d_rgbm, rp, w, h, s));
             im.rgbm = d_rgbm;
             im.rgbm_pitch = rp;

@@ -15,32 +15,13 @@
 #include <cstring>
 
 #include "sb_launch.h"
-#include "sb_pyramid.cuh"
+#include "sb_gather.cuh"
 
 namespace sb {
 
 namespace {
 
 constexpr int CL_BX = 32, CL_BY = 8;
-#define SB_WEIGHT_EPS 1e-5f
-
-__device__ __forceinline__ void store_final(const PanoOut &out, int x, int y, const int v[3], bool on, unsigned mask_value)
-{
-    if (out.s16) {
-        int16_t *d = out.s16 + (long long)y * out.s16_pitch + (long long)x * 3;
-        d[0] = (int16_t)(on ? v[0] : 0);
-        d[1] = (int16_t)(on ? v[1] : 0);
-        d[2] = (int16_t)(on ? v[2] : 0);
-    }
-    if (out.rgb) {
-        uint8_t *d = out.rgb + (long long)y * out.rgb_pitch + (long long)x * 3;
-        // convertScaleAbs: min(|v|, 255)
-        d[0] = (uint8_t)(on ? min(abs(v[0]), 255) : 0);
-        d[1] = (uint8_t)(on ? min(abs(v[1]), 255) : 0);
-        d[2] = (uint8_t)(on ? min(abs(v[2]), 255) : 0);
-    }
-    if (out.mask) out.mask[(long long)y * out.mask_pitch + x] = (uint8_t)mask_value;
-}
 
 // simple variant: one thread per pano pixel of level l, loops over all images with a rect test
 __global__ void __launch_bounds__(CL_BX *CL_BY)
@@ -52,45 +33,7 @@ __global__ void __launch_bounds__(CL_BX *CL_BY)
     if (x >= lw || y >= lh) return;
     if (l == 0 && (x >= out.w || y >= out.h)) return;  // level 0 is the last step: the pad is never read
 
-    int acc[3] = {0, 0, 0};
-    float wsum = 0.f;
-    for (int i = 0; i < n; ++i) {
-        const FeedImage &im = imgs[i];
-        const int X = x - (im.px >> l), Y = y - (im.py >> l);
-        const int w_l = im.pw >> l, h_l = im.ph >> l;
-        if ((unsigned)X >= (unsigned)w_l || (unsigned)Y >= (unsigned)h_l) continue;
-        int g[3];
-        float wt;
-        load_level(im, l, X, Y, g, wt);
-        if (l < nb) {
-            int up[3];
-            pyrup_level_at(im.lv[l + 1], w_l >> 1, h_l >> 1, X, Y, up);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) g[c] = sat_s16(g[c] - up[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] += f2s_wrap(fmul((float)g[c], wt));
-        wsum = fadd(wsum, wt);
-    }
-    const float den = fadd(wsum, SB_WEIGHT_EPS);
-    int v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv((float)(short)acc[c], den));
-    if (l < nb) {
-        const PanoLevel &P = pano[l + 1];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = sat_s16(pyrup_at(P.c + c * P.plane, P.pitch, P.w_px, P.h_px, x, y) + v[c]);
-    }
-    if (l > 0) {
-        const PanoLevel &P = pano[l];
-        const long long o = (long long)y * P.pitch + x;
-        P.c[o] = (int16_t)v[0];
-        P.c[P.plane + o] = (int16_t)v[1];
-        P.c[2 * P.plane + o] = (int16_t)v[2];
-    } else {
-        const bool on = wsum > SB_WEIGHT_EPS;
-        store_final(out, x, y, v, on, on ? 255u : 0u);
-    }
+    collapse_pixel(imgs, n, pano, l, nb, x, y, out);
 }
 
 // feather / no: one thread per pano pixel, images in feed order
@@ -197,8 +140,7 @@ __global__ void k_dt_cols(const FeedImage *__restrict__ imgs, int i, float sharp
 }  // namespace
 
 int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
-                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s, const TileDesc *tile,
-                    const void *maps, int map_c_up)
+                    const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s, const TileDesc *tile)
 {
     int gw = l == 0 ? out.w : lw, gh = l == 0 ? out.h : lh;
     if (gw <= 0 || gh <= 0) return SB_OK;
@@ -217,9 +159,7 @@ int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const
         A.out = out;
         A.out_hi = out.w;
         A.tile = tile;
-        A.maps = maps;
-        A.map_c_up = map_c_up;
-        if (tile && l < nb) {  // TMA-staged tiles (sb_collapse_tile.cu) where the launch qualifies
+        if (tile && l < nb) {  // shared-memory tiles (sb_collapse_tile.cu) where the launch qualifies
             const int rc = launch_collapse_tile(A, l, nb, s);
             if (rc != SB_ERR_STATE) return rc;
         }

@@ -1,30 +1,35 @@
-// sb_collapse_tile.cu -- the per-level multiband kernel on TMA-staged shared-memory tiles (levels 0 .. nb-1).
+// sb_collapse_tile.cu -- the per-level multiband kernel on shared-memory tiles (levels 0 .. nb-1).
 //
 // Same arithmetic as k_collapse_fast / k_collapse_gather (reference call chain stitching/blender.py:41,46 ->
 // MultiBandBlender::feed / ::blend): per pano pixel, in feed order over the images covering it,
 //   L = G_l - pyrUp(G_{l+1});  acc += (short)trunc(L * w);  wsum += w;
 // then n = (short)trunc(acc / (wsum + 1e-5)), C_l = sat16(pyrUp(C_{l+1}) + n), and at level 0 mask / |.| / uint8.
 //
-// What changed against k_collapse_fast is where the operands come from and how often they are touched.  The round-1
-// profile (profiles/ncu_r02_a_*) showed 845 warp instructions per quad at level 0: 340 in the final pyrUp + store,
-// ~190 per covering image, mostly address arithmetic, bounds tests and 9 + 27 scattered global taps per thread.  Here
-// a CTA owns a 64x16 tile (one thread per 2x2 quad) and ONE elected thread asks the copy engine (TMA,
-// cp.async.bulk.tensor, sb_tma.cuh) for every window the tile needs -- per covering image the 64x16 level-l pixels
-// (level 0: packed RGBM; above: colour lane pairs + weights) and the 34x10 window of level l+1 that holds the 3x3
-// pyrUp neighbourhoods of all quads, plus the 40x10x3 window of the collapsed level C_{l+1}.  Out-of-range elements
-// arrive as zeros, which is exactly "weight 0": no rect tests, no address arithmetic, no predicated loads in the
-// threads.  The pyrUp is separable and neighbouring quads share two of their three coarse columns: every thread
+// What changed against k_collapse_fast is where the operands come from and how often they are touched.  The profile of
+// k_collapse_fast (profiles/ncu_r02_a_*) shows 845 warp instructions per quad at level 0: 340 in the final pyrUp +
+// store, ~190 per covering image, mostly address arithmetic, bounds tests and 9 + 27 scattered global taps per thread.
+// Here a CTA owns a 64x16 tile (one thread per 2x2 quad) and stages every window the tile needs in shared memory with
+// asynchronous 16-byte copies (cp.async / LDGSTS, zero fill outside the source, the next image's windows in flight
+// while the current one is consumed): per covering image the 64x16 level-l pixels (level 0: packed RGBM; above: colour
+// lane pairs + weights) and the 34x10 window of level l+1 that holds the 3x3 pyrUp neighbourhoods of all quads, plus
+// the 34x10x3 window of the collapsed level C_{l+1}.  Elements outside a source arrive as zeros, which is exactly
+// "weight 0": no rect tests and no predicated taps in the consumers, whose shared-memory loads sit at compile-time
+// offsets.  The pyrUp is separable and neighbouring quads share two of their three coarse columns: every thread
 // computes the vertical column sums of ONE coarse column into shared memory and reads its three columns back (3 + 3
 // shared loads instead of 9 global ones per image, 9 + 6 instead of 27 for C_{l+1}).  The blend division, the
 // collapse add and |.| / min run on two 16-bit lanes per word (VIADD.16x2, VIMNMX.S16x2) with exact integer forms
 // for the weight sums 0, 1 and 2 that make up almost all of a panorama.
 //
+// (The first version staged the windows with the tensor copy engine, cp.async.bulk.tensor / UTMALDG.  On this pool's
+// B200 boxes every tensor-map instruction -- the CUDA programming guide's own sample included -- ends in "illegal
+// instruction", while the 1-D bulk copy works: tests/tools/tma_*.cu, profiles/tma_probe_r02.md.  The staging therefore
+// uses cp.async; sb_tma.cuh keeps the wrappers.)
+//
 // Scope: the plain single-GPU roles (every item a byte-fed image, whole level, uint8 image + mask output).  Slabs,
 // partial sums, int16 output and the top level stay with k_collapse_fast (launch_collapse_tile says so by returning
-// SB_ERR_STATE).  The emulation build (tests/emu) has no copy engine and does not compile this file's kernels.
+// SB_ERR_STATE).  The emulation build (tests/emu) does not compile this file's kernels.
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
-#include "sb_tma.cuh"
 
 namespace sb {
 
@@ -32,41 +37,73 @@ namespace sb {
 namespace {
 
 constexpr int TW = SB_TILE_W, TH = SB_TILE_H, QX = TW / 2, QY = TH / 2;  // 64 x 16 pixels, 32 x 8 quads
-constexpr int UPW = SB_TILE_UPW, UPH = SB_TILE_UPH, C1W = SB_TILE_C1W;
+constexpr int UPW = SB_TILE_UPW, UPH = SB_TILE_UPH;
 #define SB_WEIGHT_EPS 1e-5f
+
+// Window geometry.  A staged row starts at a 16-byte boundary of its source row, so the logical window sits at a small
+// column offset inside the staged one: the window of the collapsed level (origin = 32 k - 1 int16 elements) at +7; the
+// windows of an image at offsets that depend on where its rect starts on the pano lattice (tile-uniform, run time):
+// RGBM and weights at (tile_x - rect_x) & 3 elements, the 8-byte lane pairs of the coarser level at origin & 1.
+constexpr int UPS = UPW + 2;                 // staged lane-pair window: 36 columns = 18 chunks, logical origin at +0 / +1 (run time)
+constexpr int C1S = 48, C1O = 7;             // staged int16 window: 48 columns = 6 chunks
+constexpr int RGS = TW + 4;                  // staged RGBM window: 68 pixels = 17 chunks
 
 // the staged windows of one covering image
 template <int LV>
 struct ItemBuf;
 template <>
-struct alignas(128) ItemBuf<0> {
-    uint32_t own[TH][TW];  // packed RGBM, zero outside the image
-    uint2 up[UPH][UPW];    // level-1 lane pairs around the tile
-    static constexpr unsigned bytes = sizeof(uint32_t) * TH * TW + sizeof(uint2) * UPH * UPW;
+struct alignas(16) ItemBuf<0> {
+    uint32_t own[TH][RGS];  // packed RGBM, zero outside the image
+    uint2 up[UPH][UPS];     // level-1 lane pairs around the tile
 };
 template <>
-struct alignas(128) ItemBuf<1> {
-    uint2 own[TH][TW];     // level-l lane pairs
-    float w[TH][TW];       // level-l weights, zero outside the padded rect
-    uint2 up[UPH][UPW];
-    static constexpr unsigned bytes = (sizeof(uint2) + sizeof(float)) * TH * TW + sizeof(uint2) * UPH * UPW;
+struct alignas(16) ItemBuf<1> {
+    uint2 own[TH][TW];      // level-l lane pairs (rect origins are even: 16-byte rows)
+    float w[TH][RGS];       // level-l weights, zero outside the padded rect
+    uint2 up[UPH][UPS];
 };
 
-template <int LV, int KB>
+template <int LV>
 struct Smem {
-    ItemBuf<LV> item[KB];
-    alignas(128) int16_t c1[3][UPH][C1W];
-    alignas(16) uint4 cs[2][QY][UPW];  // column sums of the image in flight (double buffered); reused for C_{l+1}
-    alignas(8) uint64_t bar[KB + 1];
+    ItemBuf<LV> item[2];                // the image being consumed and the next one in flight
+    alignas(16) int16_t c1[3][UPH][C1S];
+    alignas(16) uint4 cs[2][QY][UPW];   // column sums of the image in flight (double buffered); reused for C_{l+1}
     int list_n;
     unsigned short list[SB_MAX_ITEMS];
 };
 
+// 16-byte asynchronous copy global -> shared; `valid` false: nothing is read and the 16 bytes become zeros
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Stage ROWS x (CHUNKS * 16 bytes) of a source whose rows are `pitch_b` bytes apart: window row r <- source row row0 + r,
+// bytes [xb0, xb0 + 16 CHUNKS) (xb0 a multiple of 16, possibly negative).  Source rows outside [0, rows_valid) and
+// chunks outside [0, row_bytes) arrive as zeros.  row_bytes is the valid width rounded UP to 16 bytes: the bytes between
+// the valid width and row_bytes are the allocation's own zero-initialised row padding (BlendPlan / compositor).
+template <int ROWS, int CHUNKS>
+__device__ __forceinline__ void stage_rows(void *dst, const void *src, long long pitch_b, int xb0, int row0, int rows_valid, int row_bytes, int tid)
+{
+#pragma unroll
+    for (int i = tid; i < ROWS * CHUNKS; i += QX * QY) {
+        const int r = i / CHUNKS, c = i - r * CHUNKS;
+        const int row = row0 + r, xb = xb0 + 16 * c;
+        const bool ok = (unsigned)row < (unsigned)rows_valid && (unsigned)xb < (unsigned)row_bytes;
+        const char *g = reinterpret_cast<const char *>(src) + (ok ? (long long)row * pitch_b + xb : 0ll);
+        cp_async16(reinterpret_cast<char *>(dst) + 16 * i, g, ok);
+    }
+}
+
 // pyrUp borders of a staged window (rows x cols elements, window origin (bx, by) in the source level of aw x ah
 // elements): index -1 reads index 1 (reflect-101), index aw reads aw-1 (replicate); the copy engine delivered zeros
 // there.  Only those two lines can be read by a quad inside the level.  Tile-uniform call (contains barriers).
-template <typename T, int ROWS, int COLS>
-__device__ __forceinline__ void fix_borders(T (*t)[COLS], int bx, int by, int aw, int ah, int tid)
+// `t` points at logical column 0 of a staged window whose rows are STRIDE elements apart; COLS logical columns.
+template <typename T, int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ void fix_borders(T (*t)[STRIDE], int bx, int by, int aw, int ah, int tid)
 {
     const int cl = -1 - bx, cr = aw - bx;  // window columns of index -1 and index aw
     if (tid < ROWS) {
@@ -84,7 +121,7 @@ __device__ __forceinline__ void fix_borders(T (*t)[COLS], int bx, int by, int aw
 
 // vertical column sums of coarse column `col` for the quads of row `row` (lane pairs: two 16-bit lanes per word; the
 // largest value, 8 * 255, leaves room for the horizontal pass: 8 * 2040 + 32 < 2^15)
-__device__ __forceinline__ void colsum_lanes(const uint2 (*up)[UPW], uint4 (*cs)[UPW], int col, int row)
+__device__ __forceinline__ void colsum_lanes(const uint2 (*up)[UPS], uint4 (*cs)[UPW], int col, int row)  // col: staged column
 {
     const uint2 a0 = up[row][col], a1 = up[row + 1][col], a2 = up[row + 2][col];
     uint4 v;
@@ -120,17 +157,25 @@ __device__ __forceinline__ unsigned norm_two2(unsigned a)
     return __vsub2((xb >> 1) & 0x7fff7fffu, 0x02000200u);
 }
 
-template <int LV, int KB>
+template <int LV>
 __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const __grid_constant__ CollapseArgs A)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem<LV, KB> &S = *reinterpret_cast<Smem<LV, KB> *>(smem_raw);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<LV> &S = *reinterpret_cast<Smem<LV> *>(smem_raw);
     const TileDesc *__restrict__ tile = A.tile;
-    const TensorMap *maps = reinterpret_cast<const TensorMap *>(A.maps);
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QX + tx;
     const int tile_x = A.rx0 + blockIdx.x * TW, tile_y = A.ry0 + blockIdx.y * TH;
 
-    // the items whose rect touches this tile, in feed order (warp 0), and the barriers of the copy engine
+    // the collapsed level l+1 around the tile: in flight while the item list is built
+    {
+        const int bx = (tile_x >> 1) - 1 - C1O, by = (tile_y >> 1) - 1;  // bx = 32 k - 8: a 16-byte boundary of an int16 row
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            stage_rows<UPH, C1S / 8>(S.c1[c], A.up.c + (long long)c * A.up.plane, 2ll * A.up.pitch, 2 * bx, by, A.up.h_px,
+                                     (2 * A.up.w_px + 15) & ~15, tid);
+        cp_async_commit();
+    }
+    // the items whose rect touches this tile, in feed order (warp 0)
     if (ty == 0) {
         int cnt = 0;
         for (int base = 0; base < A.n; base += 32) {
@@ -144,37 +189,32 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
             if (c) S.list[cnt + __popc(m & ((1u << tx) - 1u))] = (unsigned short)i;
             cnt += __popc(m);
         }
-        if (tx == 0) {
-            S.list_n = cnt;
-#pragma unroll
-            for (int k = 0; k <= KB; ++k) mbar_init(&S.bar[k], 1);
-            mbar_fence_init();
-        }
+        if (tx == 0) S.list_n = cnt;
     }
     __syncthreads();
     const int n_cover = S.list_n;
 
-    auto issue_item = [&](int k) {  // one thread
-        const TileDesc &d = tile[S.list[k]];
-        const int4 o = __ldg(reinterpret_cast<const int4 *>(&d.ox));
-        const int4 mi = __ldg(reinterpret_cast<const int4 *>(&d.map_own));
-        ItemBuf<LV> &B = S.item[k % KB];
-        uint64_t *bar = &S.bar[k % KB];
-        mbar_expect_tx(bar, ItemBuf<LV>::bytes);
-        if (LV == 0) {
-            const int2 io = __ldg(reinterpret_cast<const int2 *>(&d.x0));
-            tma_load_2d(B.own, maps + mi.x, tile_x - io.x, tile_y - io.y, bar);
+    // all threads: the asynchronous copies of item k's windows into buffer k & 1 (one commit group per item)
+    auto stage_item = [&](int k) {
+        const int idx = S.list[k];
+        const TileDesc &d = tile[idx];
+        const ColDesc &cd = A.col[idx];
+        const int4 r = __ldg(reinterpret_cast<const int4 *>(&d.x0));   // x0, y0, w, h
+        const int4 o = __ldg(reinterpret_cast<const int4 *>(&d.ox));   // ox, oy, uw, uh
+        ItemBuf<LV> &B = S.item[k & 1];
+        if constexpr (LV == 0) {
+            const int px = (tile_x - r.x) & ~3;  // first staged pixel column: a 16-byte boundary of the image's rows
+            stage_rows<TH, RGS / 4>(B.own, cd.rgbm, 4ll * cd.rgbm_pitch, 4 * px, tile_y - r.y, r.w, (4 * r.z + 15) & ~15, tid);
         } else {
-            tma_load_2d(B.own, maps + mi.x, tile_x - o.x, tile_y - o.y, bar);
-            tma_load_2d(reinterpret_cast<ItemBuf<1> &>(B).w, maps + mi.y, tile_x - o.x, tile_y - o.y, bar);
+            const int X = tile_x - o.x, Y = tile_y - o.y;  // X even (rect origins below the top level are even)
+            stage_rows<TH, TW / 2>(B.own, cd.q, 8ll * cd.pitch, 8 * X, Y, r.w, (8 * r.z + 15) & ~15, tid);
+            stage_rows<TH, RGS / 4>(B.w, cd.w, 4ll * cd.pitch, 4 * (X & ~3), Y, r.w, (4 * r.z + 15) & ~15, tid);
         }
-        tma_load_2d(B.up, maps + mi.z, ((tile_x - o.x) >> 1) - 1, ((tile_y - o.y) >> 1) - 1, bar);
+        const int bx = (((tile_x - o.x) >> 1) - 1) & ~1, by = ((tile_y - o.y) >> 1) - 1;  // the even column at or left of the origin
+        stage_rows<UPH, UPS / 2>(B.up, cd.uq, 8ll * cd.upitch, 8 * bx, by, o.w, (8 * o.z + 15) & ~15, tid);
+        cp_async_commit();
     };
-    if (tid == 0) {
-        mbar_expect_tx(&S.bar[KB], sizeof S.c1);
-        tma_load_3d(S.c1, maps + A.map_c_up, (tile_x >> 1) - 1, (tile_y >> 1) - 1, 0, &S.bar[KB]);
-        for (int k = 0; k < KB && k < n_cover; ++k) issue_item(k);
-    }
+    if (n_cover > 0) stage_item(0);
 
     // accumulators of the quad (index dy * 2 + dx): red | blue << 16 as two wrap-around lanes, green, weight sum
     unsigned acc_rb[4] = {0u, 0u, 0u, 0u};
@@ -182,33 +222,35 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
     float wsum[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int k = 0; k < n_cover; ++k) {
-        const int slot = k % KB;
-        if (k >= KB && slot == 0) {  // every window of the previous group has been consumed: stage the next group
-            __syncthreads();
-            if (tid == 0) {
-                fence_proxy_async();
-                for (int j = k; j < k + KB && j < n_cover; ++j) issue_item(j);
-            }
+        // item k+1 goes into the other buffer, whose last reader passed the second barrier of iteration k-1
+        if (k + 1 < n_cover) {
+            stage_item(k + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        ItemBuf<LV> &B = S.item[slot];
-        const int4 o = __ldg(reinterpret_cast<const int4 *>(&tile[S.list[k]].ox));  // ox, oy, uw, uh
-        mbar_wait(&S.bar[slot], (unsigned)(k / KB) & 1u);
-        {
-            const int bx = ((tile_x - o.x) >> 1) - 1, by = ((tile_y - o.y) >> 1) - 1;
-            if (bx < 0 || by < 0 || bx + UPW > o.z || by + UPH > o.w) fix_borders<uint2, UPH, UPW>(B.up, bx, by, o.z, o.w, tid);
-        }
+        __syncthreads();  // item k's windows (and C_{l+1}'s) are complete for every thread
+        ItemBuf<LV> &B = S.item[k & 1];
+        const TileDesc &d = tile[S.list[k]];
+        const int4 o = __ldg(reinterpret_cast<const int4 *>(&d.ox));  // ox, oy, uw, uh
+        const int bx = ((tile_x - o.x) >> 1) - 1, by = ((tile_y - o.y) >> 1) - 1;
+        const int su = bx & 1;  // logical column c of the coarse window = staged column c + su
+        if (bx < 0 || by < 0 || bx + UPW > o.z || by + UPH > o.w)
+            fix_borders<uint2, UPH, UPW, UPS>(reinterpret_cast<uint2(*)[UPS]>(&B.up[0][su]), bx, by, o.z, o.w, tid);
         uint4(*cs)[UPW] = S.cs[k & 1];
-        colsum_lanes(B.up, cs, tx, ty);
-        if (tid < 2 * QY) colsum_lanes(B.up, cs, QX + (tid & 1), tid >> 1);  // the two columns right of the last quad
+        {
+            const uint2(*ups)[UPS] = reinterpret_cast<const uint2(*)[UPS]>(&B.up[0][su]);
+            colsum_lanes(ups, cs, tx, ty);
+            if (tid < 2 * QY) colsum_lanes(ups, cs, QX + (tid & 1), tid >> 1);  // the two columns right of the last quad
+        }
 
         // the quad's own pixels: g_rb = r | b << 16, g_g = green, wt = weight
         unsigned g_rb[4], g_g[4];
         float wt[4];
         bool nothing, unit;
-        if (LV == 0) {
-            const uint2 r0 = *reinterpret_cast<const uint2 *>(&B.own[2 * ty][2 * tx]);
-            const uint2 r1 = *reinterpret_cast<const uint2 *>(&B.own[2 * ty + 1][2 * tx]);
-            const unsigned p[4] = {r0.x, r0.y, r1.x, r1.y};
+        if constexpr (LV == 0) {
+            const int sx = ((tile_x - __ldg(&d.x0)) & 3) + 2 * tx;  // the staged window starts at a multiple of 4 pixels
+            const unsigned p[4] = {B.own[2 * ty][sx], B.own[2 * ty][sx + 1], B.own[2 * ty + 1][sx], B.own[2 * ty + 1][sx + 1]};
             nothing = ((p[0] | p[1] | p[2] | p[3]) >> 24) == 0u;           // all four weights are exactly 0
             unit = ((p[0] & p[1] & p[2] & p[3]) >> 24) == 255u;             // all four weights are exactly 1
 #pragma unroll
@@ -218,11 +260,11 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
                 wt[q] = unit ? 1.f : fmul((float)(p[q] >> 24), SB_INV255);  // 255 * fl(1/255) == 1 exactly
             }
         } else {
-            const ItemBuf<1> &B1 = reinterpret_cast<const ItemBuf<1> &>(B);
-            const float2 w0 = *reinterpret_cast<const float2 *>(&B1.w[2 * ty][2 * tx]);
-            const float2 w1 = *reinterpret_cast<const float2 *>(&B1.w[2 * ty + 1][2 * tx]);
-            const uint4 a = *reinterpret_cast<const uint4 *>(&B1.own[2 * ty][2 * tx]);
-            const uint4 b = *reinterpret_cast<const uint4 *>(&B1.own[2 * ty + 1][2 * tx]);
+            const int sw = ((tile_x - o.x) & 3) + 2 * tx;  // the staged weight window starts at a multiple of 4 columns
+            const float2 w0 = *reinterpret_cast<const float2 *>(&B.w[2 * ty][sw]);
+            const float2 w1 = *reinterpret_cast<const float2 *>(&B.w[2 * ty + 1][sw]);
+            const uint4 a = *reinterpret_cast<const uint4 *>(&B.own[2 * ty][2 * tx]);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&B.own[2 * ty + 1][2 * tx]);
             wt[0] = w0.x; wt[1] = w0.y; wt[2] = w1.x; wt[3] = w1.y;
             g_rb[0] = a.x; g_g[0] = a.y; g_rb[1] = a.z; g_g[1] = a.w;
             g_rb[2] = b.x; g_g[2] = b.y; g_rb[3] = b.z; g_g[3] = b.w;
@@ -266,12 +308,16 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
     }
 
     // ---- pyrUp of the collapsed level l+1 ---------------------------------------------------------------------------
-    mbar_wait(&S.bar[KB], 0u);
+    if (n_cover == 0) {
+        cp_async_wait<0>();
+        __syncthreads();
+    }
     {
         const int bx = (tile_x >> 1) - 1, by = (tile_y >> 1) - 1;
         if (bx < 0 || by < 0 || bx + UPW > A.up.w_px || by + UPH > A.up.h_px) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) fix_borders<int16_t, UPH, C1W>(S.c1[c], bx, by, A.up.w_px, A.up.h_px, tid);
+            for (int c = 0; c < 3; ++c)
+                fix_borders<int16_t, UPH, UPW, C1S>(reinterpret_cast<int16_t(*)[C1S]>(&S.c1[c][0][C1O]), bx, by, A.up.w_px, A.up.h_px, tid);
         }
     }
     __syncthreads();  // nobody reads the images' column sums any more: the buffers now take those of C_{l+1}
@@ -281,7 +327,7 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
         int e[3], od[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const int a0 = S.c1[c][row][col], a1 = S.c1[c][row + 1][col], a2 = S.c1[c][row + 2][col];
+            const int a0 = S.c1[c][row][col + C1O], a1 = S.c1[c][row + 1][col + C1O], a2 = S.c1[c][row + 2][col + C1O];
             e[c] = a0 + a2 + 6 * a1;
             od[c] = a1 + a2;
         }
@@ -410,22 +456,20 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 5 : 4) k_collapse_tile(const
     }
 }
 
-constexpr int KB0 = 3, KB1 = 2;
-
 }  // namespace
 
 bool collapse_tile_enabled()
 {
     static const bool on = [] {
         const char *e = getenv("SB_TILE");
-        return !(e && e[0] == '0') && tensor_maps_available();
+        return !(e && e[0] == '0');
     }();
     return on;
 }
 
 int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
 {
-    if (!A.tile || !A.maps || A.map_c_up < 0 || l >= nb || A.partial || A.n > SB_MAX_ITEMS || !collapse_tile_enabled()) return SB_ERR_STATE;
+    if (!A.tile || l >= nb || A.partial || A.n > SB_MAX_ITEMS || !collapse_tile_enabled()) return SB_ERR_STATE;
     if ((A.rx0 | A.ry0 | A.rw | A.rh) & 1) return SB_ERR_STATE;
     if (l == 0) {
         const PanoOut &out = A.out;
@@ -438,15 +482,15 @@ int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
     if (A.rw <= 0 || A.rh <= 0) return SB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0, KB0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0, KB0>)));
-        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1, KB1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1, KB1>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
         attr_set = true;
     }
     dim3 block(QX, QY), grid(div_up(A.rw, TW), div_up(A.rh, TH));
     if (l == 0)
-        launch(k_collapse_tile<0, KB0>, grid, block, sizeof(Smem<0, KB0>), s, A);
+        launch(k_collapse_tile<0>, grid, block, sizeof(Smem<0>), s, A);
     else
-        launch(k_collapse_tile<1, KB1>, grid, block, sizeof(Smem<1, KB1>), s, A);
+        launch(k_collapse_tile<1>, grid, block, sizeof(Smem<1>), s, A);
     return launch_check("k_collapse_tile");
 }
 #else   // SB_EMU

@@ -177,6 +177,8 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         if (!mine(i)) continue;  // another rank warps this image: only its geometry is needed here
         SB_TRY(dev_alloc((void **)&c->src_dev[i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
         SB_TRY(dev_alloc((void **)&c->rgbm_dev[i], (size_t)rgbm_pitch_of(rect[2]) * rect[3] * 4, s));
+        // the row padding (never written by the warp kernel) is read by the tile kernels' 16-byte copies: weight 0
+        SB_CUDA(cudaMemsetAsync(c->rgbm_dev[i], 0, (size_t)rgbm_pitch_of(rect[2]) * rect[3] * 4, s));
         SB_TRY(dev_alloc((void **)&c->tab_dev[i], warp_table_floats(rect[2], rect[3]) * sizeof(float), s));
         SB_TRY(make_warp_job(p, rect, c->src_w[i], c->src_h[i], c->tab_dev[i], &c->jobs[i], s, host_tab));
         SB_CUDA(cudaStreamSynchronize(s));  // host_tab is reused by the next image

@@ -147,19 +147,17 @@ struct alignas(16) PyrDesc {       // pyrDown of level l -> l+1
     int pad0, pad1, pad2, pad4;
 };
 
-// Per-(level, image) descriptor of the TMA tile kernels (sb_collapse_tile.cu): the rect that decides whether an item
-// touches a tile, the origins of its staged windows and the indices of its tensor maps (sb_tma.cuh) in BlendPlan::maps_dev.
+// Per-(level, image) descriptor of the tile kernels (sb_collapse_tile.cu), next to the item's ColDesc: the rect that
+// decides whether the item touches a tile (= the extent of its level-l source) and the origins of its staged windows.
 struct alignas(16) TileDesc {
     int x0, y0, w, h;           // level 0: the fed IMAGE inside its padded rect (weights are 0 outside); levels >= 1: the padded rect
     int ox, oy, uw, uh;         // padded rect origin at this level; size of the next coarser level (source of the pyrUp)
-    int map_own, map_w, map_up, pad;  // level 0: RGBM image; levels >= 1: colour lane pairs + weights; next level's lane pairs
 };
 // window shapes of the tile kernels (one CTA = TILE_W x TILE_H pixels of a level, one thread per 2x2 quad)
 #define SB_TILE_W 64
 #define SB_TILE_H 16
 #define SB_TILE_UPW (SB_TILE_W / 2 + 2)   // 34: the 3x3 neighbourhoods of the tile's quads at the coarser level
 #define SB_TILE_UPH (SB_TILE_H / 2 + 2)   // 10
-#define SB_TILE_C1W 40                    // int16 window of a collapsed level: 34 columns rounded up to 16-byte rows
 
 struct PanoLevel {
     int16_t *c;  // collapsed planar int16 x3 [3][h][pitch]
@@ -187,12 +185,9 @@ struct CollapseArgs {
     int slab_pitch, slab_plane;
     PanoOut out;              // level 0: final outputs; the buffer covers pano columns [out_x0, out_x0 + out.w)
     int out_x0, out_lo, out_hi;  // only columns [out_lo, out_hi) are stored (a strip's margin is not output)
-    // TMA tile kernels (null / -1: not available for this launch)
-    const TileDesc *tile;     // items of this level, same order as col
-    const void *maps;         // TensorMap array (device)
-    int map_c_up;             // tensor map of C_{l+1} (three int16 planes)
+    const TileDesc *tile;     // tile kernels: items of this level, same order as col (null: not available for this launch)
 };
-// the TMA tile version of the per-level kernel for the plain single-GPU roles; returns SB_ERR_STATE when the launch
+// the shared-memory tile version of the per-level kernel for the plain single-GPU roles; returns SB_ERR_STATE when the launch
 // does not qualify (the caller then uses launch_collapse_fast)
 int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s);
 bool collapse_tile_enabled();
@@ -216,8 +211,11 @@ bool use_simple_kernels();
 struct TileDesc;
 int launch_collapse(const FeedImage *imgs_dev, const FeedImage *imgs_host, const ColDesc *col, int n, const PanoLevel *pano_dev,
                     const PanoLevel *pano_host, int l, int nb, int lw, int lh, PanoOut out, cudaStream_t s,
-                    const TileDesc *tile = nullptr, const void *maps = nullptr, int map_c_up = -1);
+                    const TileDesc *tile = nullptr);
 // feather: distance-transform weight maps, then one fused accumulate/normalise pass; NO blender
+// levels T .. nb in one launch (sb_tail.cu); SB_ERR_STATE: not available (emulation build), launch per level instead
+int launch_tail(const FeedImage *imgs_dev, const PanoLevel *pano_dev, int first, int count, int n, int T, int nb, int wp, int hp, const PanoOut &out,
+                unsigned *state, cudaStream_t s);
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);

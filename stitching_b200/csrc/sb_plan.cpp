@@ -181,11 +181,13 @@ int BlendPlan::allocate(cudaStream_t s)
     const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
     const size_t col_off = carve(sizeof(ColDesc) * (size_t)std::max(n, 1) * (nb + 1));
     const size_t pyr_off = carve(sizeof(PyrDesc) * (size_t)std::max(n, 1) * (nb + 1));
-    const size_t n_maps = (size_t)3 * std::max(n, 1) * (nb + 1) + (nb + 1);
     const size_t tile_off = carve(sizeof(TileDesc) * (size_t)std::max(n, 1) * (nb + 1));
-    const size_t maps_off = carve(sizeof(TensorMap) * n_maps);
+    const size_t tail_off = carve(256);
     arena_bytes_ = off;
     SB_TRY(dev_alloc(&arena_, arena_bytes_, s));
+    // zero once: the row padding of every level (pitch - width elements, never written by a kernel) is read as part of
+    // 16-byte chunks by the tile kernels' staged copies and must be "weight 0"
+    SB_CUDA(cudaMemsetAsync(arena_, 0, arena_bytes_, s));
     char *base = (char *)arena_;
     std::memset(pano, 0, sizeof pano);
     if (kind == SB_BLEND_MULTIBAND) {
@@ -215,6 +217,18 @@ int BlendPlan::allocate(cudaStream_t s)
     pano_dev = (PanoLevel *)(base + panod_off);
     col_dev = (ColDesc *)(base + col_off);
     pyr_dev = (PyrDesc *)(base + pyr_off);
+    tail_state_dev = (unsigned *)(base + tail_off);
+    // fused tail (sb_tail.cu): OFF by default -- measured on B200 (profiles/bench_r02_c_tail.json) the one-launch
+    // per-pixel version of levels 3..7 takes 0.19 ms against 0.11 ms for the twelve tuned per-level launches.
+    // SB_TAIL_FROM=<level> enables it from that level on (A/B measurements, tests).
+    tail_from = 1 << 30;
+    if (kind == SB_BLEND_MULTIBAND && active_count < 0 && n > 0) {
+        static const int forced = [] {
+            const char *e = getenv("SB_TAIL_FROM");
+            return e ? atoi(e) : -1;
+        }();
+        if (forced >= 0 && forced < nb) tail_from = forced;
+    }
     // compact per-(level, image) descriptors for the fast kernels: [l * n + i]
     std::vector<ColDesc> &col = col_host;
     std::vector<PyrDesc> &pyr = pyr_host;
@@ -270,30 +284,18 @@ int BlendPlan::allocate(cudaStream_t s)
             SB_CUDA(cudaMemcpyAsync(col_dev, col.data(), sizeof(ColDesc) * col.size(), cudaMemcpyHostToDevice, s));
             SB_CUDA(cudaMemcpyAsync(pyr_dev, pyr.data(), sizeof(PyrDesc) * pyr.size(), cudaMemcpyHostToDevice, s));
         }
-        // TMA tile kernels: tensor maps of every window they stage + per-(level, image) descriptors.  Byte-fed images
-        // with storage on this device only; any geometry the copy engine refuses leaves tile_dev null (no error).
+        // tile kernels (sb_collapse_tile.cu): per-(level, image) rects.  Byte-fed images with storage on this device;
+        // the staged copies need 16-byte rows (RGBM pitch a multiple of 4 pixels, 16-byte aligned base)
         tile_dev = nullptr;
-        maps_dev = nullptr;
         bool tiles = n > 0 && nb >= 1 && active_count < 0 && collapse_tile_enabled();
-        for (int i = 0; i < n && tiles; ++i) tiles = imgs[i].rgbm != nullptr;
+        for (int i = 0; i < n && tiles; ++i)
+            tiles = imgs[i].rgbm != nullptr && imgs[i].rgbm_pitch % 4 == 0 && ((uintptr_t)imgs[i].rgbm & 15) == 0;
         if (tiles) {
-            std::vector<TensorMap> maps(n_maps);
             std::vector<TileDesc> td((size_t)n * (nb + 1));
             std::memset(td.data(), 0, sizeof(TileDesc) * td.size());
-            auto midx = [&](int l, int i, int kind) { return (int)(((size_t)l * n + i) * 3 + kind); };
-            map_pano_base = 3 * n * (nb + 1);
-            int rc = SB_OK;
-            for (int l = 0; l <= nb && rc == SB_OK; ++l)
-                for (int i = 0; i < n && rc == SB_OK; ++i) {
+            for (int l = 0; l <= nb; ++l)
+                for (int i = 0; i < n; ++i) {
                     const FeedImage &im = imgs[i];
-                    if (l == 0) {
-                        rc = tensor_map_encode(&maps[midx(0, i, 0)], TMA_U32, im.rgbm, im.w, im.h, im.rgbm_pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
-                    } else {
-                        const Level &L = im.lv[l];
-                        rc = tensor_map_encode(&maps[midx(l, i, 0)], TMA_U64, L.q, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
-                        if (rc == SB_OK) rc = tensor_map_encode(&maps[midx(l, i, 1)], TMA_F32, L.w, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_W, SB_TILE_H, 1);
-                        if (rc == SB_OK) rc = tensor_map_encode(&maps[midx(l, i, 2)], TMA_U64, L.q, L.w_px, L.h_px, L.pitch, 0, 0, SB_TILE_UPW, SB_TILE_UPH, 1);
-                    }
                     TileDesc &t = td[(size_t)l * n + i];
                     t.ox = im.px >> l;
                     t.oy = im.py >> l;
@@ -310,20 +312,10 @@ int BlendPlan::allocate(cudaStream_t s)
                     }
                     t.uw = im.pw >> (l + 1);
                     t.uh = im.ph >> (l + 1);
-                    t.map_own = midx(l, i, 0);
-                    t.map_w = midx(l, i, 1);
-                    t.map_up = midx(l + 1 <= nb ? l + 1 : nb, i, 2);
                 }
-            for (int l = 1; l <= nb && rc == SB_OK; ++l)
-                rc = tensor_map_encode(&maps[map_pano_base + l], TMA_U16, pano[l].c, pano[l].w_px, pano[l].h_px, pano[l].pitch, 3, pano[l].plane,
-                                       SB_TILE_C1W, SB_TILE_UPH, 3);
-            if (rc == SB_OK) {
-                tile_dev = (TileDesc *)(base + tile_off);
-                maps_dev = base + maps_off;
-                SB_CUDA(cudaMemcpyAsync(tile_dev, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice, s));
-                SB_CUDA(cudaMemcpyAsync(maps_dev, maps.data(), sizeof(TensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
-                SB_CUDA(cudaStreamSynchronize(s));  // `maps` / `td` are locals
-            }
+            tile_dev = (TileDesc *)(base + tile_off);
+            SB_CUDA(cudaMemcpyAsync(tile_dev, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaStreamSynchronize(s));  // `td` is a local
         }
     }
     if (n) SB_CUDA(cudaMemcpyAsync(imgs_dev, imgs.data(), sizeof(FeedImage) * n, cudaMemcpyHostToDevice, s));
@@ -343,7 +335,7 @@ void BlendPlan::release(cudaStream_t s)
     col_dev = nullptr;
     pyr_dev = nullptr;
     tile_dev = nullptr;
-    maps_dev = nullptr;
+    tail_state_dev = nullptr;
 }
 
 int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(const std::string &)> &mark)
@@ -351,7 +343,20 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
     const int n = (int)imgs.size();
     auto note = [&](const std::string &name) -> int { return mark ? mark(name) : SB_OK; };
     if (kind == SB_BLEND_MULTIBAND) {
+        int T = tail_from <= nb ? tail_from : nb + 1;  // levels >= T: one launch (sb_tail.cu)
+        bool tail_done = false;
         for (int l = 0; l < nb; ++l) {
+            if (l >= T) {
+                if (tail_done) continue;
+                const int rc = launch_tail(imgs_dev, pano_dev, 0, n, n, T, nb, wp, hp, out, tail_state_dev, s);
+                if (rc == SB_OK) {
+                    tail_done = true;
+                    SB_TRY(note("tail_l" + std::to_string(T) + "-" + std::to_string(nb)));
+                    continue;
+                }
+                if (rc != SB_ERR_STATE) return rc;
+                T = nb + 1;  // not available here: per-level launches
+            }
             int mw = 0, mh = 0;
             for (const FeedImage &im : imgs) {
                 mw = std::max(mw, im.pw >> (l + 1));
@@ -361,8 +366,9 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
             SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
         for (int l = nb; l >= 0; --l) {
+            if (tail_done && l >= T) continue;
             SB_TRY(launch_collapse(imgs_dev, imgs.data(), col_dev + (size_t)l * n, n, pano_dev, pano, l, nb, wp >> l, hp >> l, out, s,
-                                   tile_dev ? tile_dev + (size_t)l * n : nullptr, maps_dev, map_pano_base + l + 1));
+                                   tile_dev ? tile_dev + (size_t)l * n : nullptr));
             SB_TRY(note("collapse_l" + std::to_string(l)));
         }
     } else {
@@ -383,13 +389,22 @@ std::vector<std::pair<std::string, double>> BlendPlan::launch_bytes() const
     std::vector<std::pair<std::string, double>> v;
     const double l0 = imgs.empty() ? 4.0 : (imgs[0].rgbm ? 4.0 : 7.0);  // bytes per level-0 pixel
     if (kind == SB_BLEND_MULTIBAND) {
+#ifdef SB_EMU
+        const int T = nb + 1;
+#else
+        const int T = tail_from <= nb ? tail_from : nb + 1;
+#endif
+        double tail = 0;
         for (int l = 0; l < nb; ++l) {
             double b = 0;
             for (const FeedImage &im : imgs) {
                 const double src = (double)(im.pw >> l) * (im.ph >> l);
                 b += (l == 0 ? l0 : 10.0) * src + 10.0 * src / 4;  // read level l, write level l+1
             }
-            v.emplace_back("pyrdown_l" + std::to_string(l), b);
+            if (l >= T)
+                tail += b;
+            else
+                v.emplace_back("pyrdown_l" + std::to_string(l), b);
         }
         for (int l = nb; l >= 0; --l) {
             double b = 0;
@@ -401,7 +416,12 @@ std::vector<std::pair<std::string, double>> BlendPlan::launch_bytes() const
             const double P = (double)(wp >> l) * (hp >> l);
             if (l < nb) b += 6.0 * P / 4;        // C_{l+1}
             b += l > 0 ? 6.0 * P : 4.0 * (double)roi.w * roi.h;  // C_l, or the final uint8x3 + mask
-            v.emplace_back("collapse_l" + std::to_string(l), b);
+            if (l >= T) {
+                tail += b;
+                if (l == T) v.emplace_back("tail_l" + std::to_string(T) + "-" + std::to_string(nb), tail);
+            } else {
+                v.emplace_back("collapse_l" + std::to_string(l), b);
+            }
         }
     } else {
         double bw = 0, bb = 0;

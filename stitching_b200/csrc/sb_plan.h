@@ -6,7 +6,6 @@
 #include <vector>
 
 #include "sb_internal.h"
-#include "sb_tma.cuh"
 
 namespace sb {
 
@@ -44,11 +43,12 @@ public:
     PyrDesc *pyr_dev = nullptr;
     std::vector<ColDesc> col_host;  // host copies (the sharded compositor builds its item lists from them)
     std::vector<PyrDesc> pyr_host;
-    // TMA tile kernels (sb_collapse_tile.cu): tensor maps of every staged window and the per-(level, image) descriptors;
-    // null when the copy engine cannot serve this plan's geometry (the fast kernels then do the work)
+    // tile kernels (sb_collapse_tile.cu): per-(level, image) descriptors; null when the plan does not qualify
+    // (generic int16 feeds, a sharded composite): the fast kernels then do the work
     TileDesc *tile_dev = nullptr;   // [(nb+1)][n]
-    void *maps_dev = nullptr;       // TensorMap array
-    int map_pano_base = 0;          // index of the map of collapsed level l: map_pano_base + l
+    // fused pyramid tail (sb_tail.cu): levels >= tail_from run in one launch; tail_from > nb: no tail
+    int tail_from = 1 << 30;
+    unsigned *tail_state_dev = nullptr;  // the grid barrier's two words
     // images [active_first, active_first + active_count) get pyramid storage; the others (owned by other ranks of
     // a sharded composite) only take part in the geometry.  active_count < 0: all images.
     int active_first = 0, active_count = -1;

@@ -6,7 +6,7 @@
 #include <cstdlib>
 
 #include "sb_launch.h"
-#include "sb_pyramid.cuh"
+#include "sb_gather.cuh"
 
 namespace sb {
 
@@ -18,46 +18,12 @@ constexpr int PD_BX = 32, PD_BY = 8;
 __global__ void __launch_bounds__(PD_BX *PD_BY) k_pyrdown_gather(const FeedImage *__restrict__ imgs, int first, int l)
 {
     const FeedImage &im = imgs[first + blockIdx.z];
-    const int sw = im.pw >> l, sh = im.ph >> l;  // source level size
-    const int dw = sw >> 1, dh = sh >> 1;
+    const int dw = im.pw >> (l + 1), dh = im.ph >> (l + 1);  // destination level size
     const int x = blockIdx.x * PD_BX + threadIdx.x;
     const int y = blockIdx.y * PD_BY + threadIdx.y;
     if (x >= dw || y >= dh) return;
 
-    int xi[5], yi[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        xi[k] = reflect101(2 * x + k - 2, sw);
-        yi[k] = reflect101(2 * y + k - 2, sh);
-    }
-    const bool h_simd = x >= 1 && x < pyrdown_hs_end(sw);
-    const bool v_simd = x < (dw / 4) * 4;
-
-    int acc[3] = {0, 0, 0};
-    float rowf[5];
-    const int kw[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-        int hs[3] = {0, 0, 0};
-        float wv[5];
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            int c[3];
-            load_level(im, l, xi[kx], yi[ky], c, wv[kx]);
-            hs[0] += kw[kx] * c[0];
-            hs[1] += kw[kx] * c[1];
-            hs[2] += kw[kx] * c[2];
-        }
-        acc[0] += kw[ky] * hs[0];
-        acc[1] += kw[ky] * hs[1];
-        acc[2] += kw[ky] * hs[2];
-        rowf[ky] = tap5_h(wv[0], wv[1], wv[2], wv[3], wv[4], h_simd);
-    }
-    const Level &D = im.lv[l + 1];
-    const long long o = (long long)y * D.pitch + x;
-    const int out[3] = {(acc[0] + 128) >> 8, (acc[1] + 128) >> 8, (acc[2] + 128) >> 8};
-    store_colours(D, o, out);
-    D.w[o] = tap5_v(rowf[0], rowf[1], rowf[2], rowf[3], rowf[4], v_simd);
+    pyrdown_pixel(im, l, x, y);
 }
 
 

@@ -60,7 +60,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const TensorMap *map, int
                  "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_desc(const TensorMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+// A tensor map that lives in GLOBAL memory and was written by the host (cudaMemcpy): the thread that is going to use it
+// makes the tensormap proxy acquire it first (CUDA programming guide, "tensor maps in global memory")
+__device__ __forceinline__ void tma_acquire_desc(const TensorMap *map)
+{
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace sb

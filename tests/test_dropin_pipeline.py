@@ -207,3 +207,18 @@ def test_stitcher_runs_end_to_end_on_the_swapped_classes(reference_stitching, us
     assert pano.ndim == 3 and pano.dtype == np.uint8
     assert abs(pano.shape[0] - ref_pano.shape[0]) <= 30 and abs(pano.shape[1] - ref_pano.shape[1]) <= 30  # tests/test_stitcher.py:229-231 style
     assert (pano.sum(axis=2) > 0).mean() > 0.5
+
+
+def test_stitch_verbose_runs_after_install(reference_stitching, use_emu, tmp_path):
+    """Stitcher.stitch_verbose (verbose.py) after install(): it draws the FINAL-resolution seam masks with
+    SeamFinder.draw_seam_mask, i.e. cv.UMat.get(seam_mask) (seam_finder.py:47, verbose.py:149-156) -- the drop-in
+    SeamFinder.resize therefore has to hand out what the reference hands out (a cv.UMat)."""
+    stitching, cv = reference_stitching
+    import stitching_b200
+
+    stitching_b200.install(stitching)
+    views = synthetic_views(cv)
+    pano = stitching.Stitcher(**SETTINGS).stitch_verbose([v.copy() for v in views], verbose_dir=str(tmp_path))
+    assert pano.ndim == 3 and pano.dtype == np.uint8 and (pano.sum(axis=2) > 0).mean() > 0.5
+    written = sorted(os.listdir(tmp_path))
+    assert any(name.startswith("08_seam_mask") for name in written) and "09_result.jpg" in written, written

@@ -391,3 +391,44 @@ def test_against_cv2_directly_when_available(cuda_lib):
     pano, pmask = b.blend()
     assert_parity(pano, cv.convertScaleAbs(ref), "cv2 multiband pano")
     assert np.array_equal(pmask, ref_mask)
+
+
+def _full_size_case(name, n_images=None, noise=False):
+    """GPU composite vs the reference's cv2 call sequence (oracle/cv_path.py) on the same full-size inputs."""
+    pytest.importorskip("cv2")
+    from oracle import cv_path
+
+    cfg = rigs.config(name, 1)
+    cams = cfg["cameras"][: n_images or cfg["n"]]
+    n = len(cams)
+    gen = rigs.noise_image if noise else rigs.synth_image
+    imgs = [gen(cfg["h"], cfg["w"], 40 + i) for i in range(n)]
+    c = Compositor(cams, [(cfg["w"], cfg["h"])] * n, cfg["warper"], cfg["blender"], cfg["strength"])
+    pano, mask = c.composite(imgs)
+    nb = c.num_bands
+    c.close()
+    t0 = time.time()
+    ref_pano, ref_mask, _ = cv_path.composite(cfg, cams, imgs, os.cpu_count())
+    if hasattr(ref_mask, "get"):
+        ref_mask = ref_mask.get()
+    print(f"{name}/{n}: cv2 reference path {time.time() - t0:.1f} s, pano {pano.shape}, {nb} bands")
+    assert_parity(pano, ref_pano, f"{name}/{n} full-size panorama vs cv2")
+    assert np.array_equal(mask, ref_mask), f"{name}/{n}: {int((mask != ref_mask).sum())} mask values differ"
+    return nb
+
+
+def test_benchmarked_configuration_at_full_size_against_cv2(cuda_lib):
+    """EXACTLY what bench.py times at N = 1 -- BASELINE configs[1]: 8 x 4000x3000, spherical, multiband, 7 bands -- end to
+    end against the reference's CPU path: panorama and mask bit for bit (the reference's own tests pin only the shape,
+    tests/test_stitcher.py:229-231)."""
+    assert _full_size_case("cfg2") == 7
+
+
+def test_other_configurations_at_full_size_against_cv2(cuda_lib):
+    """configs[4] (16 x 2000x1500 affine + feather) whole; configs[2] (cylindrical, f = 8000) and configs[3]
+    (8000x6000 spherical) at full image size on the first images of their rings (what cv2 finishes in about a minute);
+    cfg 2 once more on pure noise, the adversarial input for rounding."""
+    _full_size_case("cfg5")
+    _full_size_case("cfg3", 12)
+    _full_size_case("cfg4", 3)
+    _full_size_case("cfg2", 4, noise=True)
