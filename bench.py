@@ -314,6 +314,34 @@ def set_extras(comp):
         comp.set_seam_mask(i, seam)
 
 
+def dropin_e2e(cfg, imgs, reps=3):
+    """The path the north_star names: the reference's own call sequence (stitcher.py:185-189, 219-225, 241-259) through the
+    drop-in classes -- Warper.warp_images + create_and_warp_masks + warp_rois, Blender.prepare / feed / blend -- with host
+    ndarrays in and out, every call synchronous like the reference's.  Returns (MPix/s, ms per composite, result)."""
+    from stitching_b200 import Blender, Warper
+
+    cams = cfg["cameras"]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    times = []
+    pano = mask = None
+    for _ in range(reps + 1):  # the first pass is the warm-up
+        t0 = time.perf_counter()
+        warper = Warper(cfg["warper"])
+        warper.set_scale(cams)
+        warped = list(warper.warp_images(imgs, cams))
+        masks = list(warper.create_and_warp_masks(sizes, cams))
+        corners, wsizes = warper.warp_rois(sizes, cams)
+        blender = Blender(cfg["blender"], cfg["strength"])
+        blender.prepare(corners, wsizes)
+        for img, m, c in zip(warped, masks, corners):
+            blender.feed(img, m, c)
+        pano, mask = blender.blend()
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times[1:]))
+    mpix = len(cams) * cfg["w"] * cfg["h"] / 1e6
+    return mpix / dt, 1e3 * dt, pano, mask
+
+
 def run_ours(args, rank, local_rank, world):
     from stitching_b200 import Compositor, _lib
 
@@ -437,6 +465,15 @@ def run_ours(args, rank, local_rank, world):
            "api": "stitching_b200.Compositor.submit/wait (sb_compositor_submit/_wait C ABI): per step H2D of the sources "
                   "from pinned host memory + warp/blend + D2H of panorama and mask; consecutive steps pipelined 3 deep"}
     assert np.array_equal(pano, pano2), "pipelined slots disagree"
+    # the same step through the drop-in Warper / Blender classes (what stitcher.py calls), host ndarrays in and out
+    dropin = None
+    if rank == 0 and not args.no_dropin:
+        dv, dms, dpano, dmask = dropin_e2e(cfg, imgs)
+        dropin = {"value": dv, "unit": UNIT, "ms_per_step": dms, "h2d_bytes_per_step": n * src_bytes, "d2h_bytes_per_step": ph * pw * 4,
+                  "identical_to_compositor": bool(np.array_equal(dpano, pano) and np.array_equal(dmask, pmask)),
+                  "api": "stitching_b200.Warper.warp_images / create_and_warp_masks / warp_rois + Blender.prepare / feed / blend "
+                         "(the calls of stitcher.py:185-189, 241-259): pageable host ndarrays in and out, one synchronous call per image and stage"}
+        e2e["dropin"] = dropin
     checksum = int(pano[::97, ::89].astype(np.uint64).sum())  # the result was really produced and read back
 
     # ---- CPU baseline: the reference's cv2 path on this box's host cores (rank 0, N = 1 only), and parity ------
@@ -550,20 +587,69 @@ def run_sharded(args, rank, local_rank, world):
     e2e_s = dist.max(time.perf_counter() - t0)
     h2d = dist.sum(len(imgs) * src_bytes)
     d2h = dist.sum(ph * sw * 4)
+
+    # ---- parity of the sharded result (outside every timed region): every rank's strip against ONE single-GPU
+    # composite of the whole ring computed on rank 0's GPU.  int16 sums are exact under any grouping; the float weight
+    # sums are grouped per rank (re-associated where images of three or more ranks meet): +-1 LSB is the stated bar.
+    import torch
+
+    parity, like_for_like = None, None
+    strips = [None] * world
+    dist.pg.all_gather_object(strips, (int(comp.strip[0]), int(comp.strip[1])))
+    if rank == 0:
+        t0 = time.perf_counter()
+        whole = Compositor(cams, [(w, h)] * n, "cylindrical", "multiband", 5)
+        ref_pano, ref_mask = whole.composite([rigs.synth_image(h, w, i) for i in range(n)])
+        whole.close()
+        differing, max_abs, mask_diff, values = 0, 0, 0, 0
+        for r in range(world):
+            lo, hi = strips[r]
+            if hi <= lo:
+                continue
+            if r == 0:
+                sp, sm = np.array(pano), np.array(pmask)
+            else:
+                tp = torch.empty((ph, hi - lo, 3), dtype=torch.uint8)
+                tm = torch.empty((ph, hi - lo), dtype=torch.uint8)
+                dist.pg.recv(tp, src=r)
+                dist.pg.recv(tm, src=r)
+                sp, sm = tp.numpy(), tm.numpy()
+            d = np.abs(sp.astype(np.int16) - ref_pano[:, lo:hi].astype(np.int16))
+            differing += int(np.count_nonzero(d))
+            max_abs = max(max_abs, int(d.max()) if d.size else 0)
+            mask_diff += int(np.count_nonzero(sm != ref_mask[:, lo:hi]))
+            values += int(sp.size)
+        parity = {"differing": differing, "max_abs": max_abs, "mask_differing": mask_diff, "values": values,
+                  "against": f"a single-GPU composite of the same {n}-image ring on rank 0 (strips gathered over gloo), {time.perf_counter() - t0:.1f} s"}
+        # like-for-like weak-scaling baseline: ONE GPU compositing 4 images of the same ring (the per-GPU work of this run)
+        one = Compositor(cams[:per_gpu], [(w, h)] * per_gpu, "cylindrical", "multiband", 5)
+        one.upload([rigs.synth_image(h, w, i) for i in range(per_gpu)])
+        for _ in range(args.warmup):
+            one.run()
+        one.sync()
+        one_ms, _ = one.time(args.steps)
+        one.close()
+        like_for_like = {"value": per_gpu * w * h / 1e6 / (one_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": one_ms / args.steps,
+                         "workload": f"{per_gpu}x{w}x{h} cylindrical + multiband on ONE GPU: the first {per_gpu} images of the same ring "
+                                     f"(the N = 1 point of this weak-scaling family; `bench.py --gpus 1` runs BASELINE configs[1] instead)"}
+    elif sw > 0:
+        dist.pg.send(torch.from_numpy(np.ascontiguousarray(pano)), dst=0)
+        dist.pg.send(torch.from_numpy(np.ascontiguousarray(pmask)), dst=0)
+    dist.barrier()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
             "config": {
-                "workload": f"cfg3 family: {n}x{w}x{h} RGB, cylindrical warp + multiband blend, ONE panorama sharded over {world} GPUs "
-                            f"({per_gpu} images per GPU; N=8 is BASELINE configs[2])" + (f" SCALED DOWN x{SCALE_DOWN} (debug)" if SCALE_DOWN != 1 else ""),
+                "workload": sharded_workload_name(n, w, h, world),
                 "images_per_gpu": per_gpu, "pano": [comp.roi[2], comp.roi[3]], "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
                 "parallelism": f"{world} GPUs: image blocks per rank, pano column strips per rank, grouped NCCL send/recv of the "
                                f"per-band partial sums in two parts on a communication stream, overlapped with the kernels "
                                f"({slab_total / 1e6:.1f} MB per step in total)",
                 "l2": f"no flush: each rank streams its {per_gpu * src_bytes / 1e6:.0f} MB of sources every step (> 126 MB L2)",
                 "timed": "plan built once; a step = warp + pyramids + partial sums + NCCL exchange (level-0 slabs leave after the first pyrDown) + collapse of the own strip",
+                "like_for_like_n1": like_for_like,
             },
             "clocks": clocks,
             "e2e": {"value": total_mpix * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -572,7 +658,7 @@ def run_sharded(args, rank, local_rank, world):
             "gpu_launches": int(launches1 - launches0),
             "roofline": {"bound": "hbm", "kernel": None, "achieved": None, "peak": measured_peak_gbs()[0], "unit": "GB/s", "frac": None,
                          "traffic": None, "note": "per-kernel roofline is reported at N = 1", "launches_ms_rank0": {k: round(v, 4) for k, v in launches}},
-            "cpu_baseline": None,
+            "cpu_baseline": None, "parity": parity,
             "result_checksum": int(pano[::97, ::89].astype(np.uint64).sum()),
         }
         print(json.dumps(line), flush=True)
@@ -592,6 +678,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=2, help="N = 1: independent batches in flight (own stream + buffers each)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images of the ring per step of the reference arm (default: the whole configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the end-to-end measurement through the drop-in Warper / Blender classes")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one independent panorama per GPU instead of one sharded panorama")
     ap.add_argument("--extras", action="store_true", help="also fuse exposure gains and seam masks into the step (SURVEY 8f f1, f2)")
     ap.add_argument("--scale-down", type=int, default=1, help="debug: shrink the workload (not a valid measurement)")

@@ -111,6 +111,7 @@ __device__ __forceinline__ int norm16(int acc, float den, float rr)
 template <int LV>
 __global__ void __launch_bounds__(CF_BX *CF_BY, 5) k_collapse_fast(const __grid_constant__ CollapseArgs A)
 {
+    grid_dependency_sync();
     const ColDesc *__restrict__ col = A.col;
     const int n = A.n;
     const int tile_x = A.rx0 + blockIdx.x * (2 * CF_BX), tile_y = A.ry0 + blockIdx.y * (2 * CF_BY);
@@ -494,11 +495,11 @@ int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s)
     }
     dim3 block(CF_BX, CF_BY), grid(div_up(A.rw, 2 * CF_BX), div_up(A.rh, 2 * CF_BY));
     if (l == nb)
-        launch(k_collapse_fast<2>, grid, block, 0, s, A);
+        launch_pdl(k_collapse_fast<2>, grid, block, 0, s, A);
     else if (l == 0)
-        launch(k_collapse_fast<0>, grid, block, 0, s, A);
+        launch_pdl(k_collapse_fast<0>, grid, block, 0, s, A);
     else
-        launch(k_collapse_fast<1>, grid, block, 0, s, A);
+        launch_pdl(k_collapse_fast<1>, grid, block, 0, s, A);
     return launch_check("k_collapse_fast");
 }
 

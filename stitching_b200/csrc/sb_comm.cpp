@@ -105,6 +105,38 @@ int comm_exchange(int n, const int *peers, void *const *sendp, const size_t *sen
 }
 }  // namespace sb
 
+namespace sb {
+// every rank contributes `bytes_per_rank` bytes (host), all ranks receive the concatenation in rank order (host)
+int comm_allgather_bytes(const void *mine, void *all, size_t bytes_per_rank, cudaStream_t s)
+{
+    if (!g_comm) {
+        set_error("comm_allgather_bytes: sb_comm_init has not been called");
+        return SB_ERR_STATE;
+    }
+    typedef int (*fn_allgather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+    static fn_allgather p_allgather = (fn_allgather)dlsym(g_nccl, "ncclAllGather");
+    if (!p_allgather) {
+        set_error("NCCL library lacks ncclAllGather");
+        return SB_ERR_COMM;
+    }
+    void *d_in = nullptr, *d_out = nullptr;
+    SB_TRY(dev_alloc(&d_in, bytes_per_rank, s));
+    SB_TRY(dev_alloc(&d_out, bytes_per_rank * (size_t)g_world, s));
+    int rc = SB_OK;
+    if (cudaMemcpyAsync(d_in, mine, bytes_per_rank, cudaMemcpyHostToDevice, s) != cudaSuccess) rc = SB_ERR_CUDA;
+    if (rc == SB_OK) {
+        const int nrc = p_allgather(d_in, d_out, bytes_per_rank, 0 /* ncclChar */, g_comm, s);
+        if (nrc) rc = nccl_fail(nrc, "ncclAllGather");
+    }
+    if (rc == SB_OK && cudaMemcpyAsync(all, d_out, bytes_per_rank * (size_t)g_world, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = SB_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = SB_ERR_CUDA;
+    dev_free(d_in, s);
+    dev_free(d_out, s);
+    if (rc == SB_ERR_CUDA) set_error("comm_allgather_bytes: CUDA failure");
+    return rc;
+}
+}  // namespace sb
+
 extern "C" {
 
 int sb_comm_unique_id(uint8_t id[SB_COMM_ID_BYTES])

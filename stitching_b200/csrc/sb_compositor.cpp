@@ -315,6 +315,33 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
     SB_TRY(mark("warp"));
     const PanoOut &out = slot ? c->outx[slot - 1] : c->out;
     if (!c->sharded) return c->plan.run(out, s, events ? std::function<int(const std::string &)>(mark) : nullptr);
+    BlendPlan &P0 = c->plan;
+    if (c->shard.connected) {
+        // Direct exchange (sb_peer.cpp): the partial-sum kernels store their slabs into the owners' arenas over NVLink;
+        // flags written / awaited by stream memory operations order the ranks.  Everything on ONE stream.
+        const unsigned step = ++c->shard.step;
+        SB_TRY(shard_pyrdown(c, s, 0));
+        SB_TRY(mark("pyrdown_l0"));
+        SB_TRY(c->shard.wait_consumed(s, step - 1));  // the neighbours have read what the previous step wrote
+        SB_TRY(c->shard.partial_out(P0, s, 0, 0, true));
+        SB_TRY(c->shard.signal_data(s, 0, step));
+        SB_TRY(mark("partial_l0"));
+        for (int l = 1; l < P0.nb; ++l) {
+            SB_TRY(shard_pyrdown(c, s, l));
+            SB_TRY(mark("pyrdown_l" + std::to_string(l)));
+        }
+        SB_TRY(c->shard.partial_out(P0, s, 1, P0.nb, true));
+        SB_TRY(c->shard.signal_data(s, 1, step));
+        SB_TRY(mark("partial_coarse"));
+        SB_TRY(c->shard.wait_data(s, 1, step));
+        SB_TRY(c->shard.finish(P0, out, s, P0.nb, 1));
+        SB_TRY(mark("finish_coarse"));  // includes waiting for the coarse slabs of the neighbours
+        SB_TRY(c->shard.wait_data(s, 0, step));
+        SB_TRY(c->shard.finish(P0, out, s, 0, 0));
+        SB_TRY(c->shard.signal_consumed(s, step));
+        SB_TRY(mark("finish_l0"));      // includes waiting for the level-0 slabs
+        return SB_OK;
+    }
     // The exchange overlaps the kernels.  Level 0 of the partial sums -- three quarters of the bytes -- needs only the
     // first pyrDown, and the collapse reads it last: its slabs travel on the communication stream while the rest of the
     // pyramid, the coarser partial sums, their (small) exchange and the collapse of levels nb..1 run.

@@ -181,6 +181,15 @@ void sb_host_free(void *p)
 }  // extern "C"
 
 namespace sb {
+bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("SB_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 bool use_simple_kernels()
 {
     static const bool simple = [] {

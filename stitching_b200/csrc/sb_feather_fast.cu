@@ -26,6 +26,7 @@ __device__ __forceinline__ unsigned mask_at(const FeedImage &im, int x, int y)
 
 __global__ void __launch_bounds__(256) k_dt_rows_warp(const FeedImage *__restrict__ imgs)
 {
+    grid_dependency_sync();
     const FeedImage &im = imgs[blockIdx.y];
     const int y = blockIdx.x * 8 + threadIdx.y, lane = threadIdx.x, w = im.w;
     if (y >= im.h) return;  // warp-uniform

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
     const int lane = threadIdx.x;
     const int strip = blockIdx.x * WK_COLS;
     const int y_begin = (blockIdx.y * WK_WARPS + threadIdx.y) * rows_per_warp;
+    grid_dependency_sync();                    // (the descriptors above are written once, at plan time)
     if (strip >= dw || y_begin >= dh) return;  // warp-uniform
     const int y_end = min(y_begin + rows_per_warp, dh);
     const int x = strip + lane - 1;            // -1 .. dw: virtual columns at both ends

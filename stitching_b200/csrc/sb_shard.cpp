@@ -131,9 +131,14 @@ int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
 {
     release(s);
     const int n = (int)plan.imgs.size();
+    SB_TRY(connect(plan, s));  // direct exchange over NVLink when the ranks can map each other's memory (sb_peer.cpp)
     for (int p = 0; p < world; ++p) {
         if (send[p].bytes) SB_TRY(dev_alloc(&send[p].buf, send[p].bytes, s));
-        if (recv[p].bytes) SB_TRY(dev_alloc(&recv[p].buf, recv[p].bytes, s));
+        if (!recv[p].bytes) continue;
+        if (connected)
+            recv[p].buf = (char *)arena + recv_off[p];
+        else
+            SB_TRY(dev_alloc(&recv[p].buf, recv[p].bytes, s));
     }
     // item lists per level: slabs of lower ranks, own images, slabs of higher ranks (= feed order)
     std::vector<ColDesc> items;
@@ -179,15 +184,27 @@ void ShardPlan::release(cudaStream_t s)
         p.buf = nullptr;
     }
     for (auto &p : recv) {
-        dev_free(p.buf, s);
+        if (!connected) dev_free(p.buf, s);
         p.buf = nullptr;
+    }
+    if (connected) {
+        (void)cudaStreamSynchronize(s);
+#ifndef SB_EMU
+        for (auto &p : peer_arena)
+            if (p) (void)cudaIpcCloseMemHandle(p);
+        (void)cudaFree(arena);
+#endif
+        peer_arena.clear();
+        arena = nullptr;
+        connected = false;
     }
     dev_free(items_arena_, s);
     items_arena_ = nullptr;
 }
 
-int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo, int l_hi)
+int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo, int l_hi, bool direct)
 {
+    direct = direct && connected;
     const int n = (int)plan.imgs.size();
     for (int p = 0; p < world; ++p) {
         if (p == rank || !send[p].bytes) continue;
@@ -203,8 +220,10 @@ int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo, int 
             A.rw = L.w;
             A.rh = L.h;
             A.partial = 1;
-            A.slab_acc = (int16_t *)((char *)send[p].buf + L.acc_off);
-            A.slab_w = (float *)((char *)send[p].buf + L.w_off);
+            // direct: the slab is stored straight into its place in the owner's arena (peer stores over NVLink)
+            char *dst = direct ? peer_arena[p] + peer_slot[p] : (char *)send[p].buf;
+            A.slab_acc = (int16_t *)(dst + L.acc_off);
+            A.slab_w = (float *)(dst + L.w_off);
             A.slab_pitch = L.pitch;
             A.slab_plane = L.plane;
             SB_TRY(launch_collapse_fast(A, l, plan.nb, s));

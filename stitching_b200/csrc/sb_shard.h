@@ -27,6 +27,18 @@ public:
     std::vector<PeerSlab> send, recv;  // indexed by peer rank
     ColDesc *items_dev[SB_MAX_BANDS + 1] = {};
     int n_items[SB_MAX_BANDS + 1] = {};
+    // Direct exchange over NVLink (sb_peer.cpp): every rank's receive slabs live in ONE cudaMalloc'ed arena that its
+    // neighbours map with CUDA IPC; the partial-sum kernels then store their slabs straight into the owner's arena
+    // (peer stores, no copy, no NCCL call on the data path) and the ranks order themselves with flags written and
+    // awaited by stream memory operations.  peer_arena[p] == nullptr: not connected (the NCCL exchange is used).
+    void *arena = nullptr;                 // recv slabs of all peers (rank order) + the flags
+    size_t arena_bytes = 0, flags_off = 0;
+    std::vector<size_t> recv_off;          // slab from peer p inside MY arena
+    std::vector<char *> peer_arena;        // peer p's arena mapped into this process
+    std::vector<size_t> peer_slot;         // offset of MY slab inside peer p's arena
+    std::vector<size_t> peer_flags_off;    // offset of peer p's flags inside its arena
+    bool connected = false;
+    unsigned step = 0;                     // composites issued so far (flag values)
 
     static void block_of(int n_images, int world, int r, int *first, int *count)
     {
@@ -43,7 +55,14 @@ public:
     // phase 0: partial sums of the own images over every region a neighbour needs -> send slabs
     // (levels l_lo .. l_hi only: level 0 needs just the first pyrDown, so its slabs -- three quarters of the bytes --
     // can leave while the rest of the pyramid is still being built)
-    int partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo = 0, int l_hi = SB_MAX_BANDS);
+    int partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo = 0, int l_hi = SB_MAX_BANDS, bool direct = false);
+    // direct exchange: layout of rank `dst`'s arena (same on every rank), IPC connection, flags
+    size_t arena_layout(const BlendPlan &plan, int dst, std::vector<size_t> *off, size_t *flags) const;
+    int connect(const BlendPlan &plan, cudaStream_t s);            // collective over the NCCL communicator
+    int signal_data(cudaStream_t s, int part, unsigned value);     // part 0: level-0 slabs written, 1: the coarser levels
+    int wait_data(cudaStream_t s, int part, unsigned value);
+    int signal_consumed(cudaStream_t s, unsigned value);           // this rank has read the slabs of step `value`
+    int wait_consumed(cudaStream_t s, unsigned value);             // ... before the next ones overwrite them
     // the NCCL exchange of the slabs (grouped send/recv on stream s); part 0: the level-0 part of every slab,
     // part 1: the coarser levels, part -1: everything
     int exchange(cudaStream_t s, int part = -1);
@@ -57,6 +76,9 @@ private:
     void *items_arena_ = nullptr;
 };
 
+int comm_allgather_bytes(const void *mine, void *all, size_t bytes_per_rank, cudaStream_t s);  // host buffers
+int comm_rank();
+int comm_world();
 int comm_exchange(int n, const int *peers, void *const *sendp, const size_t *sendb, void *const *recvp, const size_t *recvb,
                   cudaStream_t s);
 bool comm_ready();

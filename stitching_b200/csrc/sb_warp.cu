@@ -281,6 +281,7 @@ __device__ SB_NOINLINE unsigned sample_general(const uint8_t *__restrict__ src, 
 template <bool HAS_BM, bool DP2A>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_constant__ WarpBatch B)
 {
+    grid_dependency_sync();
     const WarpJob &j = B.j[blockIdx.z];
     const int u = 2 * (blockIdx.x * WARP_BX + threadIdx.x);
     const int v = blockIdx.y * WARP_BY + threadIdx.y;
@@ -392,9 +393,9 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
             if (rgbm_only) {
                 dim3 grid2(div_up(max_w, 2 * WARP_BX), div_up(max_h, WARP_BY), cnt);
                 if (has_bm)
-                    launch(k_warp_rgbm<true, true>, grid2, block, 0, s, B);
+                    launch_pdl(k_warp_rgbm<true, true>, grid2, block, 0, s, B);
                 else
-                    launch(k_warp_rgbm<false, true>, grid2, block, 0, s, B);
+                    launch_pdl(k_warp_rgbm<false, true>, grid2, block, 0, s, B);
             } else {
                 launch(k_warp_wide, grid, block, 0, s, B);
             }

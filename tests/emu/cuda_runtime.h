@@ -143,6 +143,7 @@ static inline unsigned __ballot_sync(unsigned, int pred)
     emu_warp->barrier();
     return m;
 }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
