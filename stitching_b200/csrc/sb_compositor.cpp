@@ -315,24 +315,47 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
     SB_TRY(mark("warp"));
     const PanoOut &out = slot ? c->outx[slot - 1] : c->out;
     if (!c->sharded) return c->plan.run(out, s, events ? std::function<int(const std::string &)>(mark) : nullptr);
+    if (!c->comm_stream) {
+        SB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            SB_CUDA(cudaEventCreateWithFlags(&c->e_part[k], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&c->e_xchg[k], cudaEventDisableTiming));
+        }
+    }
     BlendPlan &P0 = c->plan;
     if (c->shard.connected) {
-        // Direct exchange (sb_peer.cpp): the partial-sum kernels store their slabs into the owners' arenas over NVLink;
-        // flags written / awaited by stream memory operations order the ranks.  Everything on ONE stream.
+        // Exchange over mapped peer memory (sb_peer.cpp): the slabs go from the local send buffers into the owners' arenas
+        // with copy-engine copies on the communication stream, beside the pyramid kernels; flags written / awaited by
+        // stream memory operations order the ranks (no host round trip, no NCCL call in the step).
         const unsigned step = ++c->shard.step;
+        const bool direct = c->shard.direct_stores;
+        cudaStream_t cs = direct ? s : c->comm_stream;
         SB_TRY(shard_pyrdown(c, s, 0));
         SB_TRY(mark("pyrdown_l0"));
-        SB_TRY(c->shard.wait_consumed(s, step - 1));  // the neighbours have read what the previous step wrote
-        SB_TRY(c->shard.partial_out(P0, s, 0, 0, true));
-        SB_TRY(c->shard.signal_data(s, 0, step));
+        if (step > 1 && !direct) SB_CUDA(cudaStreamWaitEvent(s, c->e_xchg[1], 0));  // the previous step's copies have left the send buffers
+        if (direct) SB_TRY(c->shard.wait_consumed(s, step - 1));
+        SB_TRY(c->shard.partial_out(P0, s, 0, 0, direct));
         SB_TRY(mark("partial_l0"));
+        if (!direct) {
+            SB_CUDA(cudaEventRecord(c->e_part[0], s));
+            SB_CUDA(cudaStreamWaitEvent(cs, c->e_part[0], 0));
+            SB_TRY(c->shard.wait_consumed(cs, step - 1));  // the neighbours have read what the previous step delivered
+            SB_TRY(c->shard.push(cs, 0));
+        }
+        SB_TRY(c->shard.signal_data(cs, 0, step));
         for (int l = 1; l < P0.nb; ++l) {
             SB_TRY(shard_pyrdown(c, s, l));
             SB_TRY(mark("pyrdown_l" + std::to_string(l)));
         }
-        SB_TRY(c->shard.partial_out(P0, s, 1, P0.nb, true));
-        SB_TRY(c->shard.signal_data(s, 1, step));
+        SB_TRY(c->shard.partial_out(P0, s, 1, P0.nb, direct));
         SB_TRY(mark("partial_coarse"));
+        if (!direct) {
+            SB_CUDA(cudaEventRecord(c->e_part[1], s));
+            SB_CUDA(cudaStreamWaitEvent(cs, c->e_part[1], 0));
+            SB_TRY(c->shard.push(cs, 1));
+        }
+        SB_TRY(c->shard.signal_data(cs, 1, step));
+        if (!direct) SB_CUDA(cudaEventRecord(c->e_xchg[1], cs));
         SB_TRY(c->shard.wait_data(s, 1, step));
         SB_TRY(c->shard.finish(P0, out, s, P0.nb, 1));
         SB_TRY(mark("finish_coarse"));  // includes waiting for the coarse slabs of the neighbours
@@ -345,13 +368,6 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
     // The exchange overlaps the kernels.  Level 0 of the partial sums -- three quarters of the bytes -- needs only the
     // first pyrDown, and the collapse reads it last: its slabs travel on the communication stream while the rest of the
     // pyramid, the coarser partial sums, their (small) exchange and the collapse of levels nb..1 run.
-    if (!c->comm_stream) {
-        SB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
-            SB_CUDA(cudaEventCreateWithFlags(&c->e_part[k], cudaEventDisableTiming));
-            SB_CUDA(cudaEventCreateWithFlags(&c->e_xchg[k], cudaEventDisableTiming));
-        }
-    }
     BlendPlan &P = c->plan;
     SB_TRY(shard_pyrdown(c, s, 0));
     SB_TRY(mark("pyrdown_l0"));

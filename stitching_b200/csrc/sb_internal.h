@@ -219,6 +219,7 @@ int launch_tail(const FeedImage *imgs_dev, const PanoLevel *pano_dev, int first,
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
+int launch_wait_flags(const unsigned *flags, unsigned mask, unsigned value, cudaStream_t s);  // lanes with a mask bit wait for flags[lane] >= value
 // ExposureErrorCompensator.apply: taps of the float32 bilinear resize of a gain map (sb_geometry.cpp), the 256-entry
 // table of a scalar gain, and the host-buffer entry's kernel (sb_warp.cu)
 void resize_f32_taps(int n_src, int n_dst, int *i0i1, float *fr);  // i0i1: 2 * n_dst ints

@@ -4,9 +4,13 @@
 // Round 1 moved the slabs with grouped ncclSend / ncclRecv on a communication stream: at 8 GPUs the exchange ran at
 // ~127 GB/s per rank and the collapse waited for it.  Here every rank keeps the slabs it RECEIVES
 // in one cudaMalloc'ed arena, exports it with CUDA IPC, and maps its neighbours' arenas.  The partial-sum launches
-// (k_collapse_fast with `partial` set) then write their slabs straight into the owner's arena -- peer stores over
-// NVLink / NVSwitch issued by the kernel that computes the values, overlapped with the rest of that kernel -- and the
-// ranks order themselves with four flags per pair, written and awaited by stream memory operations
+// (k_collapse_fast with `partial` set) write their slabs into local send buffers and the copy engines move them into
+// the owners' arenas (cudaMemcpyAsync on the mapped peer pointers: NVLink DMA at link rate, no SM, no NCCL kernel, on
+// a second stream beside the pyramid kernels).  Storing the slabs from the kernels straight into the peers' arenas is
+// available too (SB_PEER=direct) -- measured on 2 B200s it LOSES: the 2- and 4-byte scattered stores of that kernel
+// cross NVLink as small partial writes, partial_l0 0.025 -> 0.179 ms, step 0.97 -> 1.21 ms
+// (profiles/bench_r02_e_2gpu_direct_stores.json).  The ranks order themselves with four flags per pair, written and
+// awaited by stream memory operations
 // (cuStreamWriteValue32 / cuStreamWaitValue32: stream-ordered, no host round trip, no spinning kernel):
 //   data[part][p]  in the RECEIVER's arena: rank p has finished writing part `part` (0: level 0, 1: the coarser
 //                  levels) of step `value`;
@@ -63,6 +67,7 @@ int ShardPlan::connect(const BlendPlan &plan, cudaStream_t s)
 {
     connected = false;
     const char *e = getenv("SB_PEER");
+    direct_stores = e && !strcmp(e, "direct");
     if ((e && e[0] == '0') || !comm_ready() || comm_world() != world || comm_rank() != rank) return SB_OK;  // NCCL exchange
     if (!load_memops()) return SB_OK;
     // my arena: the slabs I receive (they replace the per-peer receive buffers) + the flags
@@ -124,6 +129,17 @@ static int memop(MemOpFn fn, cudaStream_t s, void *addr, unsigned value, unsigne
     return SB_OK;
 }
 
+int ShardPlan::push(cudaStream_t s, int part)
+{
+    for (int p = 0; p < world; ++p) {
+        if (p == rank || !send[p].bytes || !peer_arena[p]) continue;
+        const size_t s0 = part == 1 ? send[p].split : 0, s1 = part == 0 ? send[p].split : send[p].bytes;  // level 0 lies in front
+        if (s1 <= s0) continue;
+        SB_CUDA(cudaMemcpyAsync(peer_arena[p] + peer_slot[p] + s0, (const char *)send[p].buf + s0, s1 - s0, cudaMemcpyDeviceToDevice, s));
+    }
+    return SB_OK;
+}
+
 int ShardPlan::signal_data(cudaStream_t s, int part, unsigned value)
 {
     for (int p = 0; p < world; ++p) {
@@ -135,12 +151,15 @@ int ShardPlan::signal_data(cudaStream_t s, int part, unsigned value)
 }
 int ShardPlan::wait_data(cudaStream_t s, int part, unsigned value)
 {
-    unsigned *flags = (unsigned *)((char *)arena + flags_off);
-    for (int p = 0; p < world; ++p) {
-        if (p == rank || !recv[p].bytes) continue;
-        SB_TRY(memop(p_wait, s, flags + (size_t)part * world + p, value, CU_STREAM_WAIT_VALUE_GEQ, "cuStreamWaitValue32"));
+    if (world > 32) {
+        set_error("sharded composite: the flag wait serves at most 32 ranks");
+        return SB_ERR_INVALID;
     }
-    return SB_OK;
+    unsigned *flags = (unsigned *)((char *)arena + flags_off) + (size_t)part * world;
+    unsigned mask = 0;
+    for (int p = 0; p < world; ++p)
+        if (p != rank && recv[p].bytes) mask |= 1u << p;
+    return launch_wait_flags(flags, mask, value, s);  // a polling warp (sb_util.cu), not cuStreamWaitValue32
 }
 int ShardPlan::signal_consumed(cudaStream_t s, unsigned value)
 {
@@ -153,15 +172,15 @@ int ShardPlan::signal_consumed(cudaStream_t s, unsigned value)
 }
 int ShardPlan::wait_consumed(cudaStream_t s, unsigned value)
 {
-    unsigned *flags = (unsigned *)((char *)arena + flags_off);
-    for (int p = 0; p < world; ++p) {
-        if (p == rank || !send[p].bytes) continue;
-        SB_TRY(memop(p_wait, s, flags + (size_t)2 * world + p, value, CU_STREAM_WAIT_VALUE_GEQ, "cuStreamWaitValue32"));
-    }
-    return SB_OK;
+    unsigned *flags = (unsigned *)((char *)arena + flags_off) + (size_t)2 * world;
+    unsigned mask = 0;
+    for (int p = 0; p < world; ++p)
+        if (p != rank && send[p].bytes) mask |= 1u << p;
+    return launch_wait_flags(flags, mask, value, s);
 }
 #else
 int ShardPlan::connect(const BlendPlan &, cudaStream_t) { return SB_OK; }
+int ShardPlan::push(cudaStream_t, int) { return SB_ERR_STATE; }
 int ShardPlan::signal_data(cudaStream_t, int, unsigned) { return SB_ERR_STATE; }
 int ShardPlan::wait_data(cudaStream_t, int, unsigned) { return SB_ERR_STATE; }
 int ShardPlan::signal_consumed(cudaStream_t, unsigned) { return SB_ERR_STATE; }

@@ -59,6 +59,8 @@ public:
     // direct exchange: layout of rank `dst`'s arena (same on every rank), IPC connection, flags
     size_t arena_layout(const BlendPlan &plan, int dst, std::vector<size_t> *off, size_t *flags) const;
     int connect(const BlendPlan &plan, cudaStream_t s);            // collective over the NCCL communicator
+    int push(cudaStream_t s, int part);                            // copy-engine copies of the send slabs into the owners' arenas
+    bool direct_stores = false;                                    // SB_PEER=direct: the kernels store into the peers' arenas themselves
     int signal_data(cudaStream_t s, int part, unsigned value);     // part 0: level-0 slabs written, 1: the coarser levels
     int wait_data(cudaStream_t s, int part, unsigned value);
     int signal_consumed(cudaStream_t s, unsigned value);           // this rank has read the slabs of step `value`

@@ -55,6 +55,32 @@ int launch_selftest_division(unsigned long long n, unsigned long long seed, int 
     return launch_check("k_selftest_division");
 }
 
+#ifndef SB_EMU
+// One warp polls up to 32 flags in this device's memory until each has reached `value` (flags only ever grow).  The
+// sharded composite orders its ranks with this instead of cuStreamWaitValue32: an unsatisfied stream wait sends the
+// channel back to the runlist and is re-examined a timeslice later -- measured on 2 B200s that turned a 0.92 ms step
+// into 1.86 ms once steps were enqueued ahead (profiles/bench_r02_e_2gpu_streamwait.json); a polling warp sees the
+// peer's write within a microsecond.
+__global__ void k_wait_flags(const volatile unsigned *flags, unsigned mask, unsigned value)
+{
+    if ((mask >> threadIdx.x) & 1u) {
+        while ((int)(flags[threadIdx.x] - value) < 0) __nanosleep(100);
+    }
+    __threadfence_system();  // the slabs written before the flag are visible to what follows in the stream
+}
+#endif
+
+int launch_wait_flags(const unsigned *flags, unsigned mask, unsigned value, cudaStream_t s)
+{
+#ifndef SB_EMU
+    if (!mask) return SB_OK;
+    launch(k_wait_flags, dim3(1), dim3(32), 0, s, (const volatile unsigned *)flags, mask, value);
+    return launch_check("k_wait_flags");
+#else
+    return SB_ERR_STATE;
+#endif
+}
+
 // overwrite a buffer larger than L2 so that the next kernel starts from a cold cache
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s)
 {
