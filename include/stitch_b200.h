@@ -93,6 +93,22 @@ SB_API int sb_warp(int warp_type, float scale, const float K[9], const float R[9
                    int src_h, size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask,
                    size_t mask_pitch, int out_rect[4]);
 
+/* Device-resident twins (SURVEY.md 8b "device-handle variants"): stitcher.py hands every warped FINAL-resolution image
+ * from Warper.warp_image (:185-189) through cropping (cropper.py:150-151, slicing) and ExposureErrorCompensator.apply
+ * (:219-221) to Blender.feed (:254).  sb_warp_keep is sb_warp that additionally keeps what it computed in device memory
+ * and hands out a handle; the *_dev entries below take a rectangle of such a handle instead of a host buffer, so the
+ * image crosses PCIe once in each direction instead of three times.  A handle is dense uint8, h x w x channels. */
+typedef struct sb_devimg sb_devimg;
+SB_API int sb_warp_keep(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w,
+                        int src_h, size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask,
+                        size_t mask_pitch, int out_rect[4], sb_devimg **keep_img, sb_devimg **keep_mask);
+SB_API void sb_devimg_release(sb_devimg *d);
+SB_API int sb_devimg_info(const sb_devimg *d, int *w, int *h, int *channels);
+/* sb_gain_apply on the rectangle (x, y, w, h) of a 3-channel handle: the device copy is updated in place and the result
+ * is also written to `host` (the reference's apply modifies its argument in place and returns it) */
+SB_API int sb_gain_apply_dev(sb_devimg *img, int x, int y, int w, int h, uint8_t *host, size_t host_pitch, const float *gain_map,
+                             int gw, int gh, int gc, const double *gain_scalar);
+
 /* ---------------------------------------------------------------------------------------------
  * Blender  (stitching/blender.py)
  * ------------------------------------------------------------------------------------------- */
@@ -111,6 +127,10 @@ SB_API int sb_blender_num_bands(const sb_blender *b);
  * feeds in call order (results are identical to eager accumulation). */
 SB_API int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_pitch, const uint8_t *mask,
                            size_t mask_pitch, int w, int h, int tl_x, int tl_y);
+/* the same feed with the uint8 image taken from the rectangle (ix, iy, w, h) of a device twin and the mask either from the
+ * rectangle (mx, my, w, h) of a 1-channel twin (mask_dev != NULL) or from the host (mask_host) */
+SB_API int sb_blender_feed_dev(sb_blender *b, const sb_devimg *img, int ix, int iy, const sb_devimg *mask_dev, int mx, int my,
+                               const uint8_t *mask_host, size_t mask_pitch, int w, int h, int tl_x, int tl_y);
 /* blender.py:43-48 Blender.blend(): ::blend + cv.convertScaleAbs.  dst is uint8 HxWx3 of the prepared
  * roi size, dst_mask uint8 HxW; dst_s16 (nullable) additionally receives the int16 result before
  * convertScaleAbs (pitch in bytes).  The blender returns to the un-prepared state. */

@@ -47,6 +47,14 @@ SIGNATURES = [
     ("sb_warp_roi", C.c_int, [C.c_int, C.c_float, c_float_p, c_float_p, C.c_int, C.c_int, c_int_p]),
     ("sb_warp", C.c_int, [C.c_int, C.c_float, c_float_p, c_float_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                           C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, c_int_p]),
+    ("sb_warp_keep", C.c_int, [C.c_int, C.c_float, c_float_p, c_float_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, c_int_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("sb_devimg_release", None, [C.c_void_p]),
+    ("sb_devimg_info", C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),
+    ("sb_gain_apply_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p]),
+    ("sb_blender_feed_dev", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                      C.c_int, C.c_int, C.c_int, C.c_int]),
     ("sb_blender_create", C.c_void_p, [C.c_int, C.c_int, C.c_float]),
     ("sb_blender_destroy", None, [C.c_void_p]),
     ("sb_blender_prepare", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, device_array
 from .stitching_error import StitchingError
 
 
@@ -33,6 +33,8 @@ class _NativeBlender:
         return _lib.lib().sb_blender_num_bands(self._h)
 
     def feed(self, img, mask, corner):
+        if self._feed_twin(img, mask, corner):
+            return
         img = np.asarray(img)
         if img.ndim != 3 or img.shape[2] != 3:
             raise StitchingError("Blender.feed takes an HxWx3 image")
@@ -53,6 +55,30 @@ class _NativeBlender:
             ),
             "sb_blender_feed",
         )
+
+    def _feed_twin(self, img, mask, corner):
+        """Blender.feed without the upload when `img` still has its device twin (a warped image, possibly cropped and
+        exposure-compensated by the drop-ins); the mask comes from its twin too, or from the host."""
+        tw = device_array.twin(img)
+        if tw is None or img.ndim != 3:
+            return False
+        ptr, ix, iy, w, h = tw
+        if hasattr(mask, "get") and not isinstance(mask, np.ndarray):
+            mask = mask.get()  # cv.UMat (seam_finder.py:38-43 hands those out)
+        mtw = device_array.twin(mask) if getattr(mask, "ndim", 0) == 2 else None
+        if mtw is not None and (mtw[3], mtw[4]) == (w, h):
+            mptr, mx, my, mhost, mpitch = mtw[0], mtw[1], mtw[2], None, 0
+        else:
+            mask = np.asarray(mask)
+            if mask.dtype != np.uint8 or mask.shape != (h, w):
+                raise StitchingError("Blender.feed takes a uint8 mask of the image's size")
+            mask = np.ascontiguousarray(mask)
+            mptr, mx, my, mhost, mpitch = None, 0, 0, mask.ctypes.data_as(C.c_void_p), mask.strides[0]
+        _lib.check(
+            _lib.lib().sb_blender_feed_dev(self._h, ptr, ix, iy, mptr, mx, my, mhost, mpitch, w, h, int(corner[0]), int(corner[1])),
+            "sb_blender_feed_dev",
+        )
+        return True
 
     def blend(self, want_s16=False):
         if self.roi is None:

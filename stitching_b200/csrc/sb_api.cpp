@@ -62,6 +62,11 @@ int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, f
 }
 }  // namespace sb
 
+struct sb_devimg {
+    uint8_t *p;
+    int w, h, ch;
+};
+
 extern "C" {
 
 int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h, int out_rect[4])
@@ -76,9 +81,12 @@ int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], 
     return SB_OK;
 }
 
-int sb_warp(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w, int src_h,
-            size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int out_rect[4])
+static int warp_impl(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w, int src_h,
+                     size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int out_rect[4],
+                     sb_devimg **keep_img, sb_devimg **keep_mask)
 {
+    if (keep_img) *keep_img = nullptr;
+    if (keep_mask) *keep_mask = nullptr;
     if (!valid_warp_type(warp_type) || !K || !R || !out_rect || src_w <= 0 || src_h <= 0 || (dst_img && !src) ||
         (src && src_pitch < (size_t)src_w * 3)) {
         set_error("sb_warp: invalid argument");
@@ -108,9 +116,13 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
     std::vector<float> host_tab;
     WarpJob job;
     SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));
+    const bool keep_i = dst_img && keep_img, keep_m = dst_mask && keep_mask;
     if (dst_img) {
         SB_TRY(tmp.get(&d_src, (size_t)src_w * 3 * src_h + SB_SRC_PAD));
-        SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
+        if (keep_i)
+            SB_TRY(dev_alloc((void **)&d_img, (size_t)w * 3 * h, s));  // survives the call inside the handle
+        else
+            SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
         SB_CUDA(cudaMemcpy2DAsync(d_src, (size_t)src_w * 3, src, src_pitch, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, s));
         job.src = d_src;
         job.spitch = (long long)src_w * 3;
@@ -118,14 +130,58 @@ int sb_warp(int warp_type, float scale, const float K[9], const float R[9], cons
         job.dst_pitch = (long long)w * 3;
     }
     if (dst_mask) {
-        SB_TRY(tmp.get(&d_mask, (size_t)w * h));
+        if (keep_m)
+            SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
+        else
+            SB_TRY(tmp.get(&d_mask, (size_t)w * h));
         job.dst_mask = d_mask;
         job.mask_pitch = w;
     }
-    SB_TRY(launch_warp(&job, 1, s));
-    if (dst_img) SB_CUDA(cudaMemcpy2DAsync(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));
-    if (dst_mask) SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s));
-    SB_CUDA(cudaStreamSynchronize(s));
+    int rc = launch_warp(&job, 1, s);
+    if (rc == SB_OK && dst_img && cudaMemcpy2DAsync(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "cudaMemcpy2DAsync", __FILE__, __LINE__);
+    if (rc == SB_OK && dst_mask && cudaMemcpy2DAsync(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "cudaMemcpy2DAsync", __FILE__, __LINE__);
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (rc != SB_OK) {
+        if (keep_i) dev_free(d_img, s);
+        if (keep_m) dev_free(d_mask, s);
+        return rc;
+    }
+    if (keep_i) *keep_img = new sb_devimg{d_img, w, h, 3};
+    if (keep_m) *keep_mask = new sb_devimg{d_mask, w, h, 1};
+    return SB_OK;
+}
+
+int sb_warp(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w, int src_h,
+            size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int out_rect[4])
+{
+    return warp_impl(warp_type, scale, K, R, src, src_w, src_h, src_pitch, dst_img, dst_pitch, dst_mask, mask_pitch, out_rect, nullptr, nullptr);
+}
+
+int sb_warp_keep(int warp_type, float scale, const float K[9], const float R[9], const uint8_t *src, int src_w, int src_h,
+                 size_t src_pitch, uint8_t *dst_img, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int out_rect[4],
+                 sb_devimg **keep_img, sb_devimg **keep_mask)
+{
+    return warp_impl(warp_type, scale, K, R, src, src_w, src_h, src_pitch, dst_img, dst_pitch, dst_mask, mask_pitch, out_rect, keep_img, keep_mask);
+}
+
+void sb_devimg_release(sb_devimg *d)
+{
+    if (!d) return;
+    dev_free(d->p, default_stream());
+    delete d;
+}
+
+int sb_devimg_info(const sb_devimg *d, int *w, int *h, int *channels)
+{
+    if (!d) {
+        set_error("sb_devimg_info: null handle");
+        return SB_ERR_INVALID;
+    }
+    if (w) *w = d->w;
+    if (h) *h = d->h;
+    if (channels) *channels = d->ch;
     return SB_OK;
 }
 
@@ -246,6 +302,32 @@ int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_ma
     return rc;
 }
 
+int sb_gain_apply_dev(sb_devimg *img, int x, int y, int w, int h, uint8_t *host, size_t host_pitch, const float *gain_map, int gw, int gh,
+                      int gc, const double *gain_scalar)
+{
+    if (!img || img->ch != 3 || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > img->w || y + h > img->h || (host && host_pitch < (size_t)w * 3) ||
+        !valid_gain_args(gain_map, gw, gh, gc, gain_scalar)) {
+        set_error("sb_gain_apply_dev: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    if (!gain_map && !gain_scalar) return SB_OK;  // compensator "no": identity (host and device copies stay as they are)
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    uint8_t *view = img->p + ((size_t)y * img->w + x) * 3;
+    const long long pitch = (long long)img->w * 3;
+    WarpJob job;
+    std::memset(&job, 0, sizeof job);
+    GainData gd;
+    int rc = gain_upload(&job, &gd, w, h, gain_map, gw, gh, gc, gain_scalar, s);
+    if (rc == SB_OK) rc = launch_gain_apply(view, pitch, w, h, job, s);
+    if (rc == SB_OK && host && cudaMemcpy2DAsync(host, host_pitch, view, (size_t)pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        rc = SB_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = SB_ERR_CUDA;
+    gain_free(&gd, s);
+    if (rc == SB_ERR_CUDA) set_error("sb_gain_apply_dev: CUDA failure");
+    return rc;
+}
+
 int sb_resize_exact(const uint8_t *src, size_t src_pitch, int sw, int sh, int channels, uint8_t *dst, size_t dst_pitch, int dw, int dh)
 {
     if (!src || !dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || (channels != 1 && channels != 3) ||
@@ -353,6 +435,72 @@ int sb_blender_prepare(sb_blender *b, int x, int y, int w, int h)
 
 int sb_blender_num_bands(const sb_blender *b) { return b ? b->plan.nb : -1; }
 
+// one recorded feed: geometry first (host only, so that an out-of-roi feed fails before any device work), then the level-0
+// data on the device.  The image comes from the host (img) or from a device rectangle (dimg, dimg_pitch); likewise the mask.
+static int blender_feed_impl(sb_blender *b, const void *img, int img_is_s16, size_t img_pitch, const uint8_t *dimg, size_t dimg_pitch,
+                             const uint8_t *mask, size_t mask_pitch, const uint8_t *dmask, size_t dmask_pitch, int w, int h, int tl_x, int tl_y)
+{
+    FeedDesc f;
+    std::memset(&f, 0, sizeof f);
+    f.w = w; f.h = h; f.tlx = tl_x; f.tly = tl_y;
+    SB_TRY(b->plan.add_feed(f));
+    FeedImage &im = b->plan.imgs.back();
+    const size_t px_bytes = img_is_s16 ? 6 : 3;
+    auto upload = [&]() -> int {
+        SB_TRY(ensure_device());
+        cudaStream_t s = default_stream();
+        const uint8_t *m_ptr = dmask;
+        size_t m_pitch = dmask_pitch;
+        if (!dmask) {
+            uint8_t *d_mask = nullptr;
+            SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
+            b->level0.push_back(d_mask);
+            SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
+            m_ptr = d_mask;
+            m_pitch = (size_t)w;
+        }
+        const uint8_t *i_ptr = dimg;
+        size_t i_pitch = dimg_pitch;
+        if (!dimg) {
+            void *d_img = nullptr;
+            SB_TRY(dev_alloc(&d_img, (size_t)w * h * px_bytes, s));
+            b->level0.push_back(d_img);
+            SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * px_bytes, img, img_pitch, (size_t)w * px_bytes, h, cudaMemcpyHostToDevice, s));
+            i_ptr = (const uint8_t *)d_img;
+            i_pitch = (size_t)w * px_bytes;
+        }
+        if (img_is_s16) {
+            if (dmask) {  // the generic layout keeps a pointer to the mask: it has to outlive this call
+                uint8_t *d_mask = nullptr;
+                SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
+                b->level0.push_back(d_mask);
+                SB_CUDA(cudaMemcpy2DAsync(d_mask, w, dmask, dmask_pitch, w, h, cudaMemcpyDeviceToDevice, s));
+                m_ptr = d_mask;
+                m_pitch = (size_t)w;
+            }
+            im.s16 = (const int16_t *)i_ptr;
+            im.s16_pitch = (long long)w * 3;
+            im.mask = m_ptr;
+            im.mask_pitch = (long long)m_pitch;
+        } else {
+            uint32_t *d_rgbm = nullptr;
+            const int rp = (w + 3) & ~3;  // 16-byte rows: the tile kernels stage windows of this buffer with 16-byte copies
+            SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)rp * h * 4, s));
+            b->level0.push_back(d_rgbm);
+            if (rp != w) SB_CUDA(cudaMemsetAsync(d_rgbm, 0, (size_t)rp * h * 4, s));  // zero row padding = weight 0
+            SB_TRY(launch_pack_rgbm(i_ptr, (long long)i_pitch, m_ptr, (long long)m_pitch, d_rgbm, rp, w, h, s));
+            im.rgbm = d_rgbm;
+            im.rgbm_pitch = rp;
+        }
+        // the caller's buffers (and device twins) may change as soon as we return
+        SB_CUDA(cudaStreamSynchronize(s));
+        return SB_OK;
+    };
+    const int rc = upload();
+    if (rc != SB_OK) b->plan.imgs.pop_back();
+    return rc;
+}
+
 int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_pitch, const uint8_t *mask, size_t mask_pitch,
                     int w, int h, int tl_x, int tl_y)
 {
@@ -369,45 +517,26 @@ int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_t img_p
         set_error("sb_blender_feed: pitch smaller than a row");
         return SB_ERR_INVALID;
     }
-    FeedDesc f;
-    std::memset(&f, 0, sizeof f);
-    f.w = w; f.h = h; f.tlx = tl_x; f.tly = tl_y;
-    // geometry first (host only) so that an out-of-roi feed fails before any device work
-    SB_TRY(b->plan.add_feed(f));
-    FeedImage &im = b->plan.imgs.back();
-    auto upload = [&]() -> int {
-        SB_TRY(ensure_device());
-        cudaStream_t s = default_stream();
-        uint8_t *d_mask = nullptr;
-        void *d_img = nullptr;
-        SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
-        b->level0.push_back(d_mask);
-        SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
-        SB_TRY(dev_alloc(&d_img, (size_t)w * h * px_bytes, s));
-        b->level0.push_back(d_img);
-        SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * px_bytes, img, img_pitch, (size_t)w * px_bytes, h, cudaMemcpyHostToDevice, s));
-        if (img_is_s16) {
-            im.s16 = (const int16_t *)d_img;
-            im.s16_pitch = (long long)w * 3;
-            im.mask = d_mask;
-            im.mask_pitch = w;
-        } else {
-            uint32_t *d_rgbm = nullptr;
-            const int rp = (w + 3) & ~3;  // 16-byte rows: the copy engine (TMA) stages windows of this buffer
-            SB_TRY(dev_alloc((void **)&d_rgbm, (size_t)rp * h * 4, s));
-            b->level0.push_back(d_rgbm);
-            if (rp != w) SB_CUDA(cudaMemsetAsync(d_rgbm, 0, (size_t)rp * h * 4, s));  // zero row padding = weight 0
-            SB_TRY(launch_pack_rgbm((const uint8_t *)d_img, (long long)w * 3, d_mask, w, d_rgbm, rp, w, h, s));
-            im.rgbm = d_rgbm;
-            im.rgbm_pitch = rp;
-        }
-        // the caller's buffers may be reused as soon as we return
-        SB_CUDA(cudaStreamSynchronize(s));
-        return SB_OK;
-    };
-    const int rc = upload();
-    if (rc != SB_OK) b->plan.imgs.pop_back();
-    return rc;
+    return blender_feed_impl(b, img, img_is_s16, img_pitch, nullptr, 0, mask, mask_pitch, nullptr, 0, w, h, tl_x, tl_y);
+}
+
+int sb_blender_feed_dev(sb_blender *b, const sb_devimg *img, int ix, int iy, const sb_devimg *mask_dev, int mx, int my,
+                        const uint8_t *mask_host, size_t mask_pitch, int w, int h, int tl_x, int tl_y)
+{
+    if (!b || !img || img->ch != 3 || w <= 0 || h <= 0 || ix < 0 || iy < 0 || ix + w > img->w || iy + h > img->h ||
+        (!mask_dev && (!mask_host || mask_pitch < (size_t)w)) ||
+        (mask_dev && (mask_dev->ch != 1 || mx < 0 || my < 0 || mx + w > mask_dev->w || my + h > mask_dev->h))) {
+        set_error("sb_blender_feed_dev: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    if (!b->prepared) {
+        set_error("sb_blender_feed_dev: prepare() has not been called");
+        return SB_ERR_STATE;
+    }
+    const uint8_t *dimg = img->p + ((size_t)iy * img->w + ix) * 3;
+    const uint8_t *dmask = mask_dev ? mask_dev->p + (size_t)my * mask_dev->w + mx : nullptr;
+    return blender_feed_impl(b, nullptr, 0, 0, dimg, (size_t)img->w * 3, mask_host, mask_pitch, dmask, mask_dev ? (size_t)mask_dev->w : 0, w, h, tl_x,
+                             tl_y);
 }
 
 int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch, int16_t *dst_s16,
@@ -447,12 +576,13 @@ int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst
     }
     int rc = b->plan.allocate(s);
     if (rc == SB_OK) rc = b->plan.run(out, s);
-    if (rc == SB_OK) {
-        if (dst) SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, out.rgb, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s));
-        if (dst_mask) SB_CUDA(cudaMemcpy2DAsync(dst_mask, mask_pitch, out.mask, w, w, h, cudaMemcpyDeviceToHost, s));
-        if (dst_s16) SB_CUDA(cudaMemcpy2DAsync(dst_s16, s16_pitch, out.s16, (size_t)w * 6, (size_t)w * 6, h, cudaMemcpyDeviceToHost, s));
-        cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (rc == SB_OK) {  // (errors fall through to the clean-up below: the feeds are dropped either way)
+        cudaError_t e = cudaSuccess;
+        if (dst) e = cudaMemcpy2DAsync(dst, dst_pitch, out.rgb, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && dst_mask) e = cudaMemcpy2DAsync(dst_mask, mask_pitch, out.mask, w, w, h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && dst_s16) e = cudaMemcpy2DAsync(dst_s16, s16_pitch, out.s16, (size_t)w * 6, (size_t)w * 6, h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "sb_blender_blend: copy of the result", __FILE__, __LINE__);
     }
     // like OpenCV, blend() consumes the state: a new prepare() is needed before the next feed
     blender_drop_feeds(b);

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, device_array
 from .stitching_error import StitchingError
 
 
@@ -38,6 +38,24 @@ def apply_gain(img, gain):
     """What cv.detail ...Compensator.apply does to `img` (uint8 HxWx3) given its gain; in place when `img` is a
     C-contiguous-row uint8 array (as the reference modifies its argument), returns the image."""
     gmap, gw, gh, gc, gscalar = gain_arguments(gain)
+    tw = device_array.twin(img)
+    if tw is not None and img.ndim == 3:
+        # the warped image still has its device twin: compensate there, refresh the host copy (the reference modifies
+        # its argument in place and returns it -- so do we, for both copies; nobody else can write to this array)
+        ptr, x, y, w, h = tw
+        img.flags.writeable = True
+        try:
+            _lib.check(
+                _lib.lib().sb_gain_apply_dev(
+                    ptr, x, y, w, h, img.ctypes.data_as(C.c_void_p), img.strides[0],
+                    gmap.ctypes.data_as(C.c_void_p) if gmap is not None else None, gw, gh, gc,
+                    gscalar.ctypes.data_as(C.c_void_p) if gscalar is not None else None,
+                ),
+                "sb_gain_apply_dev",
+            )
+        finally:
+            img.flags.writeable = False
+        return img
     arr = np.asarray(img)
     if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[2] != 3:
         raise StitchingError("ExposureErrorCompensator.apply takes a uint8 HxWx3 image")

@@ -10,7 +10,7 @@ from statistics import median
 
 import numpy as np
 
-from . import _lib
+from . import _lib, device_array
 from .stitching_error import StitchingError
 
 
@@ -116,14 +116,22 @@ class Warper:
         w, h = rect[2], rect[3]
         out = np.empty((h, w, 3), np.uint8) if want_image else None
         msk = np.empty((h, w), np.uint8) if want_mask else None
+        # the arrays are filled as always; the device copy of the IMAGE stays alive behind it (device_array.DeviceBacked)
+        # so that cropping (slicing), ExposureErrorCompensator.apply and Blender.feed can go on without another upload.
+        # Masks stay plain writable ndarrays: the reference hands them to cv2 calls that write into them
+        # (seam_finder.py:35, the seam finders' find() modifies `masks` in place).
+        keep_i = C.c_void_p()
         _lib.check(
-            L.sb_warp(
+            L.sb_warp_keep(
                 wtype, scale, _fp(K), _fp(R), src_p, int(size[0]), int(size[1]), pitch,
                 out.ctypes.data_as(C.c_void_p) if want_image else None, w * 3,
                 msk.ctypes.data_as(C.c_void_p) if want_mask else None, w, rect,
+                C.byref(keep_i) if want_image else None, None,
             ),
-            "sb_warp",
+            "sb_warp_keep",
         )
+        if want_image:
+            out = device_array.wrap(out, keep_i.value)
         return out, msk
 
 

@@ -300,3 +300,54 @@ def test_exposure_gain_drop_in_and_fused(use_emu, oracle):
     replay.assert_exact(got[0], ref[0], "pano with fused exposure gains")
     replay.assert_exact(got[1], ref[1], "mask with fused exposure gains")
     assert not np.array_equal(got[0], pano0), "removing a gain must change the panorama back"
+
+
+def _twin_chain(oracle):
+    """warp -> crop (slicing, cropper.py:150-151) -> ExposureErrorCompensator.apply -> Blender.feed / blend with the warped
+    images' device twins, against the same chain on plain host copies of the same arrays."""
+    from stitching_b200 import Blender, Warper, device_array, exposure_error_compensator, rigs
+
+    cfg = rigs.config("cfg2", 20)
+    cams = cfg["cameras"][:3]
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 5 + i) for i in range(3)]
+    sizes = [(cfg["w"], cfg["h"])] * 3
+    warper = Warper("spherical")
+    warper.set_scale(cams)
+    warped = list(warper.warp_images(imgs, cams))
+    masks = list(warper.create_and_warp_masks(sizes, cams))
+    corners, wsizes = warper.warp_rois(sizes, cams)
+    assert all(isinstance(w, device_array.DeviceBacked) and device_array.twin(w) is not None and not w.flags.writeable for w in warped)
+    assert all(type(m) is np.ndarray and m.flags.writeable for m in masks), "masks stay plain ndarrays (cv2 writes into them)"
+    # what leaves the twin: copies and conversions; what keeps it: plain 2-D slices
+    assert device_array.twin(warped[0].astype(np.int16)) is None and device_array.twin(warped[0].copy()) is None
+    assert device_array.twin(warped[0][::2]) is None and device_array.twin(warped[0] + 1) is None
+    crop = (slice(3, -5), slice(7, -2))
+    cropped = [w[crop] for w in warped]
+    cmasks = [m[crop] for m in masks]
+    ccorners = [(c[0] + 7, c[1] + 3) for c in corners]
+    csizes = [(w.shape[1], w.shape[0]) for w in cropped]
+    for w in cropped:
+        tw = device_array.twin(w)
+        assert tw is not None and tw[1:] == (7, 3, w.shape[1], w.shape[0])
+    rng = np.random.default_rng(3)
+    gains = [rng.uniform(0.8, 1.2, (4, 5)).astype(np.float32), np.float64(1.07), None]
+    plain = [np.array(w) for w in cropped]  # host copies without twins: the reference path of the same drop-ins
+    for w, p, g in zip(cropped, plain, gains):
+        out = exposure_error_compensator.apply_gain(w, g)
+        assert out is w and device_array.twin(out) is not None, "apply modifies its argument in place and returns it"
+        exposure_error_compensator.apply_gain(p, g)
+        assert np.array_equal(np.asarray(w), p)
+    res = []
+    for feed_imgs in (cropped, plain):
+        b = Blender("multiband", 5)
+        b.prepare(ccorners, csizes)
+        for im, m, c in zip(feed_imgs, cmasks, ccorners):
+            b.feed(im, m, c)
+        res.append(b.blend())
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][1].any()
+    return res[0]
+
+
+def test_device_twins_through_warp_crop_compensate_feed(use_emu, oracle):
+    _twin_chain(oracle)

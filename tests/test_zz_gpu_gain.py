@@ -49,3 +49,11 @@ def test_fused_gain_in_the_compositor(cuda_lib, oracle):
     replay.assert_exact(got[0], ref[0], "pano with fused exposure gains")
     replay.assert_exact(got[1], ref[1], "mask with fused exposure gains")
     assert not np.array_equal(got[0], pano0)
+
+
+def test_device_twins_through_warp_crop_compensate_feed_on_gpu(cuda_lib, oracle):
+    """The warped images' device twins (sb_warp_keep / sb_gain_apply_dev / sb_blender_feed_dev) against the host-buffer
+    entries on the same arrays: identical panorama and mask."""
+    import test_host_logic
+
+    test_host_logic._twin_chain(oracle)
