@@ -37,7 +37,17 @@ typedef enum {
 } sb_status;
 
 /* warper.py:10-27 WARP_TYPE_CHOICES; the four projections on the hot path */
-typedef enum { SB_WARP_SPHERICAL = 0, SB_WARP_CYLINDRICAL = 1, SB_WARP_PLANE = 2, SB_WARP_AFFINE = 3 } sb_warp_type;
+/* warper.py:10-27 WARP_TYPE_CHOICES.  0-3: the projection runs on the device from separable trig tables (mercator, 14,
+ * too); 4-15: mapBackward is not separable and has to match glibc's sinf / atan2f / tanf ... bit for bit, so the float
+ * maps are built by the library's host code (libm, all cores) and the device does the resampling (sb_geometry.cpp). */
+typedef enum {
+    SB_WARP_SPHERICAL = 0, SB_WARP_CYLINDRICAL = 1, SB_WARP_PLANE = 2, SB_WARP_AFFINE = 3,
+    SB_WARP_FISHEYE = 4, SB_WARP_STEREOGRAPHIC = 5,
+    SB_WARP_COMPRESSED_PLANE_A2_B1 = 6, SB_WARP_COMPRESSED_PLANE_A1_5_B1 = 7,
+    SB_WARP_COMPRESSED_PLANE_PORTRAIT_A2_B1 = 8, SB_WARP_COMPRESSED_PLANE_PORTRAIT_A1_5_B1 = 9,
+    SB_WARP_PANINI_A2_B1 = 10, SB_WARP_PANINI_A1_5_B1 = 11, SB_WARP_PANINI_PORTRAIT_A2_B1 = 12, SB_WARP_PANINI_PORTRAIT_A1_5_B1 = 13,
+    SB_WARP_MERCATOR = 14, SB_WARP_TRANSVERSE_MERCATOR = 15
+} sb_warp_type;
 /* blender.py:8-12 BLENDER_CHOICES */
 typedef enum { SB_BLEND_NO = 0, SB_BLEND_FEATHER = 1, SB_BLEND_MULTIBAND = 2 } sb_blend_kind;
 

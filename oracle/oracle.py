@@ -16,7 +16,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libstitch_oracle.so")
 
-TYPES = {"spherical": 0, "cylindrical": 1, "plane": 2, "affine": 3}
+TYPES = {"spherical": 0, "cylindrical": 1, "plane": 2, "affine": 3, "fisheye": 4, "stereographic": 5,
+         "compressedPlaneA2B1": 6, "compressedPlaneA1.5B1": 7, "compressedPlanePortraitA2B1": 8, "compressedPlanePortraitA1.5B1": 9,
+         "paniniA2B1": 10, "paniniA1.5B1": 11, "paniniPortraitA2B1": 12, "paniniPortraitA1.5B1": 13, "mercator": 14,
+         "transverseMercator": 15}  # warper.py:10-27
 
 
 def build(force=False):

@@ -27,14 +27,19 @@
 
 #define SO_API __attribute__((visibility("default")))
 
-enum { SO_SPHERICAL = 0, SO_CYLINDRICAL = 1, SO_PLANE = 2, SO_AFFINE = 3 };
+enum { SO_SPHERICAL = 0, SO_CYLINDRICAL = 1, SO_PLANE = 2, SO_AFFINE = 3,
+       /* the other twelve names of warper.py:10-27, in that file's order; the A2B1 / A1.5B1 variants differ in `a` only */
+       SO_FISHEYE = 4, SO_STEREOGRAPHIC = 5, SO_CPLANE_A2 = 6, SO_CPLANE_A15 = 7, SO_CPLANE_PORTRAIT_A2 = 8, SO_CPLANE_PORTRAIT_A15 = 9,
+       SO_PANINI_A2 = 10, SO_PANINI_A15 = 11, SO_PANINI_PORTRAIT_A2 = 12, SO_PANINI_PORTRAIT_A15 = 13, SO_MERCATOR = 14,
+       SO_TRANSVERSE_MERCATOR = 15 };
 
 /* ------------------------------------------------------------------------------------------
  * A.1  projector set-up  (OpenCV ProjectorBase::setCameraParams; reached from warper.py:44-51)
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     float k[9], rinv[9], r_kinv[9], k_rinv[9], t[3], scale;
-    int type; /* SO_SPHERICAL / SO_CYLINDRICAL / SO_PLANE (affine is folded into plane) */
+    float a, b; /* compressedPlane* / panini*: PyRotationWarper builds them with A = 2 or 1.5, B = 1 */
+    int type; /* SO_SPHERICAL / SO_CYLINDRICAL / SO_PLANE (affine is folded into plane) / SO_FISHEYE ... (variants folded onto the A2 name) */
 } so_proj;
 
 /* plain fp32 3x3 product, each multiply and add separately rounded, left to right
@@ -88,6 +93,12 @@ static void proj_setup(so_proj *p, int type, float scale, const float *K, const 
         }
         type = SO_PLANE;
     }
+    p->a = p->b = 1.f;
+    if (type == SO_CPLANE_A2 || type == SO_CPLANE_PORTRAIT_A2 || type == SO_PANINI_A2 || type == SO_PANINI_PORTRAIT_A2) p->a = 2.f;
+    if (type == SO_CPLANE_A15 || type == SO_CPLANE_PORTRAIT_A15 || type == SO_PANINI_A15 || type == SO_PANINI_PORTRAIT_A15) {
+        p->a = 1.5f;
+        type -= 1; /* same projector class as the A2 variant */
+    }
     p->type = type;
     p->scale = scale;
     memcpy(p->k, K, sizeof p->k);
@@ -107,7 +118,47 @@ static void map_forward(const so_proj *p, float x, float y, float *u, float *v)
     float x_ = r[0] * x + r[1] * y + r[2];
     float y_ = r[3] * x + r[4] * y + r[5];
     float z_ = r[6] * x + r[7] * y + r[8];
-    if (p->type == SO_SPHERICAL) {
+    if (p->type >= SO_FISHEYE) {
+        /* cv::detail::{Fisheye, Stereographic, CompressedRectilinear[Portrait], Panini[Portrait], Mercator,
+         * TransverseMercator}Projector::mapForward (OpenCV warpers_inl.hpp, recalled; pinned bit for bit against
+         * cv.PyRotationWarper.warpPoint / warpRoi / buildMaps for all twelve names, tests/golden/gen_golden.py).
+         * The portrait projectors name the first row of r_kinv y_ and the second x_. */
+        const float sc = p->scale, a = p->a, b = p->b;
+        float xx = x_, yy = y_;
+        if (p->type == SO_CPLANE_PORTRAIT_A2 || p->type == SO_PANINI_PORTRAIT_A2) { xx = y_; yy = x_; }
+        const float u_ = atan2f(xx, z_);
+        const float len = sqrtf(xx * xx + yy * yy + z_ * z_);
+        if (p->type == SO_FISHEYE) {
+            const float v_ = PI_F - acosf(yy / len);
+            *u = sc * v_ * cosf(u_);
+            *v = sc * v_ * sinf(u_);
+        } else if (p->type == SO_STEREOGRAPHIC) {
+            const float v_ = PI_F - acosf(yy / len);
+            const float rr = sinf(v_) / (1 - cosf(v_));
+            *u = sc * rr * cosf(u_);
+            *v = sc * rr * sinf(u_);
+        } else {
+            const float v_ = asinf(yy / len);
+            if (p->type == SO_CPLANE_A2 || p->type == SO_CPLANE_PORTRAIT_A2) {
+                const float t = sc * a * tanf(u_ / a);
+                *u = p->type == SO_CPLANE_A2 ? t : -sc * a * tanf(u_ / a);
+                *v = sc * b * tanf(v_) / cosf(u_);
+            } else if (p->type == SO_PANINI_A2 || p->type == SO_PANINI_PORTRAIT_A2) {
+                const float tg = a * tanf(u_ / a);
+                const float sinu = sinf(u_);
+                *u = p->type == SO_PANINI_A2 ? sc * tg : -sc * tg;
+                if (fabs(sinu) < 1E-7) *v = sc * b * tanf(v_);
+                else *v = sc * b * tg * tanf(v_) / sinu;
+            } else if (p->type == SO_MERCATOR) {
+                *u = sc * u_;
+                *v = sc * logf(tanf((float)(3.14159265358979323846 / 4) + v_ / 2));
+            } else { /* transverse Mercator */
+                const float B = cosf(v_) * sinf(u_);
+                *u = sc / 2 * logf((1 + B) / (1 - B));
+                *v = sc * atan2f(tanf(v_), cosf(u_));
+            }
+        }
+    } else if (p->type == SO_SPHERICAL) {
         *u = p->scale * atan2f(x_, z_);
         float w = y_ / sqrtf(x_ * x_ + y_ * y_ + z_ * z_);
         *v = p->scale * (PI_F - acosf(w == w ? w : 0.f));
@@ -126,7 +177,51 @@ static void map_backward(const so_proj *p, float u, float v, float *x, float *y)
 {
     const float *k = p->k_rinv;
     float x_, y_, z_, z;
-    if (p->type == SO_SPHERICAL) {
+    if (p->type >= SO_FISHEYE) {
+        /* ...Projector::mapBackward of the same classes */
+        const float sc = p->scale, a = p->a, b = p->b;
+        const int portrait = p->type == SO_CPLANE_PORTRAIT_A2 || p->type == SO_PANINI_PORTRAIT_A2;
+        float lon, lat_sin, lat_cos; /* x_ = lat_cos sin(lon), y_ = lat_sin, z_ = lat_cos cos(lon) (axes swapped for portrait) */
+        if (p->type == SO_FISHEYE || p->type == SO_STEREOGRAPHIC) {
+            u /= sc;
+            v /= sc;
+            const float u_ = atan2f(v, u);
+            const float rr = sqrtf(u * u + v * v);
+            const float v_ = p->type == SO_FISHEYE ? rr : 2 * atanf(1.f / rr);
+            lon = u_;
+            lat_cos = sinf(PI_F - v_);
+            lat_sin = cosf(PI_F - v_);
+        } else if (p->type == SO_MERCATOR) {
+            u /= sc;
+            v /= sc;
+            const float v_ = atanf(sinhf(v));
+            lon = u;
+            lat_cos = cosf(v_);
+            lat_sin = sinf(v_);
+        } else if (p->type == SO_TRANSVERSE_MERCATOR) {
+            u /= sc;
+            v /= sc;
+            const float v_ = asinf(sinf(v) / coshf(u));
+            lon = atan2f(sinhf(u), cosf(v));
+            lat_cos = cosf(v_);
+            lat_sin = sinf(v_);
+        } else {
+            u /= portrait ? -sc : sc;
+            v /= sc;
+            const float l = a * atanf(u / a);
+            float v_;
+            if (p->type == SO_CPLANE_A2 || p->type == SO_CPLANE_PORTRAIT_A2) v_ = atanf(v * cosf(l) / b);
+            else if (fabs(l) > 1E-7) v_ = atanf(v * sinf(l) / (b * a * tanf(l / a)));
+            else v_ = atanf(v / b);
+            lon = l;
+            lat_cos = cosf(v_);
+            lat_sin = sinf(v_);
+        }
+        x_ = lat_cos * sinf(lon);
+        y_ = lat_sin;
+        z_ = lat_cos * cosf(lon);
+        if (portrait) { float tmp = x_; x_ = y_; y_ = tmp; }
+    } else if (p->type == SO_SPHERICAL) {
         u /= p->scale;
         v /= p->scale;
         float sinv = sinf(PI_F - v);
@@ -171,7 +266,11 @@ static void detect_roi(const so_proj *p, int W, int H, int *tlx, int *tly, int *
 {
     float tl_u = 3.402823466e+38f, tl_v = 3.402823466e+38f;
     float br_u = -3.402823466e+38f, br_v = -3.402823466e+38f, u, v;
-    if (p->type == SO_PLANE) {
+    if (p->type >= SO_FISHEYE) {
+        /* RotationWarperBase::detectResultRoi (the default): every source pixel */
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) { map_forward(p, (float)x, (float)y, &u, &v); UPD(u, v); }
+    } else if (p->type == SO_PLANE) {
         map_forward(p, 0.f, 0.f, &u, &v); UPD(u, v);
         map_forward(p, 0.f, (float)(H - 1), &u, &v); UPD(u, v);
         map_forward(p, (float)(W - 1), 0.f, &u, &v); UPD(u, v);

@@ -13,7 +13,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstitch_b200.so")
 
 SB_OK = 0
-WARP_TYPES = {"spherical": 0, "cylindrical": 1, "plane": 2, "affine": 3}
+WARP_TYPES = {  # warper.py:10-27 -> sb_warp_type
+    "spherical": 0, "cylindrical": 1, "plane": 2, "affine": 3, "fisheye": 4, "stereographic": 5,
+    "compressedPlaneA2B1": 6, "compressedPlaneA1.5B1": 7, "compressedPlanePortraitA2B1": 8, "compressedPlanePortraitA1.5B1": 9,
+    "paniniA2B1": 10, "paniniA1.5B1": 11, "paniniPortraitA2B1": 12, "paniniPortraitA1.5B1": 13,
+    "mercator": 14, "transverseMercator": 15,
+}
 BLEND_KINDS = {"no": 0, "feather": 1, "multiband": 2}
 
 c_float_p = C.POINTER(C.c_float)

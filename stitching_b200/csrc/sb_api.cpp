@@ -10,7 +10,7 @@ using namespace sb;
 
 namespace {
 
-bool valid_warp_type(int t) { return t >= SB_WARP_SPHERICAL && t <= SB_WARP_AFFINE; }
+bool valid_warp_type(int t) { return t >= SB_WARP_SPHERICAL && t <= SB_WARP_TRANSVERSE_MERCATOR; }
 
 // temp device buffers freed in stream order when the scope ends
 struct Scratch {
@@ -43,7 +43,7 @@ int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, f
     const int wp = (w + 3) & ~3;
     host_tab.assign(warp_table_floats(w, h), 0.f);
     float *colX = host_tab.data(), *colZ = colX + wp, *rowA = colZ + wp, *rowY = rowA + h;
-    projector_tables(p, rect, colX, colZ, rowA, rowY);
+    if (!projector_needs_maps(p)) projector_tables(p, rect, colX, colZ, rowA, rowY);  // (else: warp_maps_upload)
     SB_CUDA(cudaMemcpyAsync(tab_dev, host_tab.data(), host_tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     std::memset(job, 0, sizeof *job);
     job->sw = src_w;
@@ -56,8 +56,22 @@ int make_warp_job(const Projector &p, const int rect[4], int src_w, int src_h, f
     job->rowY = tab_dev + 2 * wp + h;
     std::memcpy(job->k, p.k_rinv, sizeof job->k);
     job->always_divide = p.type == SB_WARP_PLANE;
+    job->xmap = job->ymap = nullptr;
     job->xin_hi = 32.f * (float)(src_w - 1) - 0.5f;
     job->yin_hi = 32.f * (float)(src_h - 1) - 0.5f;
+    return SB_OK;
+}
+// projections that are not separable: the float maps of buildMaps, built on the host (libm, all cores) and uploaded;
+// `maps_dev` holds xmap then ymap (w * h floats each)
+int warp_maps_upload(const Projector &p, const int rect[4], float *maps_dev, WarpJob *job, cudaStream_t s)
+{
+    const size_t n = (size_t)rect[2] * rect[3];
+    std::vector<float> host(2 * n);
+    projector_maps(p, rect, host.data(), host.data() + n);
+    SB_CUDA(cudaMemcpyAsync(maps_dev, host.data(), 2 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));  // `host` is a local
+    job->xmap = maps_dev;
+    job->ymap = maps_dev + n;
     return SB_OK;
 }
 }  // namespace sb
@@ -116,6 +130,11 @@ static int warp_impl(int warp_type, float scale, const float K[9], const float R
     std::vector<float> host_tab;
     WarpJob job;
     SB_TRY(make_warp_job(p, rect, src_w, src_h, tab, &job, s, host_tab));
+    if (projector_needs_maps(p)) {
+        float *maps = nullptr;
+        SB_TRY(tmp.get(&maps, (size_t)2 * w * h));
+        SB_TRY(warp_maps_upload(p, rect, maps, &job, s));
+    }
     const bool keep_i = dst_img && keep_img, keep_m = dst_mask && keep_mask;
     if (dst_img) {
         SB_TRY(tmp.get(&d_src, (size_t)src_w * 3 * src_h + SB_SRC_PAD));

@@ -43,6 +43,7 @@ struct sb_compositor {
     std::vector<uint8_t *> src_dev;    // u8x3 sources
     std::vector<uint32_t *> rgbm_dev;  // warped, packed; row pitch = width rounded up to 32 pixels (128-byte rows)
     std::vector<float *> tab_dev;
+    std::vector<float *> maps_dev;     // projections that are not separable: xmap | ymap of every image (built at plan time)
     std::vector<uint8_t *> usermask_dev;
     std::vector<GainData> gain;        // exposure gains per image (sb_compositor_set_gain)
     int max_w = 0, max_h = 0;
@@ -83,6 +84,7 @@ static void compositor_free(sb_compositor *c)
     for (auto p : c->src_dev) dev_free(p, s);
     for (auto p : c->rgbm_dev) dev_free(p, s);
     for (auto p : c->tab_dev) dev_free(p, s);
+    for (auto p : c->maps_dev) dev_free(p, s);
     for (auto p : c->usermask_dev) dev_free(p, s);
     for (auto &g : c->gain) gain_free(&g, s);
     dev_free(c->out.rgb, s);
@@ -154,6 +156,7 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
     c->src_dev.assign(n, nullptr);
     c->rgbm_dev.assign(n, nullptr);
     c->tab_dev.assign(n, nullptr);
+    c->maps_dev.assign(n, nullptr);
     c->usermask_dev.assign(n, nullptr);
     c->gain.assign(n, GainData{});
     std::vector<int> corners(2 * n), sizes(2 * n);
@@ -182,6 +185,10 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         SB_TRY(dev_alloc((void **)&c->tab_dev[i], warp_table_floats(rect[2], rect[3]) * sizeof(float), s));
         SB_TRY(make_warp_job(p, rect, c->src_w[i], c->src_h[i], c->tab_dev[i], &c->jobs[i], s, host_tab));
         SB_CUDA(cudaStreamSynchronize(s));  // host_tab is reused by the next image
+        if (projector_needs_maps(p)) {
+            SB_TRY(dev_alloc((void **)&c->maps_dev[i], (size_t)2 * rect[2] * rect[3] * sizeof(float), s));
+            SB_TRY(warp_maps_upload(p, rect, c->maps_dev[i], &c->jobs[i], s));
+        }
         c->jobs[i].src = c->src_dev[i];
         c->jobs[i].spitch = (long long)c->src_w[i] * 3;
         c->jobs[i].dst_rgbm = c->rgbm_dev[i];
@@ -431,7 +438,7 @@ extern "C" {
 sb_compositor *sb_compositor_create(const sb_rig *rig)
 {
     if (!rig || rig->n_images <= 0 || rig->n_images > SB_MAX_IMAGES || !rig->src_w || !rig->src_h || !rig->K || !rig->R ||
-        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_AFFINE || rig->blend_kind < SB_BLEND_NO ||
+        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_TRANSVERSE_MERCATOR || rig->blend_kind < SB_BLEND_NO ||
         rig->blend_kind > SB_BLEND_MULTIBAND) {
         set_error("sb_compositor_create: invalid rig");
         return nullptr;
@@ -449,7 +456,7 @@ sb_compositor *sb_compositor_create(const sb_rig *rig)
 sb_compositor *sb_compositor_create_sharded(const sb_rig *rig, int rank, int world)
 {
     if (!rig || rig->n_images <= 0 || rig->n_images > SB_MAX_IMAGES || !rig->src_w || !rig->src_h || !rig->K || !rig->R ||
-        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_AFFINE || world < 1 || rank < 0 || rank >= world) {
+        rig->warp_type < SB_WARP_SPHERICAL || rig->warp_type > SB_WARP_TRANSVERSE_MERCATOR || world < 1 || rank < 0 || rank >= world) {
         set_error("sb_compositor_create_sharded: invalid argument");
         return nullptr;
     }

@@ -14,6 +14,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
+#include <vector>
 
 #include "sb_internal.h"
 
@@ -72,13 +74,71 @@ Mat3 inverse(const Mat3 &A)
 
 const float kPiF = (float)3.14159265358979323846;
 
-// forward projection of one source pixel (PyRotationWarper::warpPoint)
+// classes of the twelve projections beyond spherical / cylindrical / plane (the A2B1 / A1.5B1 variants share a class)
+enum { C_FISHEYE = 100, C_STEREO, C_CPLANE, C_CPLANE_PORTRAIT, C_PANINI, C_PANINI_PORTRAIT, C_MERCATOR, C_TMERCATOR };
+
+// forward projection of one source pixel (PyRotationWarper::warpPoint).  The formulas of the extra classes restate
+// cv::detail::{Fisheye,Stereographic,CompressedRectilinear[Portrait],Panini[Portrait],Mercator,TransverseMercator}Projector
+// ::mapForward; every operation is fp32 and rounded on its own, the libm calls are glibc's (as in the reference's
+// wheel): pinned bit for bit against cv.PyRotationWarper.warpPoint / buildMaps (oracle/stitch_oracle.c, goldens).
 inline void forward(const Projector &p, float x, float y, float &u, float &v)
 {
     const float *m = p.r_kinv;
     float X = m[0] * x + m[1] * y + m[2];
     float Y = m[3] * x + m[4] * y + m[5];
     float Z = m[6] * x + m[7] * y + m[8];
+    if (p.type >= C_FISHEYE) {
+        if (p.type == C_CPLANE_PORTRAIT || p.type == C_PANINI_PORTRAIT) std::swap(X, Y);  // the portrait classes swap the axes
+        const float u_ = atan2f(X, Z), s = p.scale, a = p.a, b = p.b;
+        switch (p.type) {
+            case C_FISHEYE: {
+                const float v_ = kPiF - acosf(Y / sqrtf(X * X + Y * Y + Z * Z));
+                u = s * v_ * cosf(u_);
+                v = s * v_ * sinf(u_);
+                return;
+            }
+            case C_STEREO: {
+                const float v_ = kPiF - acosf(Y / sqrtf(X * X + Y * Y + Z * Z));
+                const float r = sinf(v_) / (1 - cosf(v_));
+                u = s * r * cosf(u_);
+                v = s * r * sinf(u_);
+                return;
+            }
+            default: break;
+        }
+        const float v_ = asinf(Y / sqrtf(X * X + Y * Y + Z * Z));
+        switch (p.type) {
+            case C_CPLANE:
+                u = s * a * tanf(u_ / a);
+                v = s * b * tanf(v_) / cosf(u_);
+                return;
+            case C_CPLANE_PORTRAIT:
+                u = -s * a * tanf(u_ / a);
+                v = s * b * tanf(v_) / cosf(u_);
+                return;
+            case C_PANINI:
+            case C_PANINI_PORTRAIT: {
+                const float tg = a * tanf(u_ / a);
+                u = p.type == C_PANINI ? s * tg : -s * tg;
+                const float sinu = sinf(u_);
+                if (fabs(sinu) < 1E-7)
+                    v = s * b * tanf(v_);
+                else
+                    v = s * b * tg * tanf(v_) / sinu;
+                return;
+            }
+            case C_MERCATOR:
+                u = s * u_;
+                v = s * logf(tanf((float)(3.14159265358979323846 / 4) + v_ / 2));
+                return;
+            default: {  // C_TMERCATOR
+                const float B = cosf(v_) * sinf(u_);
+                u = s / 2 * logf((1 + B) / (1 - B));
+                v = s * atan2f(tanf(v_), cosf(u_));
+                return;
+            }
+        }
+    }
     switch (p.type) {
         case SB_WARP_SPHERICAL: {
             u = p.scale * atan2f(X, Z);
@@ -101,6 +161,96 @@ inline void forward(const Projector &p, float x, float y, float &u, float &v)
     }
 }
 
+// ...Projector::mapBackward of the extra classes: (u, v) of the result -> source pixel
+inline void backward(const Projector &p, float u, float v, float &x, float &y)
+{
+    const float s = p.scale, a = p.a, b = p.b;
+    float X, Y, Z;
+    switch (p.type) {
+        case C_FISHEYE:
+        case C_STEREO: {
+            u /= s;
+            v /= s;
+            const float u_ = atan2f(v, u), r = sqrtf(u * u + v * v);
+            const float v_ = p.type == C_FISHEYE ? r : 2 * atanf(1.f / r);
+            const float sinv = sinf(kPiF - v_);
+            X = sinv * sinf(u_);
+            Y = cosf(kPiF - v_);
+            Z = sinv * cosf(u_);
+            break;
+        }
+        case C_CPLANE:
+        case C_CPLANE_PORTRAIT: {
+            u /= p.type == C_CPLANE ? s : -s;
+            v /= s;
+            const float aatg = a * atanf(u / a);
+            const float v_ = atanf(v * cosf(aatg) / b), cosv = cosf(v_);
+            X = cosv * sinf(aatg);
+            Y = sinf(v_);
+            Z = cosv * cosf(aatg);
+            break;
+        }
+        case C_PANINI:
+        case C_PANINI_PORTRAIT: {
+            u /= p.type == C_PANINI ? s : -s;
+            v /= s;
+            const float lamda = a * atanf(u / a);
+            float v_;
+            if (fabs(lamda) > 1E-7)
+                v_ = atanf(v * sinf(lamda) / (b * a * tanf(lamda / a)));
+            else
+                v_ = atanf(v / b);
+            const float cosv = cosf(v_);
+            X = cosv * sinf(lamda);
+            Y = sinf(v_);
+            Z = cosv * cosf(lamda);
+            break;
+        }
+        case C_MERCATOR: {
+            u /= s;
+            v /= s;
+            const float v_ = atanf(sinhf(v)), cosv = cosf(v_);
+            X = cosv * sinf(u);
+            Y = sinf(v_);
+            Z = cosv * cosf(u);
+            break;
+        }
+        default: {  // C_TMERCATOR
+            u /= s;
+            v /= s;
+            const float v_ = asinf(sinf(v) / coshf(u)), u_ = atan2f(sinhf(u), cosf(v)), cosv = cosf(v_);
+            X = cosv * sinf(u_);
+            Y = sinf(v_);
+            Z = cosv * cosf(u_);
+        }
+    }
+    if (p.type == C_CPLANE_PORTRAIT || p.type == C_PANINI_PORTRAIT) std::swap(X, Y);
+    const float *k = p.k_rinv;
+    x = k[0] * X + k[1] * Y + k[2] * Z;
+    y = k[3] * X + k[4] * Y + k[5] * Z;
+    const float z = k[6] * X + k[7] * Y + k[8] * Z;
+    if (z > 0) {
+        x /= z;
+        y /= z;
+    } else {
+        x = y = -1;
+    }
+}
+
+// rows [0, n) dealt to the host's cores in contiguous blocks
+template <typename F>
+void parallel_rows(int n, F &&body)
+{
+    const int nt = std::max(1, std::min<int>((int)std::thread::hardware_concurrency(), std::min(n / 8 + 1, 64)));
+    if (nt == 1) {
+        body(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([&, t]() { body((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt), t); });
+    for (auto &t : th) t.join();
+}
+
 }  // namespace
 
 void projector_setup(Projector &p, int warp_type, float scale, const float *K, const float *R)
@@ -110,6 +260,14 @@ void projector_setup(Projector &p, int warp_type, float scale, const float *K, c
     std::memcpy(Rm.m, R, sizeof Rm.m);
     float T[3] = {0.f, 0.f, 0.f};
     p.type = warp_type;
+    p.a = p.b = 1.f;
+    if (warp_type >= SB_WARP_FISHEYE) {
+        static const int cls[12] = {C_FISHEYE, C_STEREO, C_CPLANE, C_CPLANE, C_CPLANE_PORTRAIT, C_CPLANE_PORTRAIT,
+                                    C_PANINI, C_PANINI, C_PANINI_PORTRAIT, C_PANINI_PORTRAIT, C_MERCATOR, C_TMERCATOR};
+        static const float as[12] = {1.f, 1.f, 2.f, 1.5f, 2.f, 1.5f, 2.f, 1.5f, 2.f, 1.5f, 1.f, 1.f};
+        p.type = cls[warp_type - SB_WARP_FISHEYE];
+        p.a = as[warp_type - SB_WARP_FISHEYE];  // cv::PyRotationWarper: A = 2 / 1.5, B = 1
+    }
     if (warp_type == SB_WARP_AFFINE) {
         // AffineStitcher (stitcher.py:267-287): "R" is a homogeneous 2-D affine H.  Split it into a
         // rotation-like part and a translation the plane projector understands:
@@ -147,7 +305,34 @@ void projector_roi(const Projector &p, int W, int H, int rect[4])
         if (u > hi_u) hi_u = u;
         if (v > hi_v) hi_v = v;
     };
-    if (p.type == SB_WARP_PLANE) {
+    if (p.type >= C_FISHEYE) {
+        // RotationWarperBase::detectResultRoi, the default: EVERY source pixel goes through mapForward (only the spherical
+        // and cylindrical warpers walk the border, only the plane warper takes the corners).  Threaded over rows; min / max
+        // of the same values in any order is the same value.
+        std::vector<float> part(4 * 64, 0.f);
+        std::vector<char> used(64, 0);
+        parallel_rows(H, [&](int y0, int y1, int t) {
+            float a = std::numeric_limits<float>::max(), b = a, c = -a, d = -a;
+            for (int y = y0; y < y1; ++y)
+                for (int x = 0; x < W; ++x) {
+                    float u, v;
+                    forward(p, (float)x, (float)y, u, v);
+                    if (u < a) a = u;
+                    if (v < b) b = v;
+                    if (u > c) c = u;
+                    if (v > d) d = v;
+                }
+            part[4 * t] = a; part[4 * t + 1] = b; part[4 * t + 2] = c; part[4 * t + 3] = d;
+            used[t] = 1;
+        });
+        for (int t = 0; t < 64; ++t)
+            if (used[t]) {
+                if (part[4 * t] < lo_u) lo_u = part[4 * t];
+                if (part[4 * t + 1] < lo_v) lo_v = part[4 * t + 1];
+                if (part[4 * t + 2] > hi_u) hi_u = part[4 * t + 2];
+                if (part[4 * t + 3] > hi_v) hi_v = part[4 * t + 3];
+            }
+    } else if (p.type == SB_WARP_PLANE) {
         // a projective plane map sends the rectangle to a quadrilateral: its 4 corners bound it
         visit(0.f, 0.f);
         visit(0.f, (float)(H - 1));
@@ -193,10 +378,35 @@ void projector_roi(const Projector &p, int W, int H, int rect[4])
     rect[3] = bry - tly + 1;
 }
 
+bool projector_needs_maps(const Projector &p) { return p.type >= C_FISHEYE && p.type != C_MERCATOR; }
+
+void projector_maps(const Projector &p, const int rect[4], float *xmap, float *ymap)
+{
+    const int w = rect[2], h = rect[3];
+    parallel_rows(h, [&](int y0, int y1, int) {
+        for (int j = y0; j < y1; ++j)
+            for (int i = 0; i < w; ++i) backward(p, (float)(rect[0] + i), (float)(rect[1] + j), xmap[(size_t)j * w + i], ymap[(size_t)j * w + i]);
+    });
+}
+
 void projector_tables(const Projector &p, const int rect[4], float *colX, float *colZ, float *rowA, float *rowY)
 {
     const int w = rect[2], h = rect[3];
     switch (p.type) {
+        case C_MERCATOR:
+            // MercatorProjector::mapBackward is separable like the spherical one: x_ = cos(v_) sin(u), y_ = sin(v_),
+            // z_ = cos(v_) cos(u) with u = column / scale and v_ = atan(sinh(row / scale))
+            for (int i = 0; i < w; ++i) {
+                float a = (float)(rect[0] + i) / p.scale;
+                colX[i] = sinf(a);
+                colZ[i] = cosf(a);
+            }
+            for (int j = 0; j < h; ++j) {
+                float v_ = atanf(sinhf((float)(rect[1] + j) / p.scale));
+                rowA[j] = cosf(v_);
+                rowY[j] = sinf(v_);
+            }
+            break;
         case SB_WARP_SPHERICAL:
             for (int i = 0; i < w; ++i) {
                 float a = (float)(rect[0] + i) / p.scale;

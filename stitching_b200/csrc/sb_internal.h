@@ -44,8 +44,9 @@ void dev_free(void *p, cudaStream_t s);
 // geometry (host, libm): sb_geometry.cpp
 // ---------------------------------------------------------------------------------------------
 struct Projector {
-    int type;  // SB_WARP_SPHERICAL / CYLINDRICAL / PLANE (affine folded into plane)
+    int type;  // SB_WARP_* (affine folded into plane; the A/B variants folded into their class, parameters in a, b)
     float scale;
+    float a, b;  // compressedPlane / panini parameters
     float k[9], rinv[9], r_kinv[9], k_rinv[9], t[3];
 };
 void projector_setup(Projector &p, int warp_type, float scale, const float *K, const float *R);
@@ -54,6 +55,10 @@ void projector_roi(const Projector &p, int src_w, int src_h, int rect[4]);
 //   x_ = rowA[v] * colX[u];  y_ = rowY[v];  z_ = rowA[v] * colZ[u]
 // (multiplication by an exact 1.0f keeps cylindrical / plane bit-identical to the unfactored form)
 void projector_tables(const Projector &p, const int rect[4], float *colX, float *colZ, float *rowA, float *rowY);
+// projections whose mapBackward is not separable: the float maps of RotationWarperBase::buildMaps over `rect`
+// (rect[3] rows of rect[2] floats each), computed with libm on all host cores
+bool projector_needs_maps(const Projector &p);
+void projector_maps(const Projector &p, const int rect[4], float *xmap, float *ymap);
 
 // ---------------------------------------------------------------------------------------------
 // device-side descriptors
@@ -73,6 +78,7 @@ struct WarpJob {
     long long blend_mask_pitch; // mask byte of dst_rgbm instead of the validity mask
     int dw, dh;
     const float *colX, *colZ, *rowA, *rowY;
+    const float *xmap, *ymap;  // non-null: backward map given per pixel (dw floats per row), the tables are unused
     float k[9];
     int always_divide;  // plane / affine: x/z, y/z unconditionally
     float xin_hi, yin_hi;  // 32 (sw-1) - 0.5, 32 (sh-1) - 0.5: upper limits of x*32, y*32 for a footprint inside the image
@@ -199,6 +205,7 @@ int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s);
 // jobs are HOST structs: they are passed by value in the kernel parameter block, SB_WARP_BATCH images per launch
 #define SB_WARP_BATCH 32
 int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s);
+int warp_maps_upload(const Projector &p, const int rect[4], float *maps_dev, WarpJob *job, cudaStream_t s);  // sb_api.cpp
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)

@@ -30,6 +30,12 @@ struct WarpBatch {
 
 __device__ __forceinline__ void project(const WarpJob &j, int u, int v, float &x, float &y)
 {
+    if (j.xmap) {  // a projection that is not separable: the host built the maps (sb_geometry.cpp projector_maps)
+        const size_t o = (size_t)v * (size_t)j.dw + (size_t)u;
+        x = __ldg(j.xmap + o);
+        y = __ldg(j.ymap + o);
+        return;
+    }
     const float cx = __ldg(j.colX + u), cz = __ldg(j.colZ + u);
     const float ra = __ldg(j.rowA + v), ry = __ldg(j.rowY + v);
     const float x_ = fmul(ra, cx), y_ = ry, z_ = fmul(ra, cz);
@@ -386,7 +392,7 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         if (!use_simple_kernels()) {
             bool rgbm_only = true, has_bm = false;
             for (int i = 0; i < cnt; ++i) {
-                rgbm_only = rgbm_only && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767 &&
+                rgbm_only = rgbm_only && !B.j[i].xmap && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767 &&
                             B.j[i].sw >= 2 && B.j[i].sh >= 2 && B.j[i].rgbm_pitch % 2 == 0;
                 has_bm = has_bm || B.j[i].blend_mask || B.j[i].gain_mode;  // per-pixel extras anywhere in the batch
             }

@@ -1,9 +1,11 @@
 """B200 drop-in for stitching.warper.Warper (reference: stitching/warper.py:7-94).
 
 Same class constants, method names, argument meaning and return types; the OpenCV calls behind them
-(cv.PyRotationWarper.warp / warpRoi) are replaced by libstitch_b200's fused sm_100a warp kernel.  The
-projections on the B200 path are spherical, cylindrical, plane and affine; the other twelve names are
-accepted by the constructor (the CLI builds its choices from WARP_TYPE_CHOICES) but raise on use.
+(cv.PyRotationWarper.warp / warpRoi) are replaced by libstitch_b200's fused sm_100a warp kernel.  All sixteen
+projections of WARP_TYPE_CHOICES are served bit-identically: spherical, cylindrical, plane, affine and mercator
+project on the device from separable trig tables; the other eleven (fisheye, stereographic, compressedPlane*,
+panini*, transverseMercator) are not separable and must match glibc's sinf / atan2f / tanf ... bit for bit, so
+their float maps are built by the library's host code (libm, all cores) and the device resamples.
 """
 import ctypes as C
 from statistics import median
@@ -87,11 +89,6 @@ class Warper:
     def _params(self, camera, aspect):
         scale = self.scale * aspect  # TypeError when set_scale was never called, like the reference
         if self.warper_type not in _lib.WARP_TYPES:
-            if self.warper_type in self.WARP_TYPE_CHOICES:
-                raise StitchingError(
-                    f"warper type '{self.warper_type}' is not on the B200 path yet "
-                    f"(available: {', '.join(_lib.WARP_TYPES)})"
-                )
             raise StitchingError(f"unknown warper type '{self.warper_type}'")
         K = np.ascontiguousarray(Warper.get_K(camera, aspect))
         R = np.asarray(camera.R)

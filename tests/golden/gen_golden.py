@@ -52,6 +52,16 @@ def gen_warp():
     for k, (wtype, R, focal, scale) in enumerate(specs):
         cam = rigs.Camera(focal, 1.0 + 0.03 * (k % 3 - 1), W / 2 + 3.5 * (k % 2), H / 2 - 2.25, R)
         cases.append((wtype, cam, scale, 1.0))
+    # the other twelve names of warper.py:10-27 (two cameras each; tests/test_stitcher.py:85,110 of the reference use
+    # fisheye and compressedPlaneA2B1)
+    extra = ["fisheye", "stereographic", "compressedPlaneA2B1", "compressedPlaneA1.5B1", "compressedPlanePortraitA2B1",
+             "compressedPlanePortraitA1.5B1", "paniniA2B1", "paniniA1.5B1", "paniniPortraitA2B1", "paniniPortraitA1.5B1", "mercator",
+             "transverseMercator"]
+    for k, wtype in enumerate(extra):
+        cases.append((wtype, rigs.Camera(95.0 + 3 * k, 1.0 + 0.02 * (k % 3 - 1), W / 2 + 2.5 * (k % 2), H / 2 - 1.25, rot(0.04 * (k % 4), 0.25 - 0.05 * k, 0.02)),
+                      88.0 + 2 * k, 1.0))
+        cases.append((wtype, rigs.Camera(70.0 + 2 * k, 1.0, W / 2, H / 2, rot(-0.3 + 0.03 * k, -0.45 + 0.06 * k, 0.15)), 64.0 + 3 * k,
+                      [1.0, 0.8][k % 2]))
     for k in range(3):
         th, s = [0.03, -0.2, 0.11][k], [1.0, 0.9, 1.15][k]
         Hm = np.array([[s * np.cos(th), -s * np.sin(th), [12.5, -80.25, 301.0][k]],

@@ -222,3 +222,16 @@ def test_stitch_verbose_runs_after_install(reference_stitching, use_emu, tmp_pat
     assert pano.ndim == 3 and pano.dtype == np.uint8 and (pano.sum(axis=2) > 0).mean() > 0.5
     written = sorted(os.listdir(tmp_path))
     assert any(name.startswith("08_seam_mask") for name in written) and "09_result.jpg" in written, written
+
+
+@pytest.mark.parametrize("warper_type", ["fisheye", "compressedPlaneA2B1"])  # the two the reference's own tests use (tests/test_stitcher.py:85,110)
+def test_stitcher_with_other_warper_types_after_install(reference_stitching, use_emu, warper_type):
+    stitching, cv = reference_stitching
+    import stitching_b200
+
+    views = synthetic_views(cv)
+    ref_pano = stitching.Stitcher(warper_type=warper_type, **SETTINGS).stitch([v.copy() for v in views])
+    stitching_b200.install(stitching)
+    pano = stitching.Stitcher(warper_type=warper_type, **SETTINGS).stitch([v.copy() for v in views])
+    assert pano.ndim == 3 and pano.dtype == np.uint8 and (pano.sum(axis=2) > 0).mean() > 0.3
+    assert abs(pano.shape[0] - ref_pano.shape[0]) <= 40 and abs(pano.shape[1] - ref_pano.shape[1]) <= 40

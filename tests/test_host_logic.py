@@ -159,10 +159,13 @@ def test_error_behaviour(use_emu):
     bad.R = np.eye(3, dtype=np.float64)  # cv2 asserts CV_32F
     with pytest.raises(StitchingError):
         w.warp_roi((64, 48), bad)
-    f = Warper("fisheye")  # the constructor accepts every reference choice; using an unported one raises
-    f.scale = 1.0
+    f = Warper("fisheye")  # every reference choice is served (warper.py:10-27) ...
+    f.scale = 70.0
+    assert len(f.warp_roi((64, 48), cams[0])) == 4
+    g = Warper("equirectangular")  # ... and a name the reference does not know fails on use, like cv.PyRotationWarper
+    g.scale = 1.0
     with pytest.raises(StitchingError):
-        f.warp_roi((64, 48), cams[0])
+        g.warp_roi((64, 48), cams[0])
     b = Blender("multiband", 5)
     with pytest.raises(AttributeError):  # blender.py:41 before prepare: self.blender is None
         b.feed(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4), np.uint8), (0, 0))
@@ -351,3 +354,24 @@ def _twin_chain(oracle):
 
 def test_device_twins_through_warp_crop_compensate_feed(use_emu, oracle):
     _twin_chain(oracle)
+
+
+def _compositor_other_projections(oracle, names):
+    """The fused compositor with the projections whose maps the library's host code builds (and mercator, which runs from
+    tables): a small yaw ring per projection against the oracle's warp + blend."""
+    for k, name in enumerate(names):
+        cfg = rigs.config("cfg2", 25)
+        cfg = dict(cfg, warper=name)
+        cams = cfg["cameras"][2:5]
+        imgs = [rigs.noise_image(cfg["h"], cfg["w"], 2000 + 10 * k + i) for i in range(len(cams))]
+        ref = replay.oracle_composite(oracle, cfg, cams, imgs)
+        c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), name, "multiband", 5)
+        assert [r[:2] for r in c.rects] == [tuple(x) for x in ref["corners"]], name
+        pano, mask = c.composite(imgs)
+        replay.assert_exact(pano, ref["pano"], f"{name} pano")
+        replay.assert_exact(mask, ref["pmask"], f"{name} mask")
+        c.close()
+
+
+def test_compositor_with_the_other_projections(use_emu, oracle):
+    _compositor_other_projections(oracle, ["fisheye", "compressedPlaneA2B1", "paniniPortraitA1.5B1", "mercator", "transverseMercator", "stereographic"])

@@ -57,3 +57,10 @@ def test_device_twins_through_warp_crop_compensate_feed_on_gpu(cuda_lib, oracle)
     import test_host_logic
 
     test_host_logic._twin_chain(oracle)
+
+
+def test_compositor_with_the_other_projections_on_gpu(cuda_lib, oracle):
+    import test_host_logic
+
+    test_host_logic._compositor_other_projections(oracle, ["fisheye", "stereographic", "compressedPlaneA1.5B1", "compressedPlanePortraitA2B1", "paniniA2B1",
+                                                           "paniniPortraitA1.5B1", "mercator", "transverseMercator"])
