@@ -532,11 +532,17 @@ def run_sharded(args, rank, local_rank, world):
         return box[0]
 
     sbdist.init_comm(rank, world, bcast, device=local_rank)
-    per_gpu, w, h = 4, 4000 // SCALE_DOWN, 3000 // SCALE_DOWN
-    n = per_gpu * world
-    cams = rigs.yaw_ring(n, w, h, 8000 / SCALE_DOWN, 10)
+    grid = args.workload == "cfg5"  # BASELINE configs[4]: the 16-image affine grid + feather, the SAME 16 images over N GPUs
+    if grid:
+        cfg = rigs.config("cfg5", SCALE_DOWN)
+        n, w, h, cams, warper, blender = cfg["n"], cfg["w"], cfg["h"], cfg["cameras"], cfg["warper"], cfg["blender"]
+        per_gpu = n // world
+    else:
+        per_gpu, w, h = 4, 4000 // SCALE_DOWN, 3000 // SCALE_DOWN
+        n = per_gpu * world
+        cams, warper, blender = rigs.yaw_ring(n, w, h, 8000 / SCALE_DOWN, 10), "cylindrical", "multiband"
     t0 = time.perf_counter()
-    comp = Compositor(cams, [(w, h)] * n, "cylindrical", "multiband", 5, rank=rank, world=world)
+    comp = Compositor(cams, [(w, h)] * n, warper, blender, 5, rank=rank, world=world)
     plan_ms = 1e3 * (time.perf_counter() - t0)
     imgs = [rigs.synth_image(h, w, i) for i in range(comp.first, comp.first + comp.count)]
     comp.upload(imgs)
@@ -564,9 +570,10 @@ def run_sharded(args, rank, local_rank, world):
     host = [comp.pinned_empty((h, w, 3)) for _ in imgs]
     for b, im in zip(host, imgs):
         b[...] = im
-    sw = comp.strip[1] - comp.strip[0]
-    ph = comp.roi[3]
-    pano, pmask = comp.pinned_empty((ph, max(sw, 1), 3)), comp.pinned_empty((ph, max(sw, 1)))
+    sw = comp.strip[1] - comp.strip[0]  # columns of the panorama, or rows when the blocks are stacked (feather grid)
+    rows = comp.strip_axis == 1
+    ph, pw = (sw, comp.roi[2]) if rows else (comp.roi[3], sw)
+    pano, pmask = comp.pinned_empty((max(ph, 1), max(pw, 1), 3)), comp.pinned_empty((max(ph, 1), max(pw, 1)))
 
     def e2e_step():
         comp.upload(host, pinned=True)
@@ -586,7 +593,7 @@ def run_sharded(args, rank, local_rank, world):
     dist.barrier()
     e2e_s = dist.max(time.perf_counter() - t0)
     h2d = dist.sum(len(imgs) * src_bytes)
-    d2h = dist.sum(ph * sw * 4)
+    d2h = dist.sum(ph * pw * 4)
 
     # ---- parity of the sharded result (outside every timed region): every rank's strip against ONE single-GPU
     # composite of the whole ring computed on rank 0's GPU.  int16 sums are exact under any grouping; the float weight
@@ -598,8 +605,14 @@ def run_sharded(args, rank, local_rank, world):
     dist.pg.all_gather_object(strips, (int(comp.strip[0]), int(comp.strip[1])))
     if rank == 0:
         t0 = time.perf_counter()
-        whole = Compositor(cams, [(w, h)] * n, "cylindrical", "multiband", 5)
+        whole = Compositor(cams, [(w, h)] * n, warper, blender, 5)
         ref_pano, ref_mask = whole.composite([rigs.synth_image(h, w, i) for i in range(n)])
+        whole_ms = None
+        if grid:  # strong scaling: the N = 1 point is this very configuration on one GPU
+            for _ in range(args.warmup):
+                whole.run()
+            whole.sync()
+            whole_ms, _ = whole.time(args.steps)
         whole.close()
         differing, max_abs, mask_diff, values = 0, 0, 0, 0
         for r in range(world):
@@ -609,29 +622,35 @@ def run_sharded(args, rank, local_rank, world):
             if r == 0:
                 sp, sm = np.array(pano), np.array(pmask)
             else:
-                tp = torch.empty((ph, hi - lo, 3), dtype=torch.uint8)
-                tm = torch.empty((ph, hi - lo), dtype=torch.uint8)
+                shape = (hi - lo, comp.roi[2]) if rows else (comp.roi[3], hi - lo)
+                tp = torch.empty(shape + (3,), dtype=torch.uint8)
+                tm = torch.empty(shape, dtype=torch.uint8)
                 dist.pg.recv(tp, src=r)
                 dist.pg.recv(tm, src=r)
                 sp, sm = tp.numpy(), tm.numpy()
-            d = np.abs(sp.astype(np.int16) - ref_pano[:, lo:hi].astype(np.int16))
+            want, want_mask = (ref_pano[lo:hi], ref_mask[lo:hi]) if rows else (ref_pano[:, lo:hi], ref_mask[:, lo:hi])
+            d = np.abs(sp.astype(np.int16) - want.astype(np.int16))
             differing += int(np.count_nonzero(d))
             max_abs = max(max_abs, int(d.max()) if d.size else 0)
-            mask_diff += int(np.count_nonzero(sm != ref_mask[:, lo:hi]))
+            mask_diff += int(np.count_nonzero(sm != want_mask))
             values += int(sp.size)
         parity = {"differing": differing, "max_abs": max_abs, "mask_differing": mask_diff, "values": values,
-                  "against": f"a single-GPU composite of the same {n}-image ring on rank 0 (strips gathered over gloo), {time.perf_counter() - t0:.1f} s"}
-        # like-for-like weak-scaling baseline: ONE GPU compositing 4 images of the same ring (the per-GPU work of this run)
-        one = Compositor(cams[:per_gpu], [(w, h)] * per_gpu, "cylindrical", "multiband", 5)
-        one.upload([rigs.synth_image(h, w, i) for i in range(per_gpu)])
-        for _ in range(args.warmup):
-            one.run()
-        one.sync()
-        one_ms, _ = one.time(args.steps)
-        one.close()
-        like_for_like = {"value": per_gpu * w * h / 1e6 / (one_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": one_ms / args.steps,
-                         "workload": f"{per_gpu}x{w}x{h} cylindrical + multiband on ONE GPU: the first {per_gpu} images of the same ring "
-                                     f"(the N = 1 point of this weak-scaling family; `bench.py --gpus 1` runs BASELINE configs[1] instead)"}
+                  "against": f"a single-GPU composite of the same {n} images on rank 0 (strips gathered over gloo), {time.perf_counter() - t0:.1f} s"}
+        if grid:
+            like_for_like = {"value": total_mpix / (whole_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": whole_ms / args.steps,
+                             "workload": f"the same {n}x{w}x{h} affine + feather configuration on ONE GPU (strong scaling: total work fixed)"}
+        else:
+            # like-for-like weak-scaling baseline: ONE GPU compositing 4 images of the same ring (the per-GPU work of this run)
+            one = Compositor(cams[:per_gpu], [(w, h)] * per_gpu, warper, blender, 5)
+            one.upload([rigs.synth_image(h, w, i) for i in range(per_gpu)])
+            for _ in range(args.warmup):
+                one.run()
+            one.sync()
+            one_ms, _ = one.time(args.steps)
+            one.close()
+            like_for_like = {"value": per_gpu * w * h / 1e6 / (one_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": one_ms / args.steps,
+                             "workload": f"{per_gpu}x{w}x{h} cylindrical + multiband on ONE GPU: the first {per_gpu} images of the same ring "
+                                         f"(the N = 1 point of this weak-scaling family; `bench.py --gpus 1` runs BASELINE configs[1] instead)"}
     elif sw > 0:
         dist.pg.send(torch.from_numpy(np.ascontiguousarray(pano)), dst=0)
         dist.pg.send(torch.from_numpy(np.ascontiguousarray(pmask)), dst=0)
@@ -639,16 +658,19 @@ def run_sharded(args, rank, local_rank, world):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if grid else "weak", "vs_baseline": None,
             "dtype": "int16+f32 (uint8 in/out)", "data": "synthetic",
             "config": {
-                "workload": sharded_workload_name(n, w, h, world),
+                "workload": (f"cfg5: {n}x{w}x{h} RGB, affine plane warp + feather blend over {world} GPUs (BASELINE configs[4])" if grid
+                             else sharded_workload_name(n, w, h, world)),
+                "strips": "rows" if rows else "columns",
                 "images_per_gpu": per_gpu, "pano": [comp.roi[2], comp.roi[3]], "num_bands": comp.num_bands, "plan_ms": round(plan_ms, 2),
-                "parallelism": f"{world} GPUs: image blocks per rank, pano column strips per rank, grouped NCCL send/recv of the "
-                               f"per-band partial sums in two parts on a communication stream, overlapped with the kernels "
-                               f"({slab_total / 1e6:.1f} MB per step in total)",
+                "parallelism": f"{world} GPUs: image blocks per rank, pano {'row' if rows else 'column'} strips per rank; the partial sums that cross strip "
+                               f"boundaries go to the owner's memory over NVLink (copy engine + flags; SB_PEER=0: grouped NCCL send/recv) on a "
+                               f"communication stream, overlapped with the kernels ({slab_total / 1e6:.1f} MB per step in total)",
                 "l2": f"no flush: each rank streams its {per_gpu * src_bytes / 1e6:.0f} MB of sources every step (> 126 MB L2)",
-                "timed": "plan built once; a step = warp + pyramids + partial sums + NCCL exchange (level-0 slabs leave after the first pyrDown) + collapse of the own strip",
+                "timed": ("plan built once; a step = warp + distance-transform weights + partial sums + exchange + normalise of the own strip" if grid else
+                          "plan built once; a step = warp + pyramids + partial sums + exchange (level-0 slabs leave after the first pyrDown) + collapse of the own strip"),
                 "like_for_like_n1": like_for_like,
             },
             "clocks": clocks,

@@ -228,6 +228,9 @@ SB_API void sb_host_free(void *p);
 SB_API sb_compositor *sb_compositor_create_sharded(const sb_rig *rig, int rank, int world);
 /* first image / number of images of this rank and its output columns [strip[0], strip[1]) in pano-roi coordinates */
 SB_API int sb_compositor_shard_info(const sb_compositor *c, int *first_image, int *n_local, int strip[2]);
+/* 0: `strip` above are columns of the panorama (multiband always; feather when the image blocks lie side by side);
+ * 1: rows (feather with image blocks stacked vertically, e.g. the rows of BASELINE configs[4]'s 4x4 grid) */
+SB_API int sb_compositor_shard_axis(const sb_compositor *c);
 /* transport hooks: phase 0 = local kernels up to the filled send slabs, phase 1 = finish after the receive slabs
  * were filled; sb_compositor_shard_slab exposes the device buffers (outgoing != 0: send slab to `peer`) */
 SB_API int sb_compositor_shard_phase(sb_compositor *c, int phase);

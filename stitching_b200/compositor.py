@@ -70,6 +70,7 @@ class Compositor:
         first, count, strip = C.c_int(), C.c_int(), (C.c_int * 2)()
         _lib.check(L.sb_compositor_shard_info(self._c, C.byref(first), C.byref(count), strip), "sb_compositor_shard_info")
         self.first, self.count, self.strip = first.value, count.value, (strip[0], strip[1])
+        self.strip_axis = int(L.sb_compositor_shard_axis(self._c))  # 0: self.strip are columns of the panorama, 1: rows
 
     # -- data movement ---------------------------------------------------------------------------
     def upload(self, images, pinned=False):
@@ -126,9 +127,12 @@ class Compositor:
         _lib.check(_lib.lib().sb_compositor_sync(self._c), "sb_compositor_sync")
 
     def download(self, out=None, out_mask=None):
-        """(pano, mask); with world > 1 the columns self.strip[0]:self.strip[1] of the panorama."""
-        h = self.roi[3]
-        w = self.strip[1] - self.strip[0]
+        """(pano, mask); with world > 1 the columns (strip_axis 0) or rows (strip_axis 1) self.strip[0]:self.strip[1]."""
+        h, w = self.roi[3], self.roi[2]
+        if self.strip_axis == 0:
+            w = self.strip[1] - self.strip[0]
+        else:
+            h = self.strip[1] - self.strip[0]
         pano = np.empty((h, w, 3), np.uint8) if out is None else out
         mask = np.empty((h, w), np.uint8) if out_mask is None else out_mask
         _lib.check(_lib.lib().sb_compositor_download(self._c, pano.ctypes.data_as(C.c_void_p), pano.strides[0],

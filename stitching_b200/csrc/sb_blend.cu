@@ -86,6 +86,60 @@ __global__ void __launch_bounds__(CL_BX *CL_BY) k_simple_blend(const FeedImage *
     store_final(out, x, y, v, on, mv);
 }
 
+// sharded feather blend (SURVEY 8e for BASELINE configs[4]): the same per-pixel arithmetic over a region of the pano,
+// with the partial sums of other ranks as additional items -- int16 wrap-around adds are exact under any grouping, the
+// float weight sums are grouped per rank (see sb_shard.cpp)
+__global__ void __launch_bounds__(CL_BX *CL_BY) k_feather_region(const __grid_constant__ FeatherRegionArgs A)
+{
+    const int x = A.rx0 + blockIdx.x * CL_BX + threadIdx.x;
+    const int y = A.ry0 + blockIdx.y * CL_BY + threadIdx.y;
+    if (x >= A.rx0 + A.rw || y >= A.ry0 + A.rh) return;
+    int acc[3] = {0, 0, 0};
+    float wsum = 0.f;
+    auto add_slab = [&](const FeatherSlab &S) {
+        const int X = x - S.x0, Y = y - S.y0;
+        if ((unsigned)X >= (unsigned)S.w || (unsigned)Y >= (unsigned)S.h) return;
+        const int o = Y * S.pitch + X;
+        acc[0] += S.acc[o];
+        acc[1] += S.acc[S.plane + o];
+        acc[2] += S.acc[2 * S.plane + o];
+        wsum = fadd(wsum, S.wsum[o]);
+    };
+    for (int k = 0; k < A.n_before; ++k) add_slab(A.slabs[k]);
+    for (int i = A.i0; i < A.i1; ++i) {
+        const FeedImage &im = A.imgs[i];
+        const int X = x - im.dx, Y = y - im.dy;
+        if ((unsigned)X >= (unsigned)im.w || (unsigned)Y >= (unsigned)im.h) continue;
+        int g[3];
+        if (im.rgbm) {
+            const unsigned p = __ldg(im.rgbm + (long long)Y * im.rgbm_pitch + X);
+            g[0] = p & 255u; g[1] = (p >> 8) & 255u; g[2] = (p >> 16) & 255u;
+        } else {
+            const int16_t *q = im.s16 + (long long)Y * im.s16_pitch + (long long)X * 3;
+            g[0] = q[0]; g[1] = q[1]; g[2] = q[2];
+        }
+        const float wt = im.fw[(long long)Y * im.w + X];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += f2s_wrap(fmul((float)g[c], wt));
+        wsum = fadd(wsum, wt);
+    }
+    for (int k = 0; k < A.n_after; ++k) add_slab(A.slabs[A.n_before + k]);
+    if (A.partial) {
+        const int o = (y - A.ry0) * A.slab_pitch + (x - A.rx0);
+        A.slab_acc[o] = (int16_t)acc[0];
+        A.slab_acc[A.slab_plane + o] = (int16_t)acc[1];
+        A.slab_acc[2 * A.slab_plane + o] = (int16_t)acc[2];
+        A.slab_w[o] = wsum;
+        return;
+    }
+    const float den = fadd(wsum, SB_WEIGHT_EPS);
+    int v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv((float)(short)acc[c], den));
+    const bool on = wsum > SB_WEIGHT_EPS;
+    store_final(A.out, x - A.out_x0, y - A.out_y0, v, on, on ? 255u : 0u);
+}
+
 // ---- feather weights: w = min(L1 distance to the nearest zero mask pixel * sharpness, 1) ------------
 // exact city-block distance = min over rows of (row distance + |dy|): a row pass then a column pass,
 // each a forward and a backward min-plus sweep.  "no zero pixel" stays at DT_INF -> weight 1.
@@ -184,6 +238,14 @@ int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host
         launch(k_dt_cols, dim3(div_up(imgs_host[i].w, 64)), dim3(64), 0, s, imgs_dev, i, sharpness);
     }
     return launch_check("k_dt");
+}
+
+int launch_feather_region(const FeatherRegionArgs &A, cudaStream_t s)
+{
+    if (A.rw <= 0 || A.rh <= 0) return SB_OK;
+    dim3 block(CL_BX, CL_BY), grid(div_up(A.rw, CL_BX), div_up(A.rh, CL_BY));
+    launch(k_feather_region, grid, block, 0, s, A);
+    return launch_check("k_feather_region");
 }
 
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s)

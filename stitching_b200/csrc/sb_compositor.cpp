@@ -213,24 +213,27 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         f.rgbm_pitch = rgbm_pitch_of(c->rects[i].w);
         SB_TRY(c->plan.add_feed(f));
     }
-    int out_w = roi.w;
+    int out_w = roi.w, out_h = roi.h;
     if (c->sharded) {
         c->plan.active_first = c->first;
         c->plan.active_count = c->count;
         SB_TRY(c->shard.build(c->plan, rank, world));
         int lo, hi;
         c->shard.strip(c->plan, &lo, &hi);
-        out_w = hi - lo;
+        if (c->shard.axis == 0)
+            out_w = hi - lo;
+        else
+            out_h = hi - lo;  // row strips (feather, image blocks stacked vertically)
     }
     SB_TRY(c->plan.allocate(s));
     if (c->sharded) SB_TRY(c->shard.allocate(c->plan, s));
     std::memset(&c->out, 0, sizeof c->out);
     c->out.w = out_w;
-    c->out.h = roi.h;
+    c->out.h = out_h;
     c->out.rgb_pitch = (long long)out_w * 3;
     c->out.mask_pitch = out_w;
-    SB_TRY(dev_alloc((void **)&c->out.rgb, (size_t)std::max(out_w, 1) * 3 * roi.h, s));
-    SB_TRY(dev_alloc((void **)&c->out.mask, (size_t)std::max(out_w, 1) * roi.h, s));
+    SB_TRY(dev_alloc((void **)&c->out.rgb, (size_t)std::max(out_w, 1) * 3 * std::max(out_h, 1), s));
+    SB_TRY(dev_alloc((void **)&c->out.mask, (size_t)std::max(out_w, 1) * std::max(out_h, 1), s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }
@@ -287,8 +290,21 @@ static int shard_pyrdown(sb_compositor *c, cudaStream_t s, int l)
 }
 
 // sharded step, local part: pyramids of the own images, then the partial sums every neighbour needs
+static int shard_feather_weights(sb_compositor *c, cudaStream_t s)
+{
+    BlendPlan &P = c->plan;
+    return launch_feather_weights(P.imgs_dev + c->first, P.imgs.data() + c->first, c->count, P.sharpness, s);
+}
+
 static int shard_local(sb_compositor *c, cudaStream_t s, const std::function<int(const std::string &)> &mark)
 {
+    if (c->plan.kind == SB_BLEND_FEATHER) {
+        SB_TRY(shard_feather_weights(c, s));
+        SB_TRY(mark("feather_weights"));
+        SB_TRY(c->shard.feather_partial_out(c->plan, s));
+        SB_TRY(mark("partial_out"));
+        return SB_OK;
+    }
     for (int l = 0; l < c->plan.nb; ++l) {
         SB_TRY(shard_pyrdown(c, s, l));
         SB_TRY(mark("pyrdown_l" + std::to_string(l)));
@@ -330,6 +346,37 @@ static int compositor_enqueue_kernels(sb_compositor *c, bool events, int slot)
         }
     }
     BlendPlan &P0 = c->plan;
+    if (P0.kind == SB_BLEND_FEATHER) {
+        // single level: distance-transform weights of the own images, partial sums for the neighbours, one exchange, finish
+        SB_TRY(shard_feather_weights(c, s));
+        SB_TRY(mark("feather_weights"));
+        if (c->shard.connected) {
+            const unsigned step = ++c->shard.step;
+            if (step > 1) SB_CUDA(cudaStreamWaitEvent(s, c->e_xchg[1], 0));  // the previous step's copies have left the send buffers
+            SB_TRY(c->shard.feather_partial_out(P0, s));
+            SB_TRY(mark("partial_out"));
+            SB_CUDA(cudaEventRecord(c->e_part[0], s));
+            SB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->e_part[0], 0));
+            SB_TRY(c->shard.wait_consumed(c->comm_stream, step - 1));
+            SB_TRY(c->shard.push(c->comm_stream, 0));
+            SB_TRY(c->shard.signal_data(c->comm_stream, 0, step));
+            SB_CUDA(cudaEventRecord(c->e_xchg[1], c->comm_stream));
+            SB_TRY(c->shard.wait_data(s, 0, step));
+            SB_TRY(c->shard.feather_finish(P0, out, s));
+            SB_TRY(c->shard.signal_consumed(s, step));
+        } else {
+            SB_TRY(c->shard.feather_partial_out(P0, s));
+            SB_TRY(mark("partial_out"));
+            SB_CUDA(cudaEventRecord(c->e_part[0], s));
+            SB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->e_part[0], 0));
+            SB_TRY(c->shard.exchange(c->comm_stream, -1));
+            SB_CUDA(cudaEventRecord(c->e_xchg[0], c->comm_stream));
+            SB_CUDA(cudaStreamWaitEvent(s, c->e_xchg[0], 0));
+            SB_TRY(c->shard.feather_finish(P0, out, s));
+        }
+        SB_TRY(mark("feather_finish"));
+        return SB_OK;
+    }
     if (c->shard.connected) {
         // Exchange over mapped peer memory (sb_peer.cpp): the slabs go from the local send buffers into the owners' arenas
         // with copy-engine copies on the communication stream, beside the pyramid kernels; flags written / awaited by
@@ -479,7 +526,7 @@ int sb_compositor_shard_info(const sb_compositor *c, int *first_image, int *n_lo
     if (strip) {
         strip[0] = 0;
         strip[1] = c->plan.roi.w;
-        if (c->sharded) c->shard.strip(c->plan, &strip[0], &strip[1]);
+        if (c->sharded) c->shard.strip(c->plan, &strip[0], &strip[1]);  // columns, or rows when sb_compositor_shard_axis() == 1
     }
     return SB_OK;
 }
@@ -497,12 +544,16 @@ int sb_compositor_shard_phase(sb_compositor *c, int phase)
     if (phase == 0) {
         SB_TRY(launch_warp(c->jobs.data() + c->first, c->count, s));
         SB_TRY(shard_local(c, s, std::function<int(const std::string &)>(nomark)));
+    } else if (c->plan.kind == SB_BLEND_FEATHER) {
+        SB_TRY(c->shard.feather_finish(c->plan, c->out, s));
     } else {
         SB_TRY(c->shard.finish(c->plan, c->out, s));
     }
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }
+
+int sb_compositor_shard_axis(const sb_compositor *c) { return c && c->sharded ? c->shard.axis : 0; }
 
 int sb_compositor_shard_slab(sb_compositor *c, int peer, int outgoing, void **dev_ptr, size_t *bytes)
 {

@@ -225,6 +225,28 @@ int launch_tail(const FeedImage *imgs_dev, const PanoLevel *pano_dev, int first,
                 unsigned *state, cudaStream_t s);
 int launch_feather_weights(const FeedImage *imgs_dev, const FeedImage *imgs_host, int n, float sharpness, cudaStream_t s);
 int launch_simple_blend(const FeedImage *imgs_dev, int n, int feather, PanoOut out, cudaStream_t s);
+// sharded feather blend: a slab of partial sums (acc int16 x3 planes with wrap-around, wsum float32) over a rectangle of
+// the pano roi, and one launch over a region: the slabs of lower ranks, images [i0, i1), the slabs of higher ranks, in that
+// order; `partial`: write the sums as a slab instead of normalising
+struct FeatherSlab {
+    int x0, y0, w, h, pitch, plane;
+    const int16_t *acc;
+    const float *wsum;
+};
+struct FeatherRegionArgs {
+    const FeedImage *imgs;
+    int i0, i1;
+    const FeatherSlab *slabs;
+    int n_before, n_after;
+    int rx0, ry0, rw, rh;    // region, pano-roi coordinates
+    int partial;
+    int16_t *slab_acc;       // partial: origin = (rx0, ry0)
+    float *slab_w;
+    int slab_pitch, slab_plane;
+    PanoOut out;             // !partial: the buffer's origin is pano pixel (out_x0, out_y0)
+    int out_x0, out_y0;
+};
+int launch_feather_region(const FeatherRegionArgs &A, cudaStream_t s);
 int launch_flush_l2(void *buf, size_t bytes, cudaStream_t s);
 int launch_wait_flags(const unsigned *flags, unsigned mask, unsigned value, cudaStream_t s);  // lanes with a mask bit wait for flags[lane] >= value
 // ExposureErrorCompensator.apply: taps of the float32 bilinear resize of a gain map (sb_geometry.cpp), the 256-entry

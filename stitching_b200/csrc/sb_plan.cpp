@@ -175,7 +175,8 @@ int BlendPlan::allocate(cudaStream_t s)
             pano_off[l] = carve((size_t)3 * h * pitch * sizeof(int16_t));
         }
     } else if (kind == SB_BLEND_FEATHER) {
-        for (int i = 0; i < n; ++i) fw_off[i] = carve((size_t)imgs[i].w * imgs[i].h * sizeof(float));
+        for (int i = 0; i < n; ++i)
+            if (active(i)) fw_off[i] = carve((size_t)imgs[i].w * imgs[i].h * sizeof(float));
     }
     const size_t imgs_off = carve(sizeof(FeedImage) * (size_t)std::max(n, 1));
     const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
@@ -211,7 +212,7 @@ int BlendPlan::allocate(cudaStream_t s)
             P.c = (int16_t *)(base + pano_off[l]);
         }
     } else if (kind == SB_BLEND_FEATHER) {
-        for (int i = 0; i < n; ++i) imgs[i].fw = (const float *)(base + fw_off[i]);
+        for (int i = 0; i < n; ++i) imgs[i].fw = active(i) ? (const float *)(base + fw_off[i]) : nullptr;
     }
     imgs_dev = (FeedImage *)(base + imgs_off);
     pano_dev = (PanoLevel *)(base + panod_off);

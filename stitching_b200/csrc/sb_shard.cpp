@@ -11,6 +11,7 @@
 // bit-identical to the single-GPU order whenever at most two ranks meet in a pixel with at most one image each
 // and otherwise differs by float re-association only (tests bound the effect on the final uint8 to +-1).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "sb_shard.h"
@@ -33,8 +34,48 @@ void ShardPlan::region_x(const BlendPlan &plan, int r, int l, int *a, int *b) co
     if (*b < *a) *b = *a;
 }
 
+// Feather (single level): rank `src` hands rank `dst` its partial sums over (bounding box of its images) x (dst's strip).
+void ShardPlan::feather_slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab *ps) const
+{
+    int f0, fc;
+    block_of((int)plan.imgs.size(), world, src, &f0, &fc);
+    std::memset(ps->lv, 0, sizeof ps->lv);
+    ps->bytes = ps->split = 0;
+    int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+    for (int i = f0; i < f0 + fc; ++i) {
+        const FeedImage &im = plan.imgs[i];
+        x0 = std::min(x0, im.dx);
+        y0 = std::min(y0, im.dy);
+        x1 = std::max(x1, im.dx + im.w);
+        y1 = std::max(y1, im.dy + im.h);
+    }
+    const int q = reversed ? world - 1 - dst : dst;  // dst's place in the spatial order of the strips
+    if (axis == 0) {
+        x0 = std::max(x0, bounds[q]);
+        x1 = std::min(x1, bounds[q + 1]);
+    } else {
+        y0 = std::max(y0, bounds[q]);
+        y1 = std::min(y1, bounds[q + 1]);
+    }
+    if (fc == 0 || x1 <= x0 || y1 <= y0) return;
+    SlabLevel &L = ps->lv[0];
+    L.x0 = x0;
+    L.y0 = y0;
+    L.w = x1 - x0;
+    L.h = y1 - y0;
+    L.pitch = (int)align_up((size_t)L.w, 8);
+    L.plane = L.pitch * L.h;
+    L.acc_off = 0;
+    L.w_off = align_up((size_t)3 * L.plane * sizeof(int16_t), 256);
+    ps->bytes = ps->split = align_up(L.w_off + (size_t)L.plane * sizeof(float), 256);  // everything travels as "part 0"
+}
+
 void ShardPlan::slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab *ps) const
 {
+    if (plan.kind == SB_BLEND_FEATHER) {
+        feather_slab_geometry(plan, src, dst, ps);
+        return;
+    }
     int f0, fc;
     block_of((int)plan.imgs.size(), world, src, &f0, &fc);
     size_t off = 0;
@@ -80,8 +121,9 @@ void ShardPlan::slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab 
 int ShardPlan::build(const BlendPlan &plan, int rank_, int world_)
 {
     const int n = (int)plan.imgs.size();
-    if (plan.kind != SB_BLEND_MULTIBAND || plan.nb < 1) {
-        set_error("sharded composite: needs the multiband blender with at least one band (got kind %d, %d bands)", plan.kind, plan.nb);
+    if (!(plan.kind == SB_BLEND_FEATHER || (plan.kind == SB_BLEND_MULTIBAND && plan.nb >= 1))) {
+        set_error("sharded composite: needs the feather blender or the multiband blender with at least one band (got kind %d, %d bands)",
+                  plan.kind, plan.nb);
         return SB_ERR_INVALID;
     }
     if (world_ < 1 || rank_ < 0 || rank_ >= world_ || n < world_) {
@@ -90,7 +132,10 @@ int ShardPlan::build(const BlendPlan &plan, int rank_, int world_)
     }
     rank = rank_;
     world = world_;
+    axis = 0;
+    reversed = false;
     block_of(n, world, rank, &first, &count);
+    if (plan.kind == SB_BLEND_FEATHER) return build_feather(plan);
     // strip boundaries: halfway between the centres of the neighbouring blocks' edge images, snapped to 2^nb
     const int a = 1 << plan.nb;
     bounds.assign(world + 1, 0);
@@ -121,10 +166,69 @@ int ShardPlan::build(const BlendPlan &plan, int rank_, int world_)
     return SB_OK;
 }
 
+// Feather: the image blocks are either side by side (a yaw ring: column strips) or stacked (the rows of an affine grid,
+// BASELINE configs[4]: row strips); the strip boundaries lie halfway between the neighbouring blocks' bounding boxes.
+int ShardPlan::build_feather(const BlendPlan &plan)
+{
+    const int n = (int)plan.imgs.size();
+    std::vector<double> cx(world), cy(world);
+    std::vector<int> lo_x(world), hi_x(world), lo_y(world), hi_y(world);
+    for (int r = 0; r < world; ++r) {
+        int f0, fc;
+        block_of(n, world, r, &f0, &fc);
+        int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+        for (int i = f0; i < f0 + fc; ++i) {
+            const FeedImage &im = plan.imgs[i];
+            x0 = std::min(x0, im.dx); y0 = std::min(y0, im.dy);
+            x1 = std::max(x1, im.dx + im.w); y1 = std::max(y1, im.dy + im.h);
+        }
+        lo_x[r] = x0; hi_x[r] = x1; lo_y[r] = y0; hi_y[r] = y1;
+        cx[r] = 0.5 * (x0 + x1);
+        cy[r] = 0.5 * (y0 + y1);
+    }
+    // the blocks follow each other along x or y, in either direction (an affine grid whose rows run bottom to top in the
+    // panorama is as good as one running top to bottom); prefer the axis along which they are spread further apart
+    bool inc_x = true, inc_y = true, dec_x = true, dec_y = true;
+    for (int r = 1; r < world; ++r) {
+        inc_x = inc_x && cx[r] > cx[r - 1];
+        dec_x = dec_x && cx[r] < cx[r - 1];
+        inc_y = inc_y && cy[r] > cy[r - 1];
+        dec_y = dec_y && cy[r] < cy[r - 1];
+    }
+    const bool mono_x = inc_x || dec_x, mono_y = inc_y || dec_y;
+    if (!mono_x && !mono_y) {
+        set_error("sharded composite: image blocks are ordered neither along x nor along y in the panorama (block centres (%.1f, %.1f) .. (%.1f, %.1f))",
+                  cx[0], cy[0], cx[world - 1], cy[world - 1]);
+        return SB_ERR_INVALID;
+    }
+    axis = (mono_y && (!mono_x || std::fabs(cy[world - 1] - cy[0]) > std::fabs(cx[world - 1] - cx[0]))) ? 1 : 0;
+    reversed = axis == 0 ? !inc_x : !inc_y;
+    const int extent = axis == 0 ? plan.roi.w : plan.roi.h;
+    bounds.assign(world + 1, 0);  // in spatial order: the strip of rank r is [bounds[q], bounds[q + 1]), q = reversed ? world-1-r : r
+    bounds[world] = extent;
+    for (int q = 1; q < world; ++q) {
+        const int ra = reversed ? world - q : q - 1, rb = reversed ? world - 1 - q : q;  // the ranks at places q-1 and q
+        const int a = axis == 0 ? hi_x[ra] : hi_y[ra], b = axis == 0 ? lo_x[rb] : lo_y[rb];
+        int m = (a + b) / 2;  // middle of the overlap (or of the gap) between the two blocks
+        m = std::max(m, bounds[q - 1]);
+        bounds[q] = std::min(m, extent);
+    }
+    send.assign(world, PeerSlab());
+    recv.assign(world, PeerSlab());
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        slab_geometry(plan, rank, p, &send[p]);
+        slab_geometry(plan, p, rank, &recv[p]);
+    }
+    return SB_OK;
+}
+
 void ShardPlan::strip(const BlendPlan &plan, int *lo, int *hi) const
 {
-    *lo = std::min(bounds[rank], plan.roi.w);
-    *hi = std::min(bounds[rank + 1], plan.roi.w);
+    const int extent = axis == 0 ? plan.roi.w : plan.roi.h;
+    const int q = reversed ? world - 1 - rank : rank;
+    *lo = std::min(bounds[q], extent);
+    *hi = std::min(bounds[q + 1], extent);
 }
 
 int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
@@ -139,6 +243,25 @@ int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
             recv[p].buf = (char *)arena + recv_off[p];
         else
             SB_TRY(dev_alloc(&recv[p].buf, recv[p].bytes, s));
+    }
+    if (plan.kind == SB_BLEND_FEATHER) {
+        // the slabs this rank receives, lower ranks first
+        std::vector<FeatherSlab> fs;
+        feather_before_ = feather_after_ = 0;
+        for (int p = 0; p < world; ++p) {
+            const SlabLevel &L = recv[p].lv[0];
+            if (p == rank || !recv[p].bytes || L.w == 0) continue;
+            FeatherSlab f;
+            f.x0 = L.x0; f.y0 = L.y0; f.w = L.w; f.h = L.h; f.pitch = L.pitch; f.plane = L.plane;
+            f.acc = (const int16_t *)((const char *)recv[p].buf + L.acc_off);
+            f.wsum = (const float *)((const char *)recv[p].buf + L.w_off);
+            fs.push_back(f);
+            (p < rank ? feather_before_ : feather_after_)++;
+        }
+        SB_TRY(dev_alloc(&feather_items_, std::max<size_t>(fs.size(), 1) * sizeof(FeatherSlab), s));
+        if (!fs.empty()) SB_CUDA(cudaMemcpyAsync(feather_items_, fs.data(), fs.size() * sizeof(FeatherSlab), cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        return SB_OK;
     }
     // item lists per level: slabs of lower ranks, own images, slabs of higher ranks (= feed order)
     std::vector<ColDesc> items;
@@ -200,6 +323,53 @@ void ShardPlan::release(cudaStream_t s)
     }
     dev_free(items_arena_, s);
     items_arena_ = nullptr;
+    dev_free(feather_items_, s);
+    feather_items_ = nullptr;
+}
+
+int ShardPlan::feather_partial_out(const BlendPlan &plan, cudaStream_t s, bool direct)
+{
+    direct = direct && connected;
+    for (int p = 0; p < world; ++p) {
+        const SlabLevel &L = send[p].lv[0];
+        if (p == rank || !send[p].bytes || L.w == 0) continue;
+        FeatherRegionArgs A;
+        std::memset(&A, 0, sizeof A);
+        A.imgs = plan.imgs_dev;
+        A.i0 = first;
+        A.i1 = first + count;
+        A.rx0 = L.x0; A.ry0 = L.y0; A.rw = L.w; A.rh = L.h;
+        A.partial = 1;
+        char *dst = direct ? peer_arena[p] + peer_slot[p] : (char *)send[p].buf;
+        A.slab_acc = (int16_t *)(dst + L.acc_off);
+        A.slab_w = (float *)(dst + L.w_off);
+        A.slab_pitch = L.pitch;
+        A.slab_plane = L.plane;
+        SB_TRY(launch_feather_region(A, s));
+    }
+    return SB_OK;
+}
+
+int ShardPlan::feather_finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s)
+{
+    int lo, hi;
+    strip(plan, &lo, &hi);
+    FeatherRegionArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.imgs = plan.imgs_dev;
+    A.i0 = first;
+    A.i1 = first + count;
+    A.slabs = (const FeatherSlab *)feather_items_;
+    A.n_before = feather_before_;
+    A.n_after = feather_after_;
+    A.rx0 = axis == 0 ? lo : 0;
+    A.ry0 = axis == 0 ? 0 : lo;
+    A.rw = axis == 0 ? hi - lo : plan.roi.w;
+    A.rh = axis == 0 ? plan.roi.h : hi - lo;
+    A.out = out;
+    A.out_x0 = A.rx0;
+    A.out_y0 = A.ry0;
+    return launch_feather_region(A, s);
 }
 
 int ShardPlan::partial_out(const BlendPlan &plan, cudaStream_t s, int l_lo, int l_hi, bool direct)

@@ -24,6 +24,9 @@ public:
     int rank = 0, world = 1;
     int first = 0, count = 0;        // this rank's image block [first, first + count)
     std::vector<int> bounds;         // strip boundaries in padded-pano columns, world + 1 entries, multiples of 2^nb
+                                     // (feather: in roi columns or rows, see `axis`)
+    bool reversed = false;           // feather: the blocks follow each other against the axis (rank 0 owns the LAST strip)
+    int axis = 0;                    // 0: column strips (multiband always); 1: row strips (feather, image blocks stacked vertically)
     std::vector<PeerSlab> send, recv;  // indexed by peer rank
     ColDesc *items_dev[SB_MAX_BANDS + 1] = {};
     int n_items[SB_MAX_BANDS + 1] = {};
@@ -50,8 +53,12 @@ public:
     // slab buffers and per-level item lists (own images + the slabs this rank receives), after plan.allocate()
     int allocate(const BlendPlan &plan, cudaStream_t s);
     void release(cudaStream_t s);
-    // output columns of this rank: [lo, hi) in pano-roi coordinates (hi <= roi.w; may be empty)
+    // output columns (axis 0) / rows (axis 1) of this rank: [lo, hi) in pano-roi coordinates (may be empty)
     void strip(const BlendPlan &plan, int *lo, int *hi) const;
+    // feather blender (single level): partial sums of the own images over the rectangle each neighbour needs; the own
+    // strip from the own images and the neighbours' slabs in rank order (sb_blend.cu k_feather_region)
+    int feather_partial_out(const BlendPlan &plan, cudaStream_t s, bool direct = false);
+    int feather_finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s);
     // phase 0: partial sums of the own images over every region a neighbour needs -> send slabs
     // (levels l_lo .. l_hi only: level 0 needs just the first pyrDown, so its slabs -- three quarters of the bytes --
     // can leave while the rest of the pyramid is still being built)
@@ -75,6 +82,10 @@ public:
 private:
     void region_x(const BlendPlan &plan, int r, int l, int *a, int *b) const;
     void slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab *ps) const;
+    void feather_slab_geometry(const BlendPlan &plan, int src, int dst, PeerSlab *ps) const;
+    int build_feather(const BlendPlan &plan);
+    void *feather_items_ = nullptr;  // FeatherSlab records of the slabs this rank receives (device)
+    int feather_before_ = 0, feather_after_ = 0;
     void *items_arena_ = nullptr;
 };
 

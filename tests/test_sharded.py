@@ -39,10 +39,13 @@ def run_sharded(cfg, cams, imgs, world, copy):
     for c in ranks:
         c.shard_phase(1)
         strips.append(c.download())
-    los = [c.strip for c in ranks]
-    assert los[0][0] == 0 and all(a[1] == b[0] for a, b in zip(los, los[1:])) and los[-1][1] == ranks[0].roi[2]
-    pano = np.concatenate([s[0] for s in strips], axis=1)
-    mask = np.concatenate([s[1] for s in strips], axis=1)
+    axis = ranks[0].strip_axis
+    assert all(c.strip_axis == axis for c in ranks)
+    order = sorted(range(world), key=lambda r: ranks[r].strip)  # spatial order of the strips (feather may run against the rank order)
+    los = [ranks[r].strip for r in order]
+    assert los[0][0] == 0 and all(a[1] == b[0] for a, b in zip(los, los[1:])) and los[-1][1] == ranks[0].roi[3 if axis else 2]
+    pano = np.concatenate([strips[r][0] for r in order], axis=0 if axis else 1)
+    mask = np.concatenate([strips[r][1] for r in order], axis=0 if axis else 1)
     for c in ranks:
         c.close()
     return pano, mask, moved
@@ -78,12 +81,43 @@ def test_sharded_cylindrical_many_images(use_emu):
     assert np.abs(pano.astype(np.int32) - ref_pano.astype(np.int32)).max() <= 1
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_feather_grid(use_emu, world):
+    """BASELINE configs[4]: 4x4 plane grid, feather blender; image blocks are grid rows, so the ranks own ROW strips."""
+    cfg = rigs.config("cfg5", 12)
+    cams = cfg["cameras"]
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 30 + i) if i % 3 == 0 else rigs.synth_image(cfg["h"], cfg["w"], 30 + i) for i in range(len(cams))]
+    single = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+    ref_pano, ref_mask = single.composite(imgs)
+    single.close()
+    pano, mask, moved = run_sharded(cfg, cams, imgs, world, lambda d, s, n: C.memmove(d, s, n))
+    assert moved > 0
+    assert pano.shape == ref_pano.shape
+    assert np.array_equal(mask, ref_mask)
+    d = np.abs(pano.astype(np.int32) - ref_pano.astype(np.int32))
+    assert d.max() <= 1, int(d.max())  # float sums regrouped per rank
+    assert (d != 0).mean() < 1e-3
+
+
+def test_sharded_feather_side_by_side(use_emu):
+    """Feather on a single-row rig: the blocks lie side by side and the strips are columns, as for multiband."""
+    cfg = dict(rigs.config("cfg2", 16), blender="feather")
+    cams = cfg["cameras"]
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 11 + i) for i in range(len(cams))]
+    single = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], "feather", cfg["strength"])
+    ref_pano, ref_mask = single.composite(imgs)
+    single.close()
+    pano, mask, _ = run_sharded(cfg, cams, imgs, 2, lambda d, s, n: C.memmove(d, s, n))
+    assert np.array_equal(mask, ref_mask)
+    assert np.abs(pano.astype(np.int32) - ref_pano.astype(np.int32)).max() <= 1
+
+
 def test_sharded_rejects_what_it_cannot_do(use_emu):
     from stitching_b200 import StitchingError
 
-    cfg = rigs.config("cfg5", 12)  # feather blender: no per-band sums to exchange
+    cfg = rigs.config("cfg5", 12)  # "no" blender: nothing to exchange, not sharded
     with pytest.raises(StitchingError):
-        Compositor(cfg["cameras"], [(cfg["w"], cfg["h"])] * cfg["n"], cfg["warper"], cfg["blender"], cfg["strength"], rank=0, world=2)
+        Compositor(cfg["cameras"], [(cfg["w"], cfg["h"])] * cfg["n"], cfg["warper"], "no", cfg["strength"], rank=0, world=2)
     cfg = rigs.config("cfg2", 16)
     c = Compositor(cfg["cameras"], [(cfg["w"], cfg["h"])] * cfg["n"], cfg["warper"], cfg["blender"], cfg["strength"], rank=1, world=2)
     with pytest.raises(StitchingError):
