@@ -322,24 +322,32 @@ def dropin_e2e(cfg, imgs, reps=3):
 
     cams = cfg["cameras"]
     sizes = [(cfg["w"], cfg["h"])] * len(cams)
-    times = []
+    times, stages = [], []
     pano = mask = None
     for _ in range(reps + 1):  # the first pass is the warm-up
-        t0 = time.perf_counter()
+        t = [time.perf_counter()]
         warper = Warper(cfg["warper"])
         warper.set_scale(cams)
         warped = list(warper.warp_images(imgs, cams))
+        t.append(time.perf_counter())
         masks = list(warper.create_and_warp_masks(sizes, cams))
+        t.append(time.perf_counter())
         corners, wsizes = warper.warp_rois(sizes, cams)
         blender = Blender(cfg["blender"], cfg["strength"])
         blender.prepare(corners, wsizes)
+        t.append(time.perf_counter())
         for img, m, c in zip(warped, masks, corners):
             blender.feed(img, m, c)
+        t.append(time.perf_counter())
         pano, mask = blender.blend()
-        times.append(time.perf_counter() - t0)
+        t.append(time.perf_counter())
+        times.append(t[-1] - t[0])
+        stages.append([b - a for a, b in zip(t, t[1:])])
     dt = float(np.median(times[1:]))
     mpix = len(cams) * cfg["w"] * cfg["h"] / 1e6
-    return mpix / dt, 1e3 * dt, pano, mask
+    names = ["warp_images", "create_and_warp_masks", "warp_rois+prepare", "feed", "blend"]
+    stage_ms = {k: round(1e3 * float(np.median([st[i] for st in stages[1:]])), 2) for i, k in enumerate(names)}
+    return mpix / dt, 1e3 * dt, pano, mask, stage_ms
 
 
 def run_ours(args, rank, local_rank, world):
@@ -468,8 +476,8 @@ def run_ours(args, rank, local_rank, world):
     # the same step through the drop-in Warper / Blender classes (what stitcher.py calls), host ndarrays in and out
     dropin = None
     if rank == 0 and not args.no_dropin:
-        dv, dms, dpano, dmask = dropin_e2e(cfg, imgs)
-        dropin = {"value": dv, "unit": UNIT, "ms_per_step": dms, "h2d_bytes_per_step": n * src_bytes, "d2h_bytes_per_step": ph * pw * 4,
+        dv, dms, dpano, dmask, dstages = dropin_e2e(cfg, imgs)
+        dropin = {"value": dv, "unit": UNIT, "ms_per_step": dms, "stage_ms": dstages, "h2d_bytes_per_step": n * src_bytes, "d2h_bytes_per_step": ph * pw * 4,
                   "identical_to_compositor": bool(np.array_equal(dpano, pano) and np.array_equal(dmask, pmask)),
                   "api": "stitching_b200.Warper.warp_images / create_and_warp_masks / warp_rois + Blender.prepare / feed / blend "
                          "(the calls of stitcher.py:185-189, 241-259): pageable host ndarrays in and out, one synchronous call per image and stage"}

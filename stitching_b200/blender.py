@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib, device_array
+from . import _lib, device_array, host_pool
 from .stitching_error import StitchingError
 
 
@@ -84,9 +84,9 @@ class _NativeBlender:
         if self.roi is None:
             raise StitchingError("blend() before prepare()")
         _, _, w, h = self.roi
-        dst = np.empty((h, w, 3), np.uint8)
-        msk = np.empty((h, w), np.uint8)
-        s16 = np.empty((h, w, 3), np.int16) if want_s16 else None
+        dst = host_pool.empty((h, w, 3), np.uint8)  # page-locked: the panorama is the largest copy of a stitch
+        msk = host_pool.empty((h, w), np.uint8)
+        s16 = host_pool.empty((h, w, 3), np.int16) if want_s16 else None
         _lib.check(
             _lib.lib().sb_blender_blend(
                 self._h, dst.ctypes.data_as(C.c_void_p), w * 3, msk.ctypes.data_as(C.c_void_p), w,

@@ -778,8 +778,11 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
     const int slot = (int)(t % SB_PIPE_DEPTH);
     const std::vector<uint8_t *> &sdev = slot ? c->src_devx[slot - 1] : c->src_dev;
     const PanoOut &o = slot ? c->outx[slot - 1] : c->out;
-    // sources of this slot are free once the previous compute that read them has finished
-    if (t >= SB_PIPE_DEPTH) SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
+    // sources of this slot are free once the previous compute that read them has finished; on a slot's first use
+    // that is whatever upload() / run() / sb_compositor_time() queued on the compute stream before this submit
+    // (download() is synchronous, so the output buffers need no such guard)
+    if (t < SB_PIPE_DEPTH) SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
+    SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
     for (int i = 0; i < c->n; ++i)
         SB_CUDA(sb_copy2d(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
                                   cudaMemcpyHostToDevice, c->h2d));

@@ -12,7 +12,7 @@ from statistics import median
 
 import numpy as np
 
-from . import _lib, device_array
+from . import _lib, device_array, host_pool
 from .stitching_error import StitchingError
 
 
@@ -111,8 +111,9 @@ class Warper:
         L = _lib.lib()
         _lib.check(L.sb_warp_roi(wtype, scale, _fp(K), _fp(R), int(size[0]), int(size[1]), rect), "sb_warp_roi")
         w, h = rect[2], rect[3]
-        out = np.empty((h, w, 3), np.uint8) if want_image else None
-        msk = np.empty((h, w), np.uint8) if want_mask else None
+        # page-locked result arrays (host_pool): one DMA instead of page faults + a staged copy
+        out = host_pool.empty((h, w, 3), np.uint8) if want_image else None
+        msk = host_pool.empty((h, w), np.uint8) if want_mask else None
         # the arrays are filled as always; the device copy of the IMAGE stays alive behind it (device_array.DeviceBacked)
         # so that cropping (slicing), ExposureErrorCompensator.apply and Blender.feed can go on without another upload.
         # Masks stay plain writable ndarrays: the reference hands them to cv2 calls that write into them
