@@ -141,11 +141,25 @@ SB_API int sb_blender_feed(sb_blender *b, const void *img, int img_is_s16, size_
  * rectangle (mx, my, w, h) of a 1-channel twin (mask_dev != NULL) or from the host (mask_host) */
 SB_API int sb_blender_feed_dev(sb_blender *b, const sb_devimg *img, int ix, int iy, const sb_devimg *mask_dev, int mx, int my,
                                const uint8_t *mask_host, size_t mask_pitch, int w, int h, int tl_x, int tl_y);
+
 /* blender.py:43-48 Blender.blend(): ::blend + cv.convertScaleAbs.  dst is uint8 HxWx3 of the prepared
  * roi size, dst_mask uint8 HxW; dst_s16 (nullable) additionally receives the int16 result before
  * convertScaleAbs (pitch in bytes).  The blender returns to the un-prepared state. */
 SB_API int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst_mask, size_t mask_pitch,
                             int16_t *dst_s16, size_t s16_pitch);
+
+/* ---------------------------------------------------------------------------------------------
+ * Timelapser  (stitching/timelapser.py) -- the other consumer of warped frames (stitcher.py:249-252)
+ * ------------------------------------------------------------------------------------------- */
+/* timelapser.py:40-52 Timelapser.process_frame + get_frame -> cv.detail.Timelapser(AS_IS | CROP).process / getDst +
+ * cv.convertScaleAbs: the uint8 frame of the prepared roi (`roi` = x, y, w, h: cv.detail.resultRoi of the warped rects for
+ * "as_is", resultRoiIntersection for "crop", timelapser.py:36-37 initialize) that is zero except for ONE warped image
+ * pasted at its corner (tlx, tly); pixels outside the roi are dropped, values shown as min(|v|, 255).
+ * The image comes from the host (`img`: uint8 x3, or int16 x3 when is_s16, pitch in bytes) or, when `dev` is given, from
+ * the rectangle (dev_x, dev_y, w, h) of a warped image that still lies in device memory (sb_warp_keep). */
+SB_API int sb_timelapse_frame(const void *img, int is_s16, size_t pitch, const sb_devimg *dev, int dev_x, int dev_y, int w, int h,
+                              int tlx, int tly, const int roi[4], uint8_t *dst, size_t dst_pitch);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Fused compositor: warp + blend with every intermediate resident in HBM.

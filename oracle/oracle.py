@@ -261,6 +261,46 @@ def result_roi(corners, sizes):
     return (tlx, tly, brx - tlx, bry - tly)
 
 
+def result_roi_intersection(corners, sizes):
+    """cv.detail.resultRoiIntersection: the rectangle every image covers, built as cv::Rect(Point tl, Point br) -- a
+    constructor that orders its two corners, so an EMPTY intersection comes back as the (positive-sized) gap rectangle."""
+    tlx = max(c[0] for c in corners)
+    tly = max(c[1] for c in corners)
+    brx = min(c[0] + s[0] for c, s in zip(corners, sizes))
+    bry = min(c[1] + s[1] for c, s in zip(corners, sizes))
+    return (min(tlx, brx), min(tly, bry), abs(brx - tlx), abs(bry - tly))
+
+
+class Timelapser:
+    """Restatement of stitching/timelapser.py:7-56 (cv.detail.Timelapser AS_IS / CROP): every frame is a zeroed canvas of
+    the prepared roi -- resultRoi for "as_is", resultRoiIntersection for "crop" -- with ONE warped image pasted at its
+    corner (pixels outside the canvas dropped), then |.| saturated to uint8 (timelapser.py:44-52: int16 -> float32 ->
+    convertScaleAbs)."""
+
+    def __init__(self, timelapse="no"):
+        self.timelapse_type = timelapse
+        self.do_timelapse = timelapse in ("as_is", "crop")
+        self.roi = None
+        self._dst = None
+
+    def initialize(self, corners, sizes):
+        self.roi = result_roi(corners, sizes) if self.timelapse_type == "as_is" else result_roi_intersection(corners, sizes)
+        self._dst = np.zeros((max(self.roi[3], 0), max(self.roi[2], 0), 3), np.int16)
+
+    def process_frame(self, img, corner):
+        img = np.asarray(img).astype(np.int16)  # timelapser.py:42
+        x, y, w, h = self.roi
+        self._dst[...] = 0
+        dx, dy = int(corner[0]) - x, int(corner[1]) - y
+        x0, y0 = max(dx, 0), max(dy, 0)
+        x1, y1 = min(dx + img.shape[1], w), min(dy + img.shape[0], h)
+        if x1 > x0 and y1 > y0:
+            self._dst[y0:y1, x0:x1] = img[y0 - dy:y1 - dy, x0 - dx:x1 - dx]
+
+    def get_frame(self):
+        return convert_scale_abs(self._dst)
+
+
 class Blender:
     """Restatement of stitching/blender.py:5-56 on top of the C oracle (same method names)."""
 

@@ -9,6 +9,7 @@ from . import exposure_error_compensator, images, seam_finder  # noqa: F401
 from .blender import Blender  # noqa: F401
 from .compositor import Compositor  # noqa: F401
 from .stitching_error import StitchingError, StitchingWarning  # noqa: F401
+from .timelapser import Timelapser  # noqa: F401
 from .warper import Warper  # noqa: F401
 
 __version__ = "0.1.0"
@@ -43,15 +44,16 @@ def install(stitching_module=None):
             return None
 
     for mod, names in (
-        ("warper", ("Warper",)), ("blender", ("Blender",)), ("stitcher", ("Warper", "Blender")),
-        ("cropper", ("Blender",)), ("seam_finder", ("Blender",)), ("verbose", ("Warper", "Blender")),
+        ("warper", ("Warper",)), ("blender", ("Blender",)), ("timelapser", ("Timelapser",)),
+        ("stitcher", ("Warper", "Blender", "Timelapser")),
+        ("cropper", ("Blender",)), ("seam_finder", ("Blender",)), ("verbose", ("Warper", "Blender", "Timelapser")),
     ):
         m = module(mod)
         if m is None:
             continue
         for name in names:
             if hasattr(m, name):
-                setattr(m, name, {"Warper": Warper, "Blender": Blender}[name])
+                setattr(m, name, {"Warper": Warper, "Blender": Blender, "Timelapser": Timelapser}[name])
     # the FINAL-resolution step of the seam finder (seam_finder.py:38-43); stitcher.py calls it through the class
     sf = module("seam_finder")
     if sf is not None:

@@ -95,6 +95,8 @@ SIGNATURES = [
     ("sb_compositor_shard_slab", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     ("sb_device_copy", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("sb_selftest_division", C.c_int, [C.c_ulonglong, C.c_ulonglong, C.c_int, C.POINTER(C.c_ulonglong)]),
+    ("sb_timelapse_frame", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.c_void_p, C.c_size_t]),
     ("sb_host_alloc", C.c_void_p, [C.c_size_t]),
     ("sb_host_free", None, [C.c_void_p]),
     ("sb_comm_unique_id", C.c_int, [c_u8_p]),

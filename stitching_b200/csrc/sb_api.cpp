@@ -142,7 +142,7 @@ static int warp_impl(int warp_type, float scale, const float K[9], const float R
             SB_TRY(dev_alloc((void **)&d_img, (size_t)w * 3 * h, s));  // survives the call inside the handle
         else
             SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
-        SB_CUDA(cudaMemcpy2DAsync(d_src, (size_t)src_w * 3, src, src_pitch, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, s));
+        SB_CUDA(sb_copy2d(d_src, (size_t)src_w * 3, src, src_pitch, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, s));
         job.src = d_src;
         job.spitch = (long long)src_w * 3;
         job.dst_rgb = d_img;
@@ -157,9 +157,9 @@ static int warp_impl(int warp_type, float scale, const float K[9], const float R
         job.mask_pitch = w;
     }
     int rc = launch_warp(&job, 1, s);
-    if (rc == SB_OK && dst_img && cudaMemcpy2DAsync(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    if (rc == SB_OK && dst_img && sb_copy2d(dst_img, dst_pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "cudaMemcpy2DAsync", __FILE__, __LINE__);
-    if (rc == SB_OK && dst_mask && cudaMemcpy2DAsync(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    if (rc == SB_OK && dst_mask && sb_copy2d(dst_mask, mask_pitch, d_mask, w, w, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "cudaMemcpy2DAsync", __FILE__, __LINE__);
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
     if (rc != SB_OK) {
@@ -221,7 +221,7 @@ int seam_resize_device(const uint8_t *seam_host, size_t seam_pitch, int sw, int 
     std::vector<int> tx((size_t)4 * w), ty((size_t)4 * h);
     resize_linear_taps(sw, w, true, tx.data());
     resize_linear_taps(sh, h, false, ty.data());
-    SB_CUDA(cudaMemcpy2DAsync(d_seam, sw, seam_host, seam_pitch, sw, sh, cudaMemcpyHostToDevice, s));
+    SB_CUDA(sb_copy2d(d_seam, sw, seam_host, seam_pitch, sw, sh, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(d_tx, tx.data(), tx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(d_ty, ty.data(), ty.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SB_TRY(launch_seam_resize(d_seam, sw, sh, d_dil, d_tx, d_ty, mask_dev, mask_pitch, dst_dev, dst_pitch, w, h, s));
@@ -308,13 +308,13 @@ int sb_gain_apply(uint8_t *img, size_t pitch, int w, int h, const float *gain_ma
     Scratch tmp(s);
     uint8_t *d_img = nullptr;
     SB_TRY(tmp.get(&d_img, (size_t)w * 3 * h));
-    SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * 3, img, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, s));
+    SB_CUDA(sb_copy2d(d_img, (size_t)w * 3, img, pitch, (size_t)w * 3, h, cudaMemcpyHostToDevice, s));
     WarpJob job;
     std::memset(&job, 0, sizeof job);
     GainData gd;
     int rc = gain_upload(&job, &gd, w, h, gain_map, gw, gh, gc, gain_scalar, s);
     if (rc == SB_OK) rc = launch_gain_apply(d_img, (long long)w * 3, w, h, job, s);
-    if (rc == SB_OK && cudaMemcpy2DAsync(img, pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    if (rc == SB_OK && sb_copy2d(img, pitch, d_img, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
         rc = SB_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = SB_ERR_CUDA;
     gain_free(&gd, s);
@@ -339,12 +339,52 @@ int sb_gain_apply_dev(sb_devimg *img, int x, int y, int w, int h, uint8_t *host,
     GainData gd;
     int rc = gain_upload(&job, &gd, w, h, gain_map, gw, gh, gc, gain_scalar, s);
     if (rc == SB_OK) rc = launch_gain_apply(view, pitch, w, h, job, s);
-    if (rc == SB_OK && host && cudaMemcpy2DAsync(host, host_pitch, view, (size_t)pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    if (rc == SB_OK && host && sb_copy2d(host, host_pitch, view, (size_t)pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s) != cudaSuccess)
         rc = SB_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess && rc == SB_OK) rc = SB_ERR_CUDA;
     gain_free(&gd, s);
     if (rc == SB_ERR_CUDA) set_error("sb_gain_apply_dev: CUDA failure");
     return rc;
+}
+
+int sb_timelapse_frame(const void *img, int is_s16, size_t pitch, const sb_devimg *dev, int dev_x, int dev_y, int w, int h, int tlx, int tly,
+                       const int roi[4], uint8_t *dst, size_t dst_pitch)
+{
+    const size_t px = is_s16 ? 6 : 3;
+    if ((!img && !dev) || !roi || !dst || w <= 0 || h <= 0 || roi[2] <= 0 || roi[3] <= 0 || dst_pitch < (size_t)roi[2] * 3 ||
+        (long long)roi[2] * roi[3] > (1ll << 31) || (!dev && pitch < (size_t)w * px) ||
+        (dev && (dev->ch != 3 || dev_x < 0 || dev_y < 0 || dev_x + w > dev->w || dev_y + h > dev->h))) {
+        set_error("sb_timelapse_frame: invalid argument");
+        return SB_ERR_INVALID;
+    }
+    SB_TRY(ensure_device());
+    cudaStream_t s = default_stream();
+    Scratch tmp(s);
+    const int cw = roi[2], ch = roi[3];
+    uint8_t *d_dst = nullptr, *d_src = nullptr;
+    SB_TRY(tmp.get(&d_dst, (size_t)cw * 3 * ch));
+    const uint8_t *src8 = nullptr;
+    const int16_t *src16 = nullptr;
+    long long spitch = 0;
+    if (dev) {
+        src8 = dev->p + ((size_t)dev_y * dev->w + dev_x) * 3;
+        spitch = (long long)dev->w * 3;
+    } else {
+        // only the rows / columns that land on the canvas travel
+        SB_TRY(tmp.get(&d_src, (size_t)w * px * h));
+        SB_CUDA(sb_copy2d(d_src, (size_t)w * px, img, pitch, (size_t)w * px, h, cudaMemcpyHostToDevice, s));
+        if (is_s16) {
+            src16 = reinterpret_cast<const int16_t *>(d_src);
+            spitch = (long long)w * 3;
+        } else {
+            src8 = d_src;
+            spitch = (long long)w * 3;
+        }
+    }
+    SB_TRY(launch_timelapse_frame(src8, src16, spitch, w, h, tlx - roi[0], tly - roi[1], d_dst, (long long)cw * 3, cw, ch, s));
+    SB_CUDA(sb_copy2d(dst, dst_pitch, d_dst, (size_t)cw * 3, (size_t)cw * 3, ch, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SB_OK;
 }
 
 int sb_resize_exact(const uint8_t *src, size_t src_pitch, int sw, int sh, int channels, uint8_t *dst, size_t dst_pitch, int dw, int dh)
@@ -368,11 +408,11 @@ int sb_resize_exact(const uint8_t *src, size_t src_pitch, int sw, int sh, int ch
     std::vector<int> tx((size_t)3 * dw), ty((size_t)3 * dh);
     resize_exact_taps(sw, dw, tx.data());
     resize_exact_taps(sh, dh, ty.data());
-    SB_CUDA(cudaMemcpy2DAsync(d_src, srow, src, src_pitch, srow, sh, cudaMemcpyHostToDevice, s));
+    SB_CUDA(sb_copy2d(d_src, srow, src, src_pitch, srow, sh, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(d_tx, tx.data(), tx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(d_ty, ty.data(), ty.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     SB_TRY(launch_resize_exact(d_src, (long long)srow, channels, d_tx, d_ty, d_dst, (long long)drow, dw, dh, s));
-    SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d_dst, drow, drow, dh, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(sb_copy2d(dst, dst_pitch, d_dst, drow, drow, dh, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }
@@ -391,9 +431,9 @@ int sb_seam_resize(const uint8_t *seam, size_t seam_pitch, int sw, int sh, const
     uint8_t *d_mask = nullptr, *d_dst = nullptr;
     SB_TRY(tmp.get(&d_mask, (size_t)w * h));
     SB_TRY(tmp.get(&d_dst, (size_t)w * h));
-    SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
+    SB_CUDA(sb_copy2d(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
     SB_TRY(seam_resize_device(seam, seam_pitch, sw, sh, d_mask, w, d_dst, w, w, h, s));
-    SB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d_dst, w, w, h, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(sb_copy2d(dst, dst_pitch, d_dst, w, w, h, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SB_OK;
 }
@@ -474,7 +514,7 @@ static int blender_feed_impl(sb_blender *b, const void *img, int img_is_s16, siz
             uint8_t *d_mask = nullptr;
             SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
             b->level0.push_back(d_mask);
-            SB_CUDA(cudaMemcpy2DAsync(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
+            SB_CUDA(sb_copy2d(d_mask, w, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, s));
             m_ptr = d_mask;
             m_pitch = (size_t)w;
         }
@@ -484,7 +524,7 @@ static int blender_feed_impl(sb_blender *b, const void *img, int img_is_s16, siz
             void *d_img = nullptr;
             SB_TRY(dev_alloc(&d_img, (size_t)w * h * px_bytes, s));
             b->level0.push_back(d_img);
-            SB_CUDA(cudaMemcpy2DAsync(d_img, (size_t)w * px_bytes, img, img_pitch, (size_t)w * px_bytes, h, cudaMemcpyHostToDevice, s));
+            SB_CUDA(sb_copy2d(d_img, (size_t)w * px_bytes, img, img_pitch, (size_t)w * px_bytes, h, cudaMemcpyHostToDevice, s));
             i_ptr = (const uint8_t *)d_img;
             i_pitch = (size_t)w * px_bytes;
         }
@@ -493,7 +533,7 @@ static int blender_feed_impl(sb_blender *b, const void *img, int img_is_s16, siz
                 uint8_t *d_mask = nullptr;
                 SB_TRY(dev_alloc((void **)&d_mask, (size_t)w * h, s));
                 b->level0.push_back(d_mask);
-                SB_CUDA(cudaMemcpy2DAsync(d_mask, w, dmask, dmask_pitch, w, h, cudaMemcpyDeviceToDevice, s));
+                SB_CUDA(sb_copy2d(d_mask, w, dmask, dmask_pitch, w, h, cudaMemcpyDeviceToDevice, s));
                 m_ptr = d_mask;
                 m_pitch = (size_t)w;
             }
@@ -597,9 +637,9 @@ int sb_blender_blend(sb_blender *b, uint8_t *dst, size_t dst_pitch, uint8_t *dst
     if (rc == SB_OK) rc = b->plan.run(out, s);
     if (rc == SB_OK) {  // (errors fall through to the clean-up below: the feeds are dropped either way)
         cudaError_t e = cudaSuccess;
-        if (dst) e = cudaMemcpy2DAsync(dst, dst_pitch, out.rgb, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && dst_mask) e = cudaMemcpy2DAsync(dst_mask, mask_pitch, out.mask, w, w, h, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && dst_s16) e = cudaMemcpy2DAsync(dst_s16, s16_pitch, out.s16, (size_t)w * 6, (size_t)w * 6, h, cudaMemcpyDeviceToHost, s);
+        if (dst) e = sb_copy2d(dst, dst_pitch, out.rgb, (size_t)w * 3, (size_t)w * 3, h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && dst_mask) e = sb_copy2d(dst_mask, mask_pitch, out.mask, w, w, h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && dst_s16) e = sb_copy2d(dst_s16, s16_pitch, out.s16, (size_t)w * 6, (size_t)w * 6, h, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = cuda_fail(e, "sb_blender_blend: copy of the result", __FILE__, __LINE__);
     }

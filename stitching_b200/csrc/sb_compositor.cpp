@@ -23,14 +23,6 @@ using namespace sb;
 
 #define SB_PIPE_DEPTH 3  // buffer sets of the pipelined submit / wait path
 
-// rows copy; a fully contiguous image goes as ONE linear transfer (the DMA engines reach PCIe line rate with those)
-static inline cudaError_t sb_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
-                                    cudaMemcpyKind kind, cudaStream_t s)
-{
-    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
-    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
-}
-
 struct sb_compositor {
     int n = 0;
     int warp_type = 0, blend_kind_requested = 0, mask_mode = 0;

@@ -253,6 +253,17 @@ int launch_wait_flags(const unsigned *flags, unsigned mask, unsigned value, cuda
 // table of a scalar gain, and the host-buffer entry's kernel (sb_warp.cu)
 void resize_f32_taps(int n_src, int n_dst, int *i0i1, float *fr);  // i0i1: 2 * n_dst ints
 void gain_scalar_lut(const double gain[3], uint8_t lut[768]);
+// rows copy; a fully contiguous image goes as ONE linear transfer (the DMA engines reach PCIe line rate with those)
+static inline cudaError_t sb_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                                    cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s);
+}
+
+// Timelapser frame: src8 (uint8 x3, pitch in bytes) or src16 (int16 x3, pitch in ELEMENTS) pasted at (dx, dy) of a cw x ch canvas
+int launch_timelapse_frame(const uint8_t *src8, const int16_t *src16, long long spitch, int sw, int sh, int dx, int dy, uint8_t *dst,
+                           long long dpitch, int cw, int ch, cudaStream_t s);
 int launch_gain_apply(uint8_t *img, long long pitch, int w, int h, const WarpJob &gain_fields, cudaStream_t s);
 // device copies of one image's gain (map + taps for a w x h target, or the scalar tables) and the WarpJob fields for them
 struct GainData {

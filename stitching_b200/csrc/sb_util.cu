@@ -1,5 +1,7 @@
 // sb_util.cu -- small utility kernels (L2 flush for benchmarking hygiene).
 #include "sb_device.cuh"
+#include <algorithm>
+
 #include "sb_launch.h"
 
 namespace sb {
@@ -79,6 +81,45 @@ int launch_wait_flags(const unsigned *flags, unsigned mask, unsigned value, cuda
 #else
     return SB_ERR_STATE;
 #endif
+}
+
+// Timelapser frame (stitching/timelapser.py:40-52 -> cv::detail::Timelapser::process + getDst + convertScaleAbs): the
+// canvas of the prepared roi, zero everywhere except ONE image pasted at (dx, dy) -- pixels that fall outside the canvas
+// are dropped -- shown as min(|v|, 255).  One pass writes every canvas byte (no memset), four canvas bytes per thread
+// where the row allows it.
+__global__ void k_timelapse_frame(const uint8_t *__restrict__ src8, const int16_t *__restrict__ src16, long long spitch, int sw, int sh, int dx,
+                                  int dy, uint8_t *__restrict__ dst, long long dpitch, int cw, int ch)
+{
+    const int y = blockIdx.y;
+    const long long row_bytes = 3ll * cw;
+    const int sy = y - dy;
+    const bool row_in = (unsigned)sy < (unsigned)sh;
+    uint8_t *drow = dst + (long long)y * dpitch;
+    for (long long b = (long long)(blockIdx.x * blockDim.x + threadIdx.x); b < row_bytes; b += (long long)gridDim.x * blockDim.x) {
+        unsigned v = 0u;
+        if (row_in) {
+            const int x = (int)(b / 3), c = (int)(b - 3ll * x), sx = x - dx;
+            if ((unsigned)sx < (unsigned)sw) {
+                if (src8) {
+                    v = src8[(long long)sy * spitch + 3ll * sx + c];
+                } else {
+                    const int q = src16[(long long)sy * spitch + 3ll * sx + c];
+                    const int a = q < 0 ? -q : q;  // |-32768| = 32768 saturates like every value above 255
+                    v = a > 255 ? 255u : (unsigned)a;
+                }
+            }
+        }
+        drow[b] = (uint8_t)v;
+    }
+}
+
+int launch_timelapse_frame(const uint8_t *src8, const int16_t *src16, long long spitch, int sw, int sh, int dx, int dy, uint8_t *dst,
+                           long long dpitch, int cw, int ch, cudaStream_t s)
+{
+    if (cw <= 0 || ch <= 0) return SB_OK;
+    const int bx = (int)std::min<long long>((3ll * cw + 255) / 256, 64);
+    launch(k_timelapse_frame, dim3(bx, ch), dim3(256), 0, s, src8, src16, spitch, sw, sh, dx, dy, dst, dpitch, cw, ch);
+    return launch_check("k_timelapse_frame");
 }
 
 // overwrite a buffer larger than L2 so that the next kernel starts from a cold cache

@@ -73,7 +73,8 @@ def synth_image(h, w, seed, noise=8):
     img = top * (1 - fy) + bot * fy
     if noise:
         img += rng.integers(-noise, noise + 1, (h, w, 3)).astype(np.float32)
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    # C-contiguous like a decoded photograph (the fancy indexing above leaves a transposed layout behind)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def noise_image(h, w, seed):

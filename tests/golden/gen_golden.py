@@ -295,6 +295,38 @@ def gen_resize():
     print("resize cases", k, [tuple(out[f"size_{i}"]) for i in range(k)])
 
 
+def gen_timelapse():
+    """Timelapser.initialize / process_frame / get_frame (stitching/timelapser.py:36-52) of the unmodified reference for
+    "as_is" and "crop": warped-image-sized frames at overlapping corners (negative ones too), int16-range inputs
+    included (the class converts with astype(int16) and shows |.| saturated)."""
+    from stitching.timelapser import Timelapser as RefTimelapser
+
+    rng = np.random.default_rng(4242)
+    out = {}
+    k = 0
+    for kind in ("as_is", "crop"):
+        for trial in range(3):
+            n = 3 + trial
+            sizes = [(int(rng.integers(20, 60)), int(rng.integers(16, 48))) for _ in range(n)]
+            corners = [(int(rng.integers(-15, 15)) + 10 * i, int(rng.integers(-12, 12))) for i in range(n)]
+            t = RefTimelapser(kind)
+            t.initialize(corners, sizes)
+            out[f"kind_{k}"] = np.array(kind)
+            out[f"corners_{k}"] = np.array(corners, np.int64)
+            out[f"sizes_{k}"] = np.array(sizes, np.int64)
+            for i, ((w, h), c) in enumerate(zip(sizes, corners)):
+                img = rigs.noise_image(h, w, 900 + 10 * k + i)
+                if trial == 2:  # values a uint8 image cannot hold: exercises |.| and the saturation of get_frame
+                    img = (img.astype(np.int16) * 3 - 300).astype(np.int16)
+                t.process_frame(img, c)
+                out[f"img_{k}_{i}"] = img
+                out[f"frame_{k}_{i}"] = t.get_frame()
+            k += 1
+    out["n"] = k
+    np.savez_compressed(os.path.join(HERE, "golden_timelapse.npz"), **out)
+    print("timelapse cases", k, [out[f"frame_{i}_0"].shape for i in range(k)])
+
+
 if __name__ == "__main__":
     print("cv2", cv.__version__)
     gen_warp()
@@ -304,6 +336,7 @@ if __name__ == "__main__":
     gen_seam()
     gen_gain()
     gen_resize()
+    gen_timelapse()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -209,6 +209,60 @@ def run_resize_goldens(resize_fn):
         assert_exact(np.asarray(resize_fn(g[f"img_{i}"], size)), g[f"out_{i}"], f"Images.resize case {i} -> {size}")
 
 
+def run_timelapse_goldens(timelapser_cls):
+    """Timelapser goldens (tests/golden/golden_timelapse.npz): initialize / process_frame / get_frame per image."""
+    g = load("golden_timelapse.npz")
+    for k in range(int(g["n"])):
+        kind = str(g[f"kind_{k}"])
+        corners = [tuple(int(v) for v in c) for c in g[f"corners_{k}"]]
+        sizes = [tuple(int(v) for v in s) for s in g[f"sizes_{k}"]]
+        t = timelapser_cls(kind)
+        t.initialize(corners, sizes)
+        for i, c in enumerate(corners):
+            t.process_frame(g[f"img_{k}_{i}"], c)
+            assert_exact(np.asarray(t.get_frame()), g[f"frame_{k}_{i}"], f"timelapse case {k} ({kind}) frame {i}")
+
+
+def timelapse_fuzz(oracle, timelapser_cls, warper_cls, rigs, scale_down, seed=77):
+    """Random rects against the oracle's restatement, int16 inputs included, and -- the pipeline's case -- frames fed from
+    warped images that still have their device twin (stitcher.py:249-252 hands Timelapser the warper's output)."""
+    rng = np.random.default_rng(seed)
+    for t in range(6):
+        kind = "as_is" if t % 2 == 0 else "crop"
+        n = int(rng.integers(2, 5))
+        sizes = [(int(rng.integers(30, 300)), int(rng.integers(20, 200))) for _ in range(n)]
+        corners = [(int(rng.integers(-40, 40)) + 25 * i, int(rng.integers(-30, 30))) for i in range(n)]
+        a, b = timelapser_cls(kind), oracle.Timelapser(kind)
+        a.initialize(corners, sizes)
+        b.initialize(corners, sizes)
+        for i, ((w, h), c) in enumerate(zip(sizes, corners)):
+            img = rigs.noise_image(h, w, 50 * t + i)
+            if t >= 4:
+                img = (img.astype(np.int32) * 300 - 38000).clip(-32768, 32767).astype(np.int16)
+            a.process_frame(img, c)
+            b.process_frame(img, c)
+            assert_exact(np.asarray(a.get_frame()), b.get_frame(), f"timelapse fuzz {t} ({kind}) frame {i}")
+    cfg = rigs.config("cfg2", scale_down)
+    cams = cfg["cameras"][1:4]
+    w = warper_cls(cfg["warper"])
+    w.set_scale(cams)
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    imgs = [rigs.synth_image(cfg["h"], cfg["w"], 9 + i) for i in range(len(cams))]
+    warped = list(w.warp_images(imgs, cams))
+    corners, wsizes = w.warp_rois(sizes, cams)
+    for kind in ("as_is", "crop"):
+        a, b = timelapser_cls(kind), oracle.Timelapser(kind)
+        a.initialize(corners, wsizes)
+        b.initialize(corners, wsizes)
+        for i, (img, c) in enumerate(zip(warped, corners)):
+            a.process_frame(img, c)               # device twin
+            b.process_frame(np.array(img), c)     # plain host copy through the oracle
+            assert_exact(np.asarray(a.get_frame()), b.get_frame(), f"timelapse of warped image {i} ({kind})")
+            a.process_frame(img[3:-2, 5:-4], (c[0] + 5, c[1] + 3))  # a cropped view keeps the twin (cropper.py:150-151)
+            b.process_frame(np.array(img[3:-2, 5:-4]), (c[0] + 5, c[1] + 3))
+            assert_exact(np.asarray(a.get_frame()), b.get_frame(), f"timelapse of cropped warped image {i} ({kind})")
+
+
 def run_gain_goldens(apply_fn):
     """ExposureErrorCompensator.apply goldens (tests/golden/golden_gain.npz): apply_fn(img, gain) -> image."""
     g = load("golden_gain.npz")

@@ -235,3 +235,27 @@ def test_stitcher_with_other_warper_types_after_install(reference_stitching, use
     pano = stitching.Stitcher(warper_type=warper_type, **SETTINGS).stitch([v.copy() for v in views])
     assert pano.ndim == 3 and pano.dtype == np.uint8 and (pano.sum(axis=2) > 0).mean() > 0.3
     assert abs(pano.shape[0] - ref_pano.shape[0]) <= 40 and abs(pano.shape[1] - ref_pano.shape[1]) <= 40
+
+
+def test_timelapse_run_after_install(reference_stitching, use_emu, tmp_path):
+    """Stitcher(timelapse="as_is") after install(): the warped FINAL-resolution frames go to the drop-in Timelapser
+    (stitcher.py:242-252) instead of the blender; one "fixed_" file per input appears next to the inputs, each the frame of
+    the whole panorama roi with one image in it."""
+    stitching, cv = reference_stitching
+    import stitching_b200
+
+    views = synthetic_views(cv)
+    names = []
+    for i, v in enumerate(views):
+        names.append(str(tmp_path / f"view{i}.png"))
+        cv.imwrite(names[-1], v)
+    stitching_b200.install(stitching)
+    assert stitching.stitcher.Timelapser is stitching_b200.Timelapser
+    out = stitching.Stitcher(timelapse="as_is", **SETTINGS).stitch(names)
+    assert out is None  # create_final_panorama returns nothing in timelapse mode (stitcher.py:257-260)
+    frames = [cv.imread(str(tmp_path / f"fixed_view{i}.png")) for i in range(len(views))]
+    assert all(f is not None and f.shape == frames[0].shape for f in frames)
+    cover = [(f.sum(axis=2) > 0) for f in frames]
+    assert all(0.1 < c.mean() < 0.9 for c in cover)                     # one image per frame, not the panorama
+    centres = [np.nonzero(c.any(axis=0))[0].mean() for c in cover]
+    assert min(abs(a - b) for i, a in enumerate(centres) for b in centres[i + 1:]) > 100  # three different places on the canvas

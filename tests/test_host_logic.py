@@ -287,6 +287,22 @@ def test_image_resize_drop_in(use_emu, oracle):
     assert images.resize_img_by_scaler(Scaler(), (120, 90), img).shape == (30, 40, 3)
 
 
+def test_timelapser_drop_in(use_emu, oracle):
+    """Timelapser (the other sink of the warped frames) through the C ABI == the reference's goldens == the oracle, from host
+    arrays and from device twins; interface constants and file naming as the reference's."""
+    from stitching_b200 import Timelapser
+
+    replay.run_timelapse_goldens(Timelapser)
+    replay.timelapse_fuzz(oracle, Timelapser, Warper, rigs, 25)
+    t = Timelapser("crop", "x_")
+    assert (Timelapser.TIMELAPSE_CHOICES, Timelapser.DEFAULT_TIMELAPSE, Timelapser.DEFAULT_TIMELAPSE_PREFIX) == (("no", "as_is", "crop"), "no", "fixed_")
+    assert t.do_timelapse and t.get_fixed_filename("/a/b/c.jpg") == "/a/b/x_c.jpg"
+    off = Timelapser()
+    assert not off.do_timelapse and off.timelapser is None
+    with pytest.raises(AttributeError):
+        off.initialize([(0, 0)], [(4, 4)])
+
+
 def test_exposure_gain_drop_in_and_fused(use_emu, oracle):
     """ExposureErrorCompensator.apply through the C ABI == the reference's goldens == the oracle; the fused
     Compositor.set_gain == warp -> apply -> feed."""

@@ -43,3 +43,8 @@ def test_oracle_image_resize_goldens(oracle):
 def test_oracle_gain_apply_goldens(oracle):
     """ExposureErrorCompensator.apply of the reference (all five compensators) == the oracle's restatement."""
     replay.run_gain_goldens(oracle.gain_apply)
+
+
+def test_oracle_timelapse_goldens(oracle):
+    """Timelapser.process_frame / get_frame of the reference (cv.detail.Timelapser AS_IS / CROP) == the oracle's restatement."""
+    replay.run_timelapse_goldens(oracle.Timelapser)

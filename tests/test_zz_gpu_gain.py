@@ -64,3 +64,11 @@ def test_compositor_with_the_other_projections_on_gpu(cuda_lib, oracle):
 
     test_host_logic._compositor_other_projections(oracle, ["fisheye", "stereographic", "compressedPlaneA1.5B1", "compressedPlanePortraitA2B1", "paniniA2B1",
                                                            "paniniPortraitA1.5B1", "mercator", "transverseMercator"])
+
+
+def test_timelapser_goldens_and_fuzz(cuda_lib, oracle):
+    """Timelapser frames on the device: goldens, fuzz against the oracle, frames from device twins."""
+    from stitching_b200 import Timelapser
+
+    replay.run_timelapse_goldens(Timelapser)
+    replay.timelapse_fuzz(oracle, Timelapser, Warper, rigs, 4)
