@@ -194,6 +194,11 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
     float sharp;
     derive_blend_params(rig->blend_kind, rig->blend_strength, roi, &kind, &nbr, &sharp);
     SB_TRY(c->plan.set_geometry(kind, nbr, sharp, roi));
+    {
+        // the mask byte of a warped pixel is the validity test's 0 / 255 until a caller supplies masks (SB_PD_BIN=0: A/B switch)
+        const char *e = getenv("SB_PD_BIN");
+        c->plan.binary_masks = !(e && e[0] == '0');
+    }
     for (int i = 0; i < n; ++i) {
         FeedDesc f;
         std::memset(&f, 0, sizeof f);
@@ -278,7 +283,7 @@ static int shard_pyrdown(sb_compositor *c, cudaStream_t s, int l)
         mw = std::max(mw, P.imgs[i].pw >> (l + 1));
         mh = std::max(mh, P.imgs[i].ph >> (l + 1));
     }
-    return launch_pyrdown(P.imgs_dev, P.imgs.data(), P.pyr_dev + (size_t)l * n, c->first, c->count, l, mw, mh, s);
+    return launch_pyrdown(P.imgs_dev, P.imgs.data(), P.pyr_dev + (size_t)l * n, c->first, c->count, l, mw, mh, s, P.binary_masks);
 }
 
 // sharded step, local part: pyramids of the own images, then the partial sums every neighbour needs
@@ -632,6 +637,7 @@ int sb_compositor_set_mask(sb_compositor *c, int i, const uint8_t *mask, size_t 
     c->jobs[i].blend_mask = c->usermask_dev[i];
     c->jobs[i].blend_mask_pitch = w;
     c->jobs[i].blend_mask_and = 0;
+    c->plan.binary_masks = false;  // a caller's mask may hold gray values
     for (auto &jx : c->jobsx)
         if (!jx.empty()) {
             jx[i].blend_mask = c->usermask_dev[i];
@@ -663,6 +669,7 @@ int sb_compositor_set_seam_mask(sb_compositor *c, int i, const uint8_t *seam, si
     c->jobs[i].blend_mask = c->usermask_dev[i];
     c->jobs[i].blend_mask_pitch = w;
     c->jobs[i].blend_mask_and = 1;
+    c->plan.binary_masks = false;  // the resized seam mask is bilinear: gray along the seam
     for (auto &jx : c->jobsx)
         if (!jx.empty()) {
             jx[i].blend_mask = c->usermask_dev[i];

@@ -3,11 +3,20 @@
 // Replaces createWeightMap of cv.detail_FeatherBlender (stitching/blender.py:34-36, :41):
 // distanceTransform(mask, DIST_L1, 3) + multiply + threshold(TRUNC 1).  The exact city-block distance is separable:
 // d(x,y) = min_y' ( r(x,y') + |y - y'| ) with r = distance along the row to the nearest zero of that row.
-//   rows:    one warp per row; per 32-pixel chunk a ballot gives the zero positions, clz / ffs the nearest zero to the
-//            left / right inside the chunk, a carried index the nearest one in earlier chunks.  Two coalesced sweeps.
-//   columns: one thread per column (coalesced across the warp), a downward and an upward min-plus sweep; the upward
-//            sweep writes the weight.  All images of the blend in one launch each.
+//   rows:    one warp per row; per 32-pixel chunk a ballot gives the zero positions.  The ballots of a whole row stay in
+//            registers (lane c & 31 keeps the word of chunk c), two warp scans turn them into "nearest zero before /
+//            after this chunk", and one store per chunk writes min(x - left zero, right zero - x): every mask byte is
+//            loaded once, nothing is read back, no load waits for a carried value (k_dt_rows_bits; rows wider than
+//            32 * 32 * DT_WORDS pixels take the two-sweep kernel k_dt_rows_warp).
+//   columns: with slope-1 costs the min-plus sweeps are prefix minima: going down d(y) = y + min_{j<=y}(r(j) - j), going
+//            up d(y) = -y + min_{j>=y}(r(j) + j).  A column is cut into SB_DT_CHUNKS row chunks with one thread each:
+//            k_dt_cols_summary reduces every chunk to its two minima, k_dt_cols_apply combines the minima of the chunks
+//            above / below into carries and walks its own chunk down and up -- the serial chain is h / 32 rows instead
+//            of 2 h (the one-thread-per-column sweeps of k_dt_cols_batched took 1.1 of the 1.5 ms of a 16 x 2000x1500
+//            feather blend).  All images of the blend in one launch each.
 // "No zero anywhere" stays at DT_INF and becomes weight 1, as with OpenCV (the image border is not a zero).
+#include <cstdlib>
+
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -54,6 +63,141 @@ __global__ void __launch_bounds__(256) k_dt_rows_warp(const FeedImage *__restric
     }
 }
 
+// ---- rows, one pass --------------------------------------------------------------------------------------------------
+constexpr int DT_WORDS = 8;  // ballot words a lane keeps: rows up to 32 * 32 * 8 = 8192 pixels
+
+__global__ void __launch_bounds__(256) k_dt_rows_bits(const FeedImage *__restrict__ imgs)
+{
+    grid_dependency_sync();
+    const FeedImage &im = imgs[blockIdx.y];
+    const int y = blockIdx.x * 8 + threadIdx.y, lane = threadIdx.x, w = im.w;
+    if (y >= im.h) return;  // warp-uniform
+    const int nchunks = (w + 31) >> 5;
+    unsigned word[DT_WORDS];  // word[k]: zero positions of chunk 32 k + lane
+#pragma unroll
+    for (int k = 0; k < DT_WORDS; ++k) {
+        word[k] = 0u;
+        if (32 * k < nchunks) {  // warp-uniform
+#pragma unroll 4
+            for (int c = 32 * k; c < min(32 * k + 32, nchunks); ++c) {
+                const int x = 32 * c + lane;
+                const bool inb = x < w;
+                const unsigned zeros = __ballot_sync(FULL, inb && mask_at(im, inb ? x : 0, y) == 0u);
+                if (lane == (c & 31)) word[k] = zeros;
+            }
+        }
+    }
+    // column of the nearest zero in the chunks before / after each chunk: an exclusive max- / min-scan over the chunks
+    int left[DT_WORDS], right[DT_WORDS];
+    int carry = -(1 << 30);
+#pragma unroll
+    for (int k = 0; k < DT_WORDS; ++k) {
+        left[k] = carry;
+        if (32 * k < nchunks) {
+            int v = word[k] ? 32 * (32 * k + lane) + 31 - __clz(word[k]) : -(1 << 30);  // last zero of the own chunk
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = (int)__shfl_up_sync(FULL, (unsigned)v, d);
+                if (lane >= d) v = max(v, o);
+            }
+            int ex = (int)__shfl_up_sync(FULL, (unsigned)v, 1);  // inclusive -> exclusive
+            if (lane == 0) ex = -(1 << 30);
+            left[k] = max(ex, carry);
+            carry = max(carry, (int)__shfl_sync(FULL, (unsigned)v, 31));
+        }
+    }
+    carry = 1 << 30;
+#pragma unroll
+    for (int k = DT_WORDS - 1; k >= 0; --k) {
+        right[k] = carry;
+        if (32 * k < nchunks) {
+            int v = word[k] ? 32 * (32 * k + lane) + __ffs(word[k]) - 1 : (1 << 30);  // first zero of the own chunk
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = (int)__shfl_down_sync(FULL, (unsigned)v, d);
+                if (lane + d < 32) v = min(v, o);
+            }
+            int ex = (int)__shfl_down_sync(FULL, (unsigned)v, 1);
+            if (lane == 31) ex = 1 << 30;
+            right[k] = min(ex, carry);
+            carry = min(carry, (int)__shfl_sync(FULL, (unsigned)v, 0));
+        }
+    }
+    int *d = (int *)im.fw + (long long)y * w;
+#pragma unroll
+    for (int k = 0; k < DT_WORDS; ++k) {
+        if (32 * k < nchunks) {
+            for (int c = 32 * k; c < min(32 * k + 32, nchunks); ++c) {
+                const int src = c & 31, x = 32 * c + lane;
+                const unsigned zeros = __shfl_sync(FULL, word[k], src);
+                const int lc = (int)__shfl_sync(FULL, (unsigned)left[k], src), rc = (int)__shfl_sync(FULL, (unsigned)right[k], src);
+                const unsigned le = zeros & (FULL >> (31 - lane)), ge = zeros & (FULL << lane);
+                const int lz = le ? 32 * c + 31 - __clz(le) : lc;
+                const int nz = ge ? 32 * c + __ffs(ge) - 1 : rc;
+                if (x < w) d[x] = min(min(x - lz, nz - x), DT_INF);
+            }
+        }
+    }
+}
+
+// ---- columns, chunked prefix minima ------------------------------------------------------------------------------------
+__device__ __forceinline__ void dt_chunk(int h, int ty, int *y0, int *y1)
+{
+    const int rows = (h + SB_DT_CHUNKS - 1) / SB_DT_CHUNKS;
+    *y0 = min(ty * rows, h);
+    *y1 = min(*y0 + rows, h);
+}
+
+__global__ void __launch_bounds__(256) k_dt_cols_summary(const FeedImage *__restrict__ imgs)
+{
+    const FeedImage &im = imgs[blockIdx.z];
+    const int x = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y, w = im.w;
+    if (x >= w) return;
+    int y0, y1;
+    dt_chunk(im.h, ty, &y0, &y1);
+    const int *r = (const int *)im.fw + x;
+    int dn = 1 << 30, up = 1 << 30;
+#pragma unroll 8
+    for (int y = y0; y < y1; ++y) {
+        const int v = r[(long long)y * w];
+        dn = min(dn, v - y);
+        up = min(up, v + y);
+    }
+    im.dts[ty * w + x] = dn;
+    im.dts[(SB_DT_CHUNKS + ty) * w + x] = up;
+}
+
+__global__ void __launch_bounds__(256) k_dt_cols_apply(const FeedImage *__restrict__ imgs, float sharpness)
+{
+    const FeedImage &im = imgs[blockIdx.z];
+    const int x = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y, w = im.w;
+    if (x >= w) return;
+    int y0, y1;
+    dt_chunk(im.h, ty, &y0, &y1);
+    if (y0 >= y1) return;
+    int run = 1 << 30;  // min over the chunks above of r(j) - j
+    for (int t = 0; t < ty; ++t) run = min(run, im.dts[t * w + x]);
+    int *d = (int *)im.fw + x;
+#pragma unroll 8
+    for (int y = y0; y < y1; ++y) {
+        run = min(run, d[(long long)y * w] - y);
+        d[(long long)y * w] = run + y;  // distance to the nearest zero at or above (may exceed DT_INF: "none")
+    }
+    run = 1 << 30;      // min over the chunks below of r(j) + j
+    for (int t = ty + 1; t < SB_DT_CHUNKS; ++t) run = min(run, im.dts[(SB_DT_CHUNKS + t) * w + x]);
+    float *f = (float *)im.fw + x;
+#pragma unroll 8
+    for (int y = y1 - 1; y >= y0; --y) {
+        // inside the own chunk the downward distances stand in for r: d_down(j) + j - y >= the true distance through
+        // row j and equals it for the zero's own row (derivation in DESIGN.md 3.3)
+        const int dd = d[(long long)y * w];
+        run = min(run, dd + y);
+        const int dist_i = min(dd, run - y);
+        const float dist = dist_i >= DT_INF ? 3.402823466e+38f : (float)dist_i;
+        f[(long long)y * w] = fminf(fmul(dist, sharpness), 1.f);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_dt_cols_batched(const FeedImage *__restrict__ imgs, float sharpness)
 {
     const FeedImage &im = imgs[blockIdx.y];
@@ -86,8 +230,23 @@ int launch_feather_weights_fast(const FeedImage *imgs_dev, const FeedImage *imgs
         mh = mh > imgs_host[i].h ? mh : imgs_host[i].h;
     }
     if (n <= 0 || mw <= 0 || mh <= 0) return SB_OK;
-    launch_lanes(k_dt_rows_warp, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
-    launch(k_dt_cols_batched, dim3(div_up(mw, 128), n), dim3(128), 0, s, imgs_dev, sharpness);
+    bool scratch = true;
+    for (int i = 0; i < n; ++i) scratch = scratch && imgs_host[i].dts != nullptr;
+    static const bool old_kernels = [] {
+        const char *e = getenv("SB_DT");
+        return e && e[0] == '0';  // SB_DT=0: the round-1 sweeps (A/B)
+    }();
+    if (mw <= 32 * 32 * DT_WORDS && !old_kernels)
+        launch_lanes(k_dt_rows_bits, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
+    else
+        launch_lanes(k_dt_rows_warp, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
+    if (scratch && !old_kernels) {
+        const dim3 grid(div_up(mw, 32), SB_DT_CHUNKS / 8, n), block(32, 8);
+        launch(k_dt_cols_summary, grid, block, 0, s, imgs_dev);
+        launch(k_dt_cols_apply, grid, block, 0, s, imgs_dev, sharpness);
+    } else {
+        launch(k_dt_cols_batched, dim3(div_up(mw, 128), n), dim3(128), 0, s, imgs_dev, sharpness);
+    }
     return launch_check("k_dt_*");
 }
 

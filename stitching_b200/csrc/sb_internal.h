@@ -109,6 +109,7 @@ struct Level {
     long long plane;   // elements between colour planes of g
 };
 
+#define SB_DT_CHUNKS 32    // row chunks per column in the parallel column pass of the L1 distance transform
 struct FeedImage {
     // level 0 (one of the two layouts)
     const uint32_t *rgbm;  // packed u8x3 + mask
@@ -123,6 +124,7 @@ struct FeedImage {
     int pw, ph;            // padded rect size (multiples of 2^nb)
     int dx, dy;            // feather / no: image origin relative to the pano roi
     const float *fw;       // feather weight map [h][w] (dense)
+    int *dts;              // feather: scratch of the distance transform's column pass, [2][SB_DT_CHUNKS][w] ints
     Level lv[SB_MAX_BANDS + 1];  // lv[0] unused
 };
 
@@ -210,8 +212,9 @@ int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mas
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)
 // `pyr` / `col`: the compact descriptors of level l for the same images (device pointers, `count` / `n` entries)
+// binary_masks: the caller guarantees that every mask byte of these images is 0 or 255 (level 0 only; sb_pyrdown_fast.cu)
 int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const PyrDesc *pyr, int first, int count, int l,
-                   int max_w, int max_h, cudaStream_t s);
+                   int max_w, int max_h, cudaStream_t s, bool binary_masks = false);
 // SB_KERNELS=simple selects the one-thread-per-pixel gather kernels everywhere (debugging / A-B parity)
 bool use_simple_kernels();
 // multiband: accumulate + normalise + collapse level l (top-down); at l == 0 writes the final outputs

@@ -156,7 +156,7 @@ int BlendPlan::allocate(cudaStream_t s)
     };
     struct Slot { size_t g, w; };
     std::vector<std::vector<Slot>> slots(n);
-    std::vector<size_t> fw_off(n, 0);
+    std::vector<size_t> fw_off(n, 0), dts_off(n, 0);
     size_t pano_off[SB_MAX_BANDS + 1] = {0};
     auto active = [&](int i) { return active_count < 0 || (i >= active_first && i < active_first + active_count); };
     if (kind == SB_BLEND_MULTIBAND) {
@@ -176,7 +176,10 @@ int BlendPlan::allocate(cudaStream_t s)
         }
     } else if (kind == SB_BLEND_FEATHER) {
         for (int i = 0; i < n; ++i)
-            if (active(i)) fw_off[i] = carve((size_t)imgs[i].w * imgs[i].h * sizeof(float));
+            if (active(i)) {
+                fw_off[i] = carve((size_t)imgs[i].w * imgs[i].h * sizeof(float));
+                dts_off[i] = carve((size_t)2 * SB_DT_CHUNKS * imgs[i].w * sizeof(int));
+            }
     }
     const size_t imgs_off = carve(sizeof(FeedImage) * (size_t)std::max(n, 1));
     const size_t panod_off = carve(sizeof(PanoLevel) * (SB_MAX_BANDS + 1));
@@ -212,7 +215,10 @@ int BlendPlan::allocate(cudaStream_t s)
             P.c = (int16_t *)(base + pano_off[l]);
         }
     } else if (kind == SB_BLEND_FEATHER) {
-        for (int i = 0; i < n; ++i) imgs[i].fw = active(i) ? (const float *)(base + fw_off[i]) : nullptr;
+        for (int i = 0; i < n; ++i) {
+            imgs[i].fw = active(i) ? (const float *)(base + fw_off[i]) : nullptr;
+            imgs[i].dts = active(i) ? (int *)(base + dts_off[i]) : nullptr;
+        }
     }
     imgs_dev = (FeedImage *)(base + imgs_off);
     pano_dev = (PanoLevel *)(base + panod_off);
@@ -363,7 +369,7 @@ int BlendPlan::run(const PanoOut &out, cudaStream_t s, const std::function<int(c
                 mw = std::max(mw, im.pw >> (l + 1));
                 mh = std::max(mh, im.ph >> (l + 1));
             }
-            SB_TRY(launch_pyrdown(imgs_dev, imgs.data(), pyr_dev + (size_t)l * n, 0, n, l, mw, mh, s));
+            SB_TRY(launch_pyrdown(imgs_dev, imgs.data(), pyr_dev + (size_t)l * n, 0, n, l, mw, mh, s, binary_masks));
             SB_TRY(note("pyrdown_l" + std::to_string(l)));
         }
         for (int l = nb; l >= 0; --l) {

@@ -32,6 +32,7 @@ class BlendPlan {
 public:
     int kind = SB_BLEND_NO;
     int nb = 0;              // effective number of bands (after clipping)
+    bool binary_masks = false;  // every fed mask byte is 0 or 255 (a compositor's validity masks): exact shortcut in pyrDown l0
     float sharpness = 0.f;
     Rect roi{0, 0, 0, 0};    // final (unpadded) pano roi
     int wp = 0, hp = 0;      // padded pano size (multiples of 2^nb)

@@ -30,10 +30,10 @@ __global__ void __launch_bounds__(PD_BX *PD_BY) k_pyrdown_gather(const FeedImage
 }  // namespace
 
 int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int count, int l, int max_w, int max_h,
-                        cudaStream_t s);  // sb_pyrdown_fast.cu
+                        cudaStream_t s, bool binary_masks);  // sb_pyrdown_fast.cu
 
 int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const PyrDesc *pyr, int first, int count, int l,
-                   int max_w, int max_h, cudaStream_t s)
+                   int max_w, int max_h, cudaStream_t s, bool binary_masks)
 {
     // max_w / max_h: largest DESTINATION level size among the images of the batch
     if (count <= 0 || max_w <= 0 || max_h <= 0) return SB_OK;
@@ -45,7 +45,7 @@ int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const 
     // on request (tests/test_host_logic.py sets SB_EMU_LANES around a small case); otherwise the gather kernel
     if (!getenv("SB_EMU_LANES")) packed = false;
 #endif
-    if (!use_simple_kernels() && packed) return launch_pyrdown_fast(pyr + first, imgs_host + first, count, l, max_w, max_h, s);
+    if (!use_simple_kernels() && packed) return launch_pyrdown_fast(pyr + first, imgs_host + first, count, l, max_w, max_h, s, binary_masks);
     dim3 block(PD_BX, PD_BY), grid(div_up(max_w, PD_BX), div_up(max_h, PD_BY), count);
     launch(k_pyrdown_gather, grid, block, 0, s, imgs_dev, first, l);
     return launch_check("k_pyrdown_gather");

@@ -19,6 +19,13 @@
 //   levels >= 1 (lane pairs r|b<<16, g per pixel + float32 weights): the own pair is one 16-byte load and the colours
 //     run through the same two-lane arithmetic; every level is written as lane pairs (one 8-byte store per pixel).
 // The float summation orders (position dependent, sb_pyramid.cuh) are per-lane constants.
+//
+// BIN (level 0, every mask byte of the batch is 0 or 255 -- the warped validity masks of a compositor without blend
+// masks): the weights w = mask * fl(1/255) are exactly 0 or 1, so every partial sum of the float pyrDown is a small
+// integer and its value does not depend on the summation order: the level-1 weight is V / 256 with V = the integer
+// 5x5 filter of the mask BITS.  The mask byte already rides through both integer passes in the spare 16-bit lane next
+// to green (V_m = 255 V <= 65280), so the float path -- half of the kernel's instructions in the profile of the generic
+// version (profiles/ncu_r02_i_*) -- disappears: V = (257 V_m + 65535) >> 16, one conversion, one exact multiply.
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -43,7 +50,7 @@ struct H1 { unsigned rb, g; float w; };
 
 // NEAR: every row index the walk produces is at most one reflection away from its range (the launcher checks the
 // geometry of all images of the batch): the border rules are two selects instead of an integer modulo per row.
-template <bool L0, bool NEAR>
+template <bool L0, bool NEAR, bool BIN>
 __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
 {
     const PyrDesc &D = descs[blockIdx.z];
@@ -97,14 +104,18 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
     auto hpass0 = [&](const Raw0 &r) -> H0 {
         const unsigned p0 = __shfl_up_sync(FULL, r.p2, 1), p1 = __shfl_up_sync(FULL, r.p3, 1);
         const unsigned p4 = __shfl_down_sync(FULL, r.p2, 1);
-        const float w2 = fmul(byte3_to_float(r.p2), SB_INV255), w3 = fmul(byte3_to_float(r.p3), SB_INV255);
-        const float w0 = __shfl_up_sync(FULL, w2, 1), w1 = __shfl_up_sync(FULL, w3, 1), w4 = __shfl_down_sync(FULL, w2, 1);
         const unsigned M = 0x00ff00ffu;
         H0 h;
         h.rb = (p0 & M) + (p4 & M) + 4u * ((p1 & M) + (r.p3 & M)) + 6u * (r.p2 & M);
         h.gm = __byte_perm(p0, 0u, 0x4341) + __byte_perm(p4, 0u, 0x4341) +
                4u * (__byte_perm(p1, 0u, 0x4341) + __byte_perm(r.p3, 0u, 0x4341)) + 6u * __byte_perm(r.p2, 0u, 0x4341);
-        h.w = tap5_h(w0, w1, w2, w3, w4, h_simd);
+        if (BIN) {
+            h.w = 0.f;  // the weight is read off the mask lane of gm after the vertical pass
+        } else {
+            const float w2 = fmul(byte3_to_float(r.p2), SB_INV255), w3 = fmul(byte3_to_float(r.p3), SB_INV255);
+            const float w0 = __shfl_up_sync(FULL, w2, 1), w1 = __shfl_up_sync(FULL, w3, 1), w4 = __shfl_down_sync(FULL, w2, 1);
+            h.w = tap5_h(w0, w1, w2, w3, w4, h_simd);
+        }
         return h;
     };
     auto fetch1 = [&](int src_row) -> Raw1 {
@@ -155,7 +166,12 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
                 const unsigned vgm = h0.gm + h4.gm + 4u * (h1.gm + h3.gm) + 6u * h2.gm + 0x00800080u;
                 const int o = y * dpitch + x;
                 dq[o] = make_uint2((vrb >> 8) & 0x00ff00ffu, (vgm >> 8) & 0xffu);
-                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
+                if (BIN) {
+                    const unsigned vm = (vgm >> 16) - 128u;                    // 255 * (filtered mask bits), <= 65280
+                    dwt[o] = fmul((float)((vm * 257u + 65535u) >> 16), 0.00390625f);
+                } else {
+                    dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
+                }
             }
             h0 = h2;
             h1 = h3;
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
 
 }  // namespace
 
-int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int count, int l, int max_w, int max_h, cudaStream_t s)
+int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int count, int l, int max_w, int max_h, cudaStream_t s, bool binary_masks)
 {
     // rows per warp: long chunks amortise the 3-row warm-up, but the small levels need more warps in flight
     long long strips = 0;
@@ -207,14 +223,18 @@ int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int coun
         near = near && (im.ph >> l) >= 4;
         if (l == 0) near = near && im.top <= im.h && im.ph - im.top - im.h <= im.h;
     }
-    if (l == 0 && near)
-        launch_lanes(k_pyrdown_walk<true, true>, grid, block, 0, s, pyr, rows);
+    if (l == 0 && binary_masks && near)
+        launch_lanes(k_pyrdown_walk<true, true, true>, grid, block, 0, s, pyr, rows);
+    else if (l == 0 && binary_masks)
+        launch_lanes(k_pyrdown_walk<true, false, true>, grid, block, 0, s, pyr, rows);
+    else if (l == 0 && near)
+        launch_lanes(k_pyrdown_walk<true, true, false>, grid, block, 0, s, pyr, rows);
     else if (l == 0)
-        launch_lanes(k_pyrdown_walk<true, false>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<true, false, false>, grid, block, 0, s, pyr, rows);
     else if (near)
-        launch_lanes(k_pyrdown_walk<false, true>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<false, true, false>, grid, block, 0, s, pyr, rows);
     else
-        launch_lanes(k_pyrdown_walk<false, false>, grid, block, 0, s, pyr, rows);
+        launch_lanes(k_pyrdown_walk<false, false, false>, grid, block, 0, s, pyr, rows);
     return launch_check("k_pyrdown_walk");
 }
 

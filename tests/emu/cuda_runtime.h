@@ -149,6 +149,7 @@ static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x - (int)d); }
 static inline unsigned __shfl_down_sync(unsigned, unsigned v, unsigned d) { return emu_warp->exchange(threadIdx.x, v, (int)threadIdx.x + (int)d); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_warp->exchange(threadIdx.x, v, src & 31); }
 static inline float __shfl_up_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_up_sync(m, __float_as_uint(v), d)); }
 static inline float __shfl_down_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_down_sync(m, __float_as_uint(v), d)); }
 

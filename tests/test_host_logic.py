@@ -246,7 +246,12 @@ def test_warp_collective_kernels_under_lane_emulation(use_emu, oracle, monkeypat
     threads that meet at every collective.  Slow, hence small rigs (level-0 and level->=1 variants, virtual halo lanes,
     border-rule templates; feather weights) against the oracle."""
     monkeypatch.setenv("SB_EMU_LANES", "1")
-    for name, sd, ncap, strength in (("cfg2", 50, 3, 5), ("cfg3", 60, 3, 20), ("cfg5", 20, 4, 5)):  # cfg5: ballot-based feather DT
+    # (the compositor's masks are the validity test's 0 / 255: level 0 takes the integer weight shortcut; the last case
+    # switches it off so that the generic float weight path of level 0 runs under the lane emulation as well)
+    for name, sd, ncap, strength in (("cfg2", 50, 3, 5), ("cfg3", 60, 3, 20), ("cfg5", 20, 4, 5), ("cfg2-generic", 50, 3, 5)):  # cfg5: ballot-based feather DT
+        if name.endswith("-generic"):
+            monkeypatch.setenv("SB_PD_BIN", "0")
+            name = name[:-8]
         cfg = rigs.config(name, sd)
         cams = cfg["cameras"][:ncap]
         imgs = [rigs.noise_image(cfg["h"], cfg["w"], 500 + i) for i in range(len(cams))]
@@ -257,6 +262,44 @@ def test_warp_collective_kernels_under_lane_emulation(use_emu, oracle, monkeypat
         c.close()
         replay.assert_exact(pano, ref["pano"], f"{name} pano through the shuffle pyrDown")
         replay.assert_exact(mask, ref["pmask"], f"{name} mask through the shuffle pyrDown")
+
+
+def test_parallel_distance_transform_under_lane_emulation(use_emu, oracle, monkeypatch):
+    """The feather weights' L1 distance transform in its parallel form -- ballot words + warp scans along the rows (several
+    words per lane for wide rows), chunked prefix minima along the columns -- against the oracle's FeatherBlender on mask
+    shapes that stress the carries: no zero at all, a single zero pixel, zero rows / columns, rows wider than 1024, fewer
+    rows than chunks, ragged last chunks."""
+    monkeypatch.setenv("SB_EMU_LANES", "1")
+    # (the lane emulation pays a 32-thread rendezvous per shuffle: small cases; tests/test_zz_gpu_gain.py runs larger ones)
+    _distance_transform_stress(oracle, [(12, 1100), (150, 37), (5, 70)])
+
+
+def _distance_transform_stress(oracle, shapes):
+    rng = np.random.default_rng(99)
+    for t, (h, w) in enumerate(shapes):
+        masks = []
+        m = np.full((h, w), 255, np.uint8)                       # no zero anywhere: weight 1 everywhere
+        masks.append(m.copy())
+        m[rng.integers(0, h), rng.integers(0, w)] = 0            # one zero pixel
+        masks.append(m.copy())
+        m = np.full((h, w), 255, np.uint8)
+        m[:, : w // 3] = 0                                       # zero columns on the left, none in the rows' right part
+        m[h // 2] = 0
+        masks.append(m.copy())
+        m = (rng.random((h, w)) > 0.002).astype(np.uint8) * 255  # sparse zeros
+        m[rng.integers(0, h)] = 255                              # ... and one row without any
+        masks.append(m)
+        for k, mask in enumerate(masks):
+            img = rigs.noise_image(h, w, 10 * t + k)
+            strength = 100 if k % 2 else 5  # soft (never saturates) and sharp (saturates after a few pixels)
+            a, b = Blender("feather", strength), oracle.Blender("feather", strength)
+            for bl in (a, b):
+                bl.prepare([(0, 0), (3, 2)], [(w, h), (w, h)])
+                bl.feed(img, mask, (0, 0))
+                bl.feed(img[::-1].copy(), mask[:, ::-1].copy(), (3, 2))
+            (pa, ma), (pb, mb) = a.blend(), b.blend()
+            replay.assert_exact(pa, pb, f"feather {h}x{w} mask {k} strength {strength}")
+            replay.assert_exact(ma, mb, f"feather mask {h}x{w} mask {k} strength {strength}")
 
 
 def test_fused_final_resolution_chain(use_emu, oracle):

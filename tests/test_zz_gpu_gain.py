@@ -72,3 +72,11 @@ def test_timelapser_goldens_and_fuzz(cuda_lib, oracle):
 
     replay.run_timelapse_goldens(Timelapser)
     replay.timelapse_fuzz(oracle, Timelapser, Warper, rigs, 4)
+
+
+def test_parallel_distance_transform_on_gpu(cuda_lib, oracle):
+    """Feather weights through the parallel L1 distance transform (ballot words + scans, chunked prefix minima) on mask shapes
+    that stress its carries, at sizes the CPU lane emulation cannot afford."""
+    import test_host_logic
+
+    test_host_logic._distance_transform_stress(oracle, [(40, 1100), (300, 37), (64, 64), (5, 70), (97, 131), (33, 2100), (700, 4500)])
