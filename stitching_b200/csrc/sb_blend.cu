@@ -39,14 +39,43 @@ __global__ void __launch_bounds__(CL_BX *CL_BY)
 // feather / no: one thread per pano pixel, images in feed order
 __global__ void __launch_bounds__(CL_BX *CL_BY) k_simple_blend(const FeedImage *__restrict__ imgs, int n, int feather, PanoOut out)
 {
+#ifndef SB_EMU
+    // the images whose rect touches this 32x8 tile, in feed order: warp 0 compacts them into shared memory (with sixteen
+    // images a pixel is covered by two or three: the per-pixel loop over all of them was most of the kernel)
+    __shared__ unsigned short list[SB_MAX_IMAGES];
+    __shared__ int list_n;
+    if (threadIdx.y == 0) {
+        const int tx0 = blockIdx.x * CL_BX, ty0 = blockIdx.y * CL_BY;
+        int cnt = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + threadIdx.x;
+            bool c = false;
+            if (i < n) {
+                const FeedImage &im = imgs[i];
+                c = tx0 < im.dx + im.w && tx0 + CL_BX > im.dx && ty0 < im.dy + im.h && ty0 + CL_BY > im.dy;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            if (c) list[cnt + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned short)i;
+            cnt += __popc(m);
+        }
+        if (threadIdx.x == 0) list_n = cnt;
+    }
+    __syncthreads();
+    const int n_cover = list_n;
+#endif
     const int x = blockIdx.x * CL_BX + threadIdx.x;
     const int y = blockIdx.y * CL_BY + threadIdx.y;
     if (x >= out.w || y >= out.h) return;
     int acc[3] = {0, 0, 0};
     float wsum = 0.f;
     unsigned mor = 0;
+#ifndef SB_EMU
+    for (int k = 0; k < n_cover; ++k) {
+        const FeedImage &im = imgs[list[k]];
+#else
     for (int i = 0; i < n; ++i) {
         const FeedImage &im = imgs[i];
+#endif
         const int X = x - im.dx, Y = y - im.dy;
         if ((unsigned)X >= (unsigned)im.w || (unsigned)Y >= (unsigned)im.h) continue;
         int g[3];

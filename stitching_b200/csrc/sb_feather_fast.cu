@@ -178,23 +178,43 @@ __global__ void __launch_bounds__(256) k_dt_cols_apply(const FeedImage *__restri
     int run = 1 << 30;  // min over the chunks above of r(j) - j
     for (int t = 0; t < ty; ++t) run = min(run, im.dts[t * w + x]);
     int *d = (int *)im.fw + x;
-#pragma unroll 8
-    for (int y = y0; y < y1; ++y) {
-        run = min(run, d[(long long)y * w] - y);
-        d[(long long)y * w] = run + y;  // distance to the nearest zero at or above (may exceed DT_INF: "none")
+    // eight rows at a time: the loads of a batch are independent of its stores (the compiler cannot know that rows do
+    // not alias and would otherwise serialise load -> store -> load down the chunk)
+    constexpr int B = 8;
+    for (int yb = y0; yb < y1; yb += B) {
+        int v[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) v[k] = yb + k < y1 ? d[(long long)(yb + k) * w] : (1 << 30);
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            run = min(run, v[k] - (yb + k));
+            v[k] = run + yb + k;  // distance to the nearest zero at or above (may exceed DT_INF: "none")
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (yb + k < y1) d[(long long)(yb + k) * w] = v[k];
     }
     run = 1 << 30;      // min over the chunks below of r(j) + j
     for (int t = ty + 1; t < SB_DT_CHUNKS; ++t) run = min(run, im.dts[(SB_DT_CHUNKS + t) * w + x]);
     float *f = (float *)im.fw + x;
-#pragma unroll 8
-    for (int y = y1 - 1; y >= y0; --y) {
+    for (int yb = y1 - 1; yb >= y0; yb -= B) {
         // inside the own chunk the downward distances stand in for r: d_down(j) + j - y >= the true distance through
         // row j and equals it for the zero's own row (derivation in DESIGN.md 3.3)
-        const int dd = d[(long long)y * w];
-        run = min(run, dd + y);
-        const int dist_i = min(dd, run - y);
-        const float dist = dist_i >= DT_INF ? 3.402823466e+38f : (float)dist_i;
-        f[(long long)y * w] = fminf(fmul(dist, sharpness), 1.f);
+        int v[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) v[k] = yb - k >= y0 ? d[(long long)(yb - k) * w] : (1 << 30);
+        float o[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int y = yb - k;
+            run = min(run, v[k] + y);
+            const int dist_i = min(v[k], run - y);
+            const float dist = dist_i >= DT_INF ? 3.402823466e+38f : (float)dist_i;
+            o[k] = fminf(fmul(dist, sharpness), 1.f);
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (yb - k >= y0) f[(long long)(yb - k) * w] = o[k];
     }
 }
 

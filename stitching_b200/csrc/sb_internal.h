@@ -212,7 +212,7 @@ int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mas
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)
 // `pyr` / `col`: the compact descriptors of level l for the same images (device pointers, `count` / `n` entries)
-// binary_masks: the caller guarantees that every mask byte of these images is 0 or 255 (level 0 only; sb_pyrdown_fast.cu)
+// binary_masks: the caller guarantees that every mask byte of these images is 0 or 255 (used for l <= 2; sb_pyrdown_fast.cu)
 int launch_pyrdown(const FeedImage *imgs_dev, const FeedImage *imgs_host, const PyrDesc *pyr, int first, int count, int l,
                    int max_w, int max_h, cudaStream_t s, bool binary_masks = false);
 // SB_KERNELS=simple selects the one-thread-per-pixel gather kernels everywhere (debugging / A-B parity)

@@ -26,6 +26,10 @@
 // 5x5 filter of the mask BITS.  The mask byte already rides through both integer passes in the spare 16-bit lane next
 // to green (V_m = 255 V <= 65280), so the float path -- half of the kernel's instructions in the profile of the generic
 // version (profiles/ncu_r02_i_*) -- disappears: V = (257 V_m + 65535) >> 16, one conversion, one exact multiply.
+// The levels built from such weights stay exact for two more steps: level-1 weights are V / 2^8 (V <= 2^8), level-2
+// weights V / 2^16, and every partial sum of the next pyrDown is an integer multiple of that unit not above 2^24 -- inside
+// the float's 24-bit significand -- so for l = 1, 2 BIN means "any summation order": the kernel evaluates one instead of
+// both.  From level 3 on the sums need up to 2^28 units and the reference's position-dependent orders matter again.
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -51,7 +55,7 @@ struct H1 { unsigned rb, g; float w; };
 // NEAR: every row index the walk produces is at most one reflection away from its range (the launcher checks the
 // geometry of all images of the batch): the border rules are two selects instead of an integer modulo per row.
 template <bool L0, bool NEAR, bool BIN>
-__global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
+__global__ void __launch_bounds__(32 * WK_WARPS, (L0 && BIN) ? 12 : 10) k_pyrdown_walk(const PyrDesc *__restrict__ descs, int rows_per_warp)
 {
     const PyrDesc &D = descs[blockIdx.z];
     const int4 da = __ldg(reinterpret_cast<const int4 *>(&D.sw));  // sw, sh, dpitch, dplane
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
         }
         const float w0 = __shfl_up_sync(FULL, r.wp.x, 1), w1 = __shfl_up_sync(FULL, r.wp.y, 1);
         const float w4 = __shfl_down_sync(FULL, r.wp.x, 1);
-        h.w = tap5_h(w0, w1, r.wp.x, r.wp.y, w4, h_simd);
+        h.w = tap5_h(w0, w1, r.wp.x, r.wp.y, w4, BIN ? true : h_simd);
         return h;
     };
 
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(32 * WK_WARPS, 10) k_pyrdown_walk(const PyrDes
                 const unsigned vg = h0.g + h4.g + 4u * (h1.g + h3.g) + 6u * h2.g + 128u;
                 const int o = y * dpitch + x;
                 dq[o] = make_uint2((vrb >> 8) & 0x00ff00ffu, vg >> 8);
-                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, v_simd);
+                dwt[o] = tap5_v(h0.w, h1.w, h2.w, h3.w, h4.w, BIN ? true : v_simd);
             }
             h0 = h2;
             h1 = h3;
@@ -231,6 +235,8 @@ int launch_pyrdown_fast(const PyrDesc *pyr, const FeedImage *imgs_host, int coun
         launch_lanes(k_pyrdown_walk<true, true, false>, grid, block, 0, s, pyr, rows);
     else if (l == 0)
         launch_lanes(k_pyrdown_walk<true, false, false>, grid, block, 0, s, pyr, rows);
+    else if (l <= 2 && binary_masks && near)  // weights still exact in any order (see the header)
+        launch_lanes(k_pyrdown_walk<false, true, true>, grid, block, 0, s, pyr, rows);
     else if (near)
         launch_lanes(k_pyrdown_walk<false, true, false>, grid, block, 0, s, pyr, rows);
     else
