@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(CL_BX *CL_BY) k_simple_blend(const FeedImage *
     bool on;
     unsigned mv;
     if (feather) {
-        const float den = fadd(wsum, SB_WEIGHT_EPS);
+        // one refined reciprocal serves the three channels (sb_device.cuh: 1e-5 <= den <= 256, |a| <= 32768: inside the
+        // ranges where the shortcut equals the IEEE division)
+        const float den = fadd(wsum, SB_WEIGHT_EPS), rr = rcp_refined(den);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv((float)(short)acc[c], den));
+        for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv_by((float)(short)acc[c], den, rr));
         on = wsum > SB_WEIGHT_EPS;
         mv = on ? 255u : 0u;
     } else {
@@ -161,10 +163,10 @@ __global__ void __launch_bounds__(CL_BX *CL_BY) k_feather_region(const __grid_co
         A.slab_w[o] = wsum;
         return;
     }
-    const float den = fadd(wsum, SB_WEIGHT_EPS);
+    const float den = fadd(wsum, SB_WEIGHT_EPS), rr = rcp_refined(den);
     int v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv((float)(short)acc[c], den));
+    for (int c = 0; c < 3; ++c) v[c] = f2s_wrap(fdiv_by((float)(short)acc[c], den, rr));
     const bool on = wsum > SB_WEIGHT_EPS;
     store_final(A.out, x - A.out_x0, y - A.out_y0, v, on, on ? 255u : 0u);
 }

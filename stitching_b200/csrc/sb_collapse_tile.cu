@@ -152,7 +152,7 @@ __device__ __forceinline__ unsigned norm_two2(unsigned a)
 }
 
 template <int LV>
-__global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const __grid_constant__ CollapseArgs A)
+__global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 5) k_collapse_tile(const __grid_constant__ CollapseArgs A)
 {
     grid_dependency_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];

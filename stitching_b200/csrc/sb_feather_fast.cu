@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(256) k_dt_rows_warp(const FeedImage *__restric
 }
 
 // ---- rows, one pass --------------------------------------------------------------------------------------------------
-constexpr int DT_WORDS = 8;  // ballot words a lane keeps: rows up to 32 * 32 * 8 = 8192 pixels
+constexpr int DT_WORDS_MAX = 8;  // ballot words a lane keeps: rows up to 32 * 32 * 8 = 8192 pixels
 
+template <int DT_WORDS>
 __global__ void __launch_bounds__(256) k_dt_rows_bits(const FeedImage *__restrict__ imgs)
 {
     grid_dependency_sync();
@@ -78,12 +79,19 @@ __global__ void __launch_bounds__(256) k_dt_rows_bits(const FeedImage *__restric
     for (int k = 0; k < DT_WORDS; ++k) {
         word[k] = 0u;
         if (32 * k < nchunks) {  // warp-uniform
-#pragma unroll 4
-            for (int c = 32 * k; c < min(32 * k + 32, nchunks); ++c) {
-                const int x = 32 * c + lane;
-                const bool inb = x < w;
-                const unsigned zeros = __ballot_sync(FULL, inb && mask_at(im, inb ? x : 0, y) == 0u);
-                if (lane == (c & 31)) word[k] = zeros;
+            // eight chunks at a time: all eight loads are in flight before the first ballot needs its value
+            for (int c0 = 32 * k; c0 < min(32 * k + 32, nchunks); c0 += 8) {
+                unsigned m[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int x = 32 * (c0 + j) + lane;
+                    m[j] = x < w ? mask_at(im, x, y) : 1u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned zeros = __ballot_sync(FULL, m[j] == 0u);
+                    if (lane == ((c0 + j) & 31)) word[k] = zeros;
+                }
             }
         }
     }
@@ -256,8 +264,10 @@ int launch_feather_weights_fast(const FeedImage *imgs_dev, const FeedImage *imgs
         const char *e = getenv("SB_DT");
         return e && e[0] == '0';  // SB_DT=0: the round-1 sweeps (A/B)
     }();
-    if (mw <= 32 * 32 * DT_WORDS && !old_kernels)
-        launch_lanes(k_dt_rows_bits, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
+    if (mw <= 32 * 32 * 2 && !old_kernels)
+        launch_lanes(k_dt_rows_bits<2>, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
+    else if (mw <= 32 * 32 * DT_WORDS_MAX && !old_kernels)
+        launch_lanes(k_dt_rows_bits<DT_WORDS_MAX>, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
     else
         launch_lanes(k_dt_rows_warp, dim3(div_up(mh, 8), n), dim3(32, 8), 0, s, imgs_dev);
     if (scratch && !old_kernels) {
