@@ -25,9 +25,12 @@
 // instruction", while the 1-D bulk copy works: tests/tools/tma_*.cu, profiles/tma_probe_r02.md.  The staging therefore
 // uses cp.async; sb_tma.cuh keeps the wrappers.)
 //
-// Scope: the plain single-GPU roles (every item a byte-fed image, whole level, uint8 image + mask output).  Slabs,
-// partial sums, int16 output and the top level stay with k_collapse_fast (launch_collapse_tile says so by returning
-// SB_ERR_STATE).  The emulation build (tests/emu) does not compile this file's kernels.
+// Scope: byte-fed images, uint8 image + mask output, whole levels or a rank's strip of one (multi-GPU: the region may start
+// anywhere even; the tile grid starts at the 64-column boundary at or left of it and quads left of the region are idle).
+// Slabs of partial sums from other ranks (ColDesc kind 1) are items too: nothing is staged for them, every quad adds its
+// four sums straight from global memory.  Producing partial sums, int16 output and the top level stay with
+// k_collapse_fast (launch_collapse_tile says so by returning SB_ERR_STATE).  The emulation build (tests/emu) does not
+// compile this file's kernels.
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
@@ -152,14 +155,14 @@ __device__ __forceinline__ unsigned norm_two2(unsigned a)
 }
 
 template <int LV>
-__global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 5) k_collapse_tile(const __grid_constant__ CollapseArgs A)
+__global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const __grid_constant__ CollapseArgs A)
 {
     grid_dependency_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<LV> &S = *reinterpret_cast<Smem<LV> *>(smem_raw);
     const TileDesc *__restrict__ tile = A.tile;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QX + tx;
-    const int tile_x = A.rx0 + blockIdx.x * TW, tile_y = A.ry0 + blockIdx.y * TH;
+    const int tile_x = (A.rx0 & ~(TW - 1)) + blockIdx.x * TW, tile_y = A.ry0 + blockIdx.y * TH;  // staged rows start at 16-byte boundaries
 
     // the collapsed level l+1 around the tile (3 planes x 10 rows x 6 chunks): in flight while the item list is built.
     // Warp ty stages plane-rows 4 ty .. 4 ty + 3, eight lanes per row, six of them with a chunk.
@@ -199,6 +202,10 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 5) k_collapse_tile(const
         const int idx = S.list[k];
         const TileDesc &d = tile[idx];
         const ColDesc &cd = A.col[idx];
+        if (__ldg(&cd.kind) == 1) {  // a slab of partial sums: read directly by the consumers (tile-uniform)
+            cp_async_commit();
+            return;
+        }
         const int4 r = __ldg(reinterpret_cast<const int4 *>(&d.x0));   // x0, y0, w, h
         const int4 o = __ldg(reinterpret_cast<const int4 *>(&d.ox));   // ox, oy, uw, uh
         ItemBuf<LV> &B = S.item[k & 1];
@@ -253,6 +260,28 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 5) k_collapse_tile(const
         __syncthreads();  // item k's windows (and C_{l+1}'s) are complete for every thread
         ItemBuf<LV> &B = S.item[k & 1];
         const TileDesc &d = tile[S.list[k]];
+        {
+            const ColDesc &cd = A.col[S.list[k]];
+            if (__ldg(&cd.kind) == 1) {
+                // partial sums of another rank over (part of) this tile: int16 wrap-around adds, the float weight sum in
+                // item order (= rank order); rect origins and sizes are even: a quad is in or out as a whole
+                const int4 r = __ldg(reinterpret_cast<const int4 *>(&cd.ox));  // ox, oy, w_l, h_l
+                const int X = tile_x + 2 * tx - r.x, Y = tile_y + 2 * ty - r.y;
+                if ((unsigned)X < (unsigned)r.z && (unsigned)Y < (unsigned)r.w) {
+                    const int pitch = __ldg(&cd.pitch), plane = __ldg(&cd.plane);
+                    const int16_t *g = cd.g;
+                    const float *w = cd.w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int o = (Y + (q >> 1)) * pitch + X + (q & 1);
+                        acc_rb[q] = __vadd2(acc_rb[q], lanes(g[o], g[2 * plane + o]));
+                        acc_g[q] += g[plane + o];
+                        wsum[q] = fadd(wsum[q], w[o]);
+                    }
+                }
+                continue;  // (tile-uniform: no thread waits at the second barrier of this iteration)
+            }
+        }
         const int4 o = __ldg(reinterpret_cast<const int4 *>(&d.ox));  // ox, oy, uw, uh
         const int bx = ((tile_x - o.x) >> 1) - 1, by = ((tile_y - o.y) >> 1) - 1;
         const int su = bx & 1;  // logical column c of the coarse window = staged column c + su
@@ -374,7 +403,7 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 5) k_collapse_tile(const
     }
 
     const int x = tile_x + 2 * tx, y = tile_y + 2 * ty;  // top-left pixel of the quad
-    if (x >= A.rx0 + A.rw || y >= A.ry0 + A.rh) return;  // (after the last barrier)
+    if (x < A.rx0 || x >= A.rx0 + A.rw || y >= A.ry0 + A.rh) return;  // (after the last barrier)
 
     // ---- blend step on lanes: words [row][0] = pixel 0 (r | b << 16), [row][1] = pixel 1, [row][2] = green of both ------
     unsigned N[2][3];
@@ -513,7 +542,7 @@ int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
         SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
         attr_set = true;
     }
-    dim3 block(QX, QY), grid(div_up(A.rw, TW), div_up(A.rh, TH));
+    dim3 block(QX, QY), grid(div_up(A.rx0 + A.rw - (A.rx0 & ~(TW - 1)), TW), div_up(A.rh, TH));
     if (l == 0)
         launch_pdl(k_collapse_tile<0>, grid, block, sizeof(Smem<0>), s, A);
     else

@@ -143,6 +143,28 @@ int BlendPlan::add_feed(const FeedDesc &f)
     return SB_OK;
 }
 
+TileDesc BlendPlan::tile_desc(const FeedImage &im, int l)
+{
+    TileDesc t;
+    std::memset(&t, 0, sizeof t);
+    t.ox = im.px >> l;
+    t.oy = im.py >> l;
+    if (l == 0) {
+        t.x0 = im.px + im.left;
+        t.y0 = im.py + im.top;
+        t.w = im.w;
+        t.h = im.h;
+    } else {
+        t.x0 = t.ox;
+        t.y0 = t.oy;
+        t.w = im.pw >> l;
+        t.h = im.ph >> l;
+    }
+    t.uw = im.pw >> (l + 1);
+    t.uh = im.ph >> (l + 1);
+    return t;
+}
+
 int BlendPlan::allocate(cudaStream_t s)
 {
     release(s);
@@ -294,32 +316,14 @@ int BlendPlan::allocate(cudaStream_t s)
         // tile kernels (sb_collapse_tile.cu): per-(level, image) rects.  Byte-fed images with storage on this device;
         // the staged copies need 16-byte rows (RGBM pitch a multiple of 4 pixels, 16-byte aligned base)
         tile_dev = nullptr;
-        bool tiles = n > 0 && nb >= 1 && active_count < 0 && collapse_tile_enabled();
-        for (int i = 0; i < n && tiles; ++i)
-            tiles = imgs[i].rgbm != nullptr && imgs[i].rgbm_pitch % 4 == 0 && ((uintptr_t)imgs[i].rgbm & 15) == 0;
+        tile_images_ok = n > 0 && nb >= 1 && collapse_tile_enabled();
+        for (int i = 0; i < n && tile_images_ok; ++i)
+            if (active(i)) tile_images_ok = imgs[i].rgbm != nullptr && imgs[i].rgbm_pitch % 4 == 0 && ((uintptr_t)imgs[i].rgbm & 15) == 0;
+        const bool tiles = tile_images_ok && active_count < 0;  // (a sharded plan builds its own item lists: ShardPlan::allocate)
         if (tiles) {
             std::vector<TileDesc> td((size_t)n * (nb + 1));
-            std::memset(td.data(), 0, sizeof(TileDesc) * td.size());
             for (int l = 0; l <= nb; ++l)
-                for (int i = 0; i < n; ++i) {
-                    const FeedImage &im = imgs[i];
-                    TileDesc &t = td[(size_t)l * n + i];
-                    t.ox = im.px >> l;
-                    t.oy = im.py >> l;
-                    if (l == 0) {
-                        t.x0 = im.px + im.left;
-                        t.y0 = im.py + im.top;
-                        t.w = im.w;
-                        t.h = im.h;
-                    } else {
-                        t.x0 = t.ox;
-                        t.y0 = t.oy;
-                        t.w = im.pw >> l;
-                        t.h = im.ph >> l;
-                    }
-                    t.uw = im.pw >> (l + 1);
-                    t.uh = im.ph >> (l + 1);
-                }
+                for (int i = 0; i < n; ++i) td[(size_t)l * n + i] = tile_desc(imgs[i], l);
             tile_dev = (TileDesc *)(base + tile_off);
             SB_CUDA(cudaMemcpyAsync(tile_dev, td.data(), sizeof(TileDesc) * td.size(), cudaMemcpyHostToDevice, s));
             SB_CUDA(cudaStreamSynchronize(s));  // `td` is a local

@@ -47,6 +47,8 @@ public:
     // tile kernels (sb_collapse_tile.cu): per-(level, image) descriptors; null when the plan does not qualify
     // (generic int16 feeds, a sharded composite): the fast kernels then do the work
     TileDesc *tile_dev = nullptr;   // [(nb+1)][n]
+    bool tile_images_ok = false;    // the images with storage on this device qualify for the tile kernels (sb_collapse_tile.cu)
+    static TileDesc tile_desc(const FeedImage &im, int l);
     // fused pyramid tail (sb_tail.cu): levels >= tail_from run in one launch; tail_from > nb: no tail
     int tail_from = 1 << 30;
     unsigned *tail_state_dev = nullptr;  // the grid barrier's two words

@@ -265,6 +265,7 @@ int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
     }
     // item lists per level: slabs of lower ranks, own images, slabs of higher ranks (= feed order)
     std::vector<ColDesc> items;
+    std::vector<TileDesc> titems;  // parallel to `items`: the rects the tile kernels test (sb_collapse_tile.cu)
     size_t offs[SB_MAX_BANDS + 2] = {0};
     for (int l = 0; l <= plan.nb; ++l) {
         offs[l] = items.size();
@@ -283,9 +284,19 @@ int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
             d.plane = L.plane;
             d.kind = 1;
             items.push_back(d);
+            TileDesc t;
+            std::memset(&t, 0, sizeof t);
+            t.x0 = t.ox = L.x0;
+            t.y0 = t.oy = L.y0;
+            t.w = L.w;
+            t.h = L.h;
+            titems.push_back(t);
         };
         for (int p = 0; p < rank; ++p) add_slab(p);
-        for (int i = first; i < first + count; ++i) items.push_back(plan.col_host[(size_t)l * n + i]);
+        for (int i = first; i < first + count; ++i) {
+            items.push_back(plan.col_host[(size_t)l * n + i]);
+            titems.push_back(BlendPlan::tile_desc(plan.imgs[i], l));
+        }
         for (int p = rank + 1; p < world; ++p) add_slab(p);
         n_items[l] = (int)(items.size() - offs[l]);
         if (n_items[l] > SB_MAX_ITEMS) {
@@ -297,6 +308,13 @@ int ShardPlan::allocate(const BlendPlan &plan, cudaStream_t s)
     if (!items.empty()) SB_CUDA(cudaMemcpyAsync(items_arena_, items.data(), items.size() * sizeof(ColDesc), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaStreamSynchronize(s));  // `items` is a local
     for (int l = 0; l <= plan.nb; ++l) items_dev[l] = (ColDesc *)items_arena_ + offs[l];
+    for (auto &t : tile_items_dev) t = nullptr;
+    if (plan.tile_images_ok && !titems.empty()) {
+        SB_TRY(dev_alloc(&tile_items_arena_, titems.size() * sizeof(TileDesc), s));
+        SB_CUDA(cudaMemcpyAsync(tile_items_arena_, titems.data(), titems.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        for (int l = 0; l <= plan.nb; ++l) tile_items_dev[l] = (TileDesc *)tile_items_arena_ + offs[l];
+    }
     return SB_OK;
 }
 
@@ -323,6 +341,9 @@ void ShardPlan::release(cudaStream_t s)
     }
     dev_free(items_arena_, s);
     items_arena_ = nullptr;
+    dev_free(tile_items_arena_, s);
+    tile_items_arena_ = nullptr;
+    for (auto &t : tile_items_dev) t = nullptr;
     dev_free(feather_items_, s);
     feather_items_ = nullptr;
 }
@@ -444,7 +465,13 @@ int ShardPlan::finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s,
         A.out_x0 = bounds[rank];
         A.out_lo = lo;
         A.out_hi = hi;
-        SB_TRY(launch_collapse_fast(A, l, plan.nb, s));
+        A.tile = tile_items_dev[l];
+        // levels 0 and 1 on shared-memory tiles when the strip qualifies (slabs are items of their own kind there)
+        const int rc = A.tile ? launch_collapse_tile(A, l, plan.nb, s) : SB_ERR_STATE;
+        if (rc == SB_ERR_STATE)
+            SB_TRY(launch_collapse_fast(A, l, plan.nb, s));
+        else
+            SB_TRY(rc);
     }
     return SB_OK;
 }

@@ -29,6 +29,7 @@ public:
     int axis = 0;                    // 0: column strips (multiband always); 1: row strips (feather, image blocks stacked vertically)
     std::vector<PeerSlab> send, recv;  // indexed by peer rank
     ColDesc *items_dev[SB_MAX_BANDS + 1] = {};
+    TileDesc *tile_items_dev[SB_MAX_BANDS + 1] = {};  // the same lists for the tile kernels (null: images do not qualify)
     int n_items[SB_MAX_BANDS + 1] = {};
     // Direct exchange over NVLink (sb_peer.cpp): every rank's receive slabs live in ONE cudaMalloc'ed arena that its
     // neighbours map with CUDA IPC; the partial-sum kernels then store their slabs straight into the owner's arena
@@ -87,6 +88,7 @@ private:
     void *feather_items_ = nullptr;  // FeatherSlab records of the slabs this rank receives (device)
     int feather_before_ = 0, feather_after_ = 0;
     void *items_arena_ = nullptr;
+    void *tile_items_arena_ = nullptr;
 };
 
 int comm_allgather_bytes(const void *mine, void *all, size_t bytes_per_rank, cudaStream_t s);  // host buffers
