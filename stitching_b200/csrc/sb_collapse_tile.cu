@@ -154,7 +154,7 @@ __device__ __forceinline__ unsigned norm_two2(unsigned a)
     return __vadd2((xb >> 1) & 0x7fff7fffu, 0xfe00fe00u);                                   // - 512 per lane
 }
 
-template <int LV>
+template <int LV, bool SLABS>
 __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const __grid_constant__ CollapseArgs A)
 {
     grid_dependency_sync();
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const
         const int idx = S.list[k];
         const TileDesc &d = tile[idx];
         const ColDesc &cd = A.col[idx];
-        if (__ldg(&cd.kind) == 1) {  // a slab of partial sums: read directly by the consumers (tile-uniform)
+        if (SLABS && __ldg(&cd.kind) == 1) {  // a slab of partial sums: read directly by the consumers (tile-uniform)
             cp_async_commit();
             return;
         }
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const
         __syncthreads();  // item k's windows (and C_{l+1}'s) are complete for every thread
         ItemBuf<LV> &B = S.item[k & 1];
         const TileDesc &d = tile[S.list[k]];
-        {
+        if (SLABS) {
             const ColDesc &cd = A.col[S.list[k]];
             if (__ldg(&cd.kind) == 1) {
                 // partial sums of another rank over (part of) this tile: int16 wrap-around adds, the float weight sum in
@@ -538,15 +538,21 @@ int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
     if (A.rw <= 0 || A.rh <= 0) return SB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0>)));
-        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0>)));
+        SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
         attr_set = true;
     }
     dim3 block(QX, QY), grid(div_up(A.rx0 + A.rw - (A.rx0 & ~(TW - 1)), TW), div_up(A.rh, TH));
-    if (l == 0)
-        launch_pdl(k_collapse_tile<0>, grid, block, sizeof(Smem<0>), s, A);
+    if (l == 0 && A.has_slabs)
+        launch_pdl(k_collapse_tile<0, true>, grid, block, sizeof(Smem<0>), s, A);
+    else if (l == 0)
+        launch_pdl(k_collapse_tile<0, false>, grid, block, sizeof(Smem<0>), s, A);
+    else if (A.has_slabs)
+        launch_pdl(k_collapse_tile<1, true>, grid, block, sizeof(Smem<1>), s, A);
     else
-        launch_pdl(k_collapse_tile<1>, grid, block, sizeof(Smem<1>), s, A);
+        launch_pdl(k_collapse_tile<1, false>, grid, block, sizeof(Smem<1>), s, A);
     return launch_check("k_collapse_tile");
 }
 #else   // SB_EMU

@@ -194,6 +194,7 @@ struct CollapseArgs {
     PanoOut out;              // level 0: final outputs; the buffer covers pano columns [out_x0, out_x0 + out.w)
     int out_x0, out_lo, out_hi;  // only columns [out_lo, out_hi) are stored (a strip's margin is not output)
     const TileDesc *tile;     // tile kernels: items of this level, same order as col (null: not available for this launch)
+    int has_slabs;            // some items are slabs of partial sums (ColDesc kind 1): the tile kernels' slab instantiation
 };
 // the shared-memory tile version of the per-level kernel for the plain single-GPU roles; returns SB_ERR_STATE when the launch
 // does not qualify (the caller then uses launch_collapse_fast)

@@ -466,6 +466,7 @@ int ShardPlan::finish(const BlendPlan &plan, const PanoOut &out, cudaStream_t s,
         A.out_lo = lo;
         A.out_hi = hi;
         A.tile = tile_items_dev[l];
+        A.has_slabs = n_items[l] > count;
         // levels 0 and 1 on shared-memory tiles when the strip qualifies (slabs are items of their own kind there)
         const int rc = A.tile ? launch_collapse_tile(A, l, plan.nb, s) : SB_ERR_STATE;
         if (rc == SB_ERR_STATE)
