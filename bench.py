@@ -504,6 +504,9 @@ def run_ours(args, rank, local_rank, world):
                       f"no flush: a step streams {total_bytes / 1e6:.0f} MB, inputs {n * src_bytes / 1e6:.0f} MB > 126 MB L2",
                 "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent {n}-image ring per GPU (no collective)",
                 "timed": "plan (roi detection, trig tables, buffers) built once outside the timed region; a step = warp + pyramids + collapse kernels",
+                "source_layout": ("one word per pixel (r | g<<8 | b<<16): every upload is followed by a repack kernel on the copy stream, outside "
+                                  "`value`'s timed region (inputs resident) and inside `e2e`'s; SB_SRC4=0 keeps the packed 3-byte sources"
+                                  if os.environ.get("SB_SRC4", "1") != "0" else "packed 3-byte sources (SB_SRC4=0)"),
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches1 - launches0), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity, "result_checksum": checksum,

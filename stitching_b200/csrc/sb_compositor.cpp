@@ -32,7 +32,10 @@ struct sb_compositor {
     std::vector<Rect> rects;           // warped rects (pano-absolute)
     std::vector<WarpJob> jobs;         // host copy
     std::vector<WarpJob> jobsx[SB_PIPE_DEPTH - 1];  // the same jobs reading the extra source buffer sets (pipelined path)
-    std::vector<uint8_t *> src_dev;    // u8x3 sources
+    std::vector<uint8_t *> src_dev;    // u8x3 sources as uploaded
+    std::vector<uint32_t *> src4_dev;  // the same, one word per pixel: what the warp kernel reads (repacked after every upload)
+    std::vector<uint32_t *> src4_devx[SB_PIPE_DEPTH - 1];
+    bool use_src4 = true;
     std::vector<uint32_t *> rgbm_dev;  // warped, packed; row pitch = width rounded up to 32 pixels (128-byte rows)
     std::vector<float *> tab_dev;
     std::vector<float *> maps_dev;     // projections that are not separable: xmap | ymap of every image (built at plan time)
@@ -74,6 +77,9 @@ static void compositor_free(sb_compositor *c)
     cudaStream_t s = c->stream ? c->stream : default_stream();
     if (c->stream) (void)cudaStreamSynchronize(c->stream);
     for (auto p : c->src_dev) dev_free(p, s);
+    for (auto p : c->src4_dev) dev_free(p, s);
+    for (auto &v : c->src4_devx)
+        for (auto p : v) dev_free(p, s);
     for (auto p : c->rgbm_dev) dev_free(p, s);
     for (auto p : c->tab_dev) dev_free(p, s);
     for (auto p : c->maps_dev) dev_free(p, s);
@@ -146,6 +152,11 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
     c->rects.resize(n);
     c->jobs.resize(n);
     c->src_dev.assign(n, nullptr);
+    c->src4_dev.assign(n, nullptr);
+    {
+        const char *e = getenv("SB_SRC4");  // SB_SRC4=0: the warp kernel reads the packed 3-byte sources (A/B switch)
+        c->use_src4 = !(e && e[0] == '0');
+    }
     c->rgbm_dev.assign(n, nullptr);
     c->tab_dev.assign(n, nullptr);
     c->maps_dev.assign(n, nullptr);
@@ -183,6 +194,10 @@ static int compositor_build(sb_compositor *c, const sb_rig *rig, int rank, int w
         }
         c->jobs[i].src = c->src_dev[i];
         c->jobs[i].spitch = (long long)c->src_w[i] * 3;
+        if (c->use_src4 && (long long)c->src_w[i] * c->src_h[i] < (1ll << 31)) {
+            SB_TRY(dev_alloc((void **)&c->src4_dev[i], ((size_t)c->src_w[i] * c->src_h[i] + 4) * sizeof(uint32_t), s));
+            c->jobs[i].src4 = c->src4_dev[i];
+        }
         c->jobs[i].dst_rgbm = c->rgbm_dev[i];
         c->jobs[i].rgbm_pitch = rgbm_pitch_of(rect[2]);
         c->warp_bytes += 3.0 * c->src_w[i] * c->src_h[i] + 4.0 * rect[2] * rect[3];
@@ -458,6 +473,11 @@ static int compositor_pipe_init(sb_compositor *c)
         for (int i = 0; i < c->n; ++i) {
             SB_TRY(dev_alloc((void **)&c->src_devx[k][i], (size_t)c->src_w[i] * 3 * c->src_h[i] + SB_SRC_PAD, s));
             c->jobsx[k][i].src = c->src_devx[k][i];
+            if (c->jobs[i].src4) {
+                if (c->src4_devx[k].empty()) c->src4_devx[k].assign(c->n, nullptr);
+                SB_TRY(dev_alloc((void **)&c->src4_devx[k][i], ((size_t)c->src_w[i] * c->src_h[i] + 4) * sizeof(uint32_t), s));
+                c->jobsx[k][i].src4 = c->src4_devx[k][i];
+            }
         }
         c->outx[k] = c->out;
         c->outx[k].rgb = nullptr;
@@ -618,6 +638,7 @@ int sb_compositor_upload(sb_compositor *c, int i, const uint8_t *src, size_t pit
     }
     SB_CUDA(sb_copy2d(c->src_dev[i], (size_t)c->src_w[i] * 3, src, pitch, (size_t)c->src_w[i] * 3, c->src_h[i],
                               cudaMemcpyHostToDevice, c->stream));
+    if (c->src4_dev[i]) SB_TRY(launch_repack_rgbx(c->src_dev[i], c->src4_dev[i], (long long)c->src_w[i] * c->src_h[i], c->stream));
     if (!pinned) SB_CUDA(cudaStreamSynchronize(c->stream));
     return SB_OK;
 }
@@ -782,9 +803,12 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
     // (download() is synchronous, so the output buffers need no such guard)
     if (t < SB_PIPE_DEPTH) SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
     SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
-    for (int i = 0; i < c->n; ++i)
+    for (int i = 0; i < c->n; ++i) {
         SB_CUDA(sb_copy2d(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
                                   cudaMemcpyHostToDevice, c->h2d));
+        uint32_t *s4 = slot ? (c->src4_devx[slot - 1].empty() ? nullptr : c->src4_devx[slot - 1][i]) : c->src4_dev[i];
+        if (s4) SB_TRY(launch_repack_rgbx(sdev[i], s4, (long long)c->src_w[i] * c->src_h[i], c->h2d));  // behind its copy, on the copy stream
+    }
     SB_CUDA(cudaEventRecord(c->e_h2d[slot], c->h2d));
     SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_h2d[slot], 0));
     // the output buffers of this slot are free once their previous download has finished

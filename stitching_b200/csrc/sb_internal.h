@@ -67,6 +67,7 @@ struct WarpJob {
     const uint8_t *src;  // u8x3 interleaved
     int sw, sh;
     long long spitch;    // bytes
+    const uint32_t *src4;  // optional: the same image as r | g<<8 | b<<16 (byte 3 zero), sw pixels per row (compositor: repacked at upload)
     uint8_t *dst_rgb;    // u8x3 interleaved or null
     long long dst_pitch;
     uint8_t *dst_mask;   // u8 or null
@@ -209,6 +210,8 @@ int launch_collapse_fast(const CollapseArgs &A, int l, int nb, cudaStream_t s);
 #define SB_WARP_BATCH 32
 int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s);
 int warp_maps_upload(const Projector &p, const int rect[4], float *maps_dev, WarpJob *job, cudaStream_t s);  // sb_api.cpp
+// u8x3 contiguous (w * h pixels) -> r | g<<8 | b<<16 words (the compositor's source layout for the warp kernel)
+int launch_repack_rgbx(const uint8_t *rgb, uint32_t *dst, long long pixels, cudaStream_t s);
 int launch_pack_rgbm(const uint8_t *rgb, long long rgb_pitch, const uint8_t *mask, long long mask_pitch, uint32_t *dst,
                      long long dst_pitch, int w, int h, cudaStream_t s);
 // level `l` -> `l+1` of images [first, first+count)

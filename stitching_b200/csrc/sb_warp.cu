@@ -262,8 +262,8 @@ __device__ __forceinline__ unsigned lerp6(unsigned l0, unsigned h0, unsigned l1,
 // the general rule for one pixel, from the projected numerators: exact division, x86 rounding, int16 saturation,
 // BORDER_REFLECT, validity from the nearest-neighbour test.  Called for the few pixels the streamlined path of
 // k_warp_rgbm does not cover (footprint on the border or outside, z <= 0, values outside the shortcut's ranges).
-__device__ SB_NOINLINE unsigned sample_general(const uint8_t *__restrict__ src, int sw, int sh, unsigned pitch, float x, float y,
-                                                float z, int always_divide)
+__device__ SB_NOINLINE unsigned sample_general(const uint8_t *__restrict__ src, const uint32_t *__restrict__ src4, int sw, int sh, unsigned pitch,
+                                                float x, float y, float z, int always_divide)
 {
     if (always_divide || z > 0.f) {
         x = fdiv(x, z);
@@ -278,13 +278,37 @@ __device__ SB_NOINLINE unsigned sample_general(const uint8_t *__restrict__ src, 
     const int x0 = reflect(ix, sw), x1 = reflect(ix + 1, sw);
     const int y0 = reflect(iy, sh), y1 = reflect(iy + 1, sh);
     unsigned a0, a1, b0, b1;
-    fetch_pair(src, (unsigned)y0 * pitch, x0, x1, a0, a1);
-    fetch_pair(src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    if (src4) {  // one word per pixel
+        const unsigned r0 = (unsigned)y0 * (unsigned)sw, r1 = (unsigned)y1 * (unsigned)sw;
+        a0 = __ldg(src4 + r0 + x0);
+        a1 = __ldg(src4 + r0 + x1);
+        b0 = __ldg(src4 + r1 + x0);
+        b1 = __ldg(src4 + r1 + x1);
+    } else {
+        fetch_pair(src, (unsigned)y0 * pitch, x0, x1, a0, a1);
+        fetch_pair(src, (unsigned)y1 * pitch, x0, x1, b0, b1);
+    }
     // as six-byte rows: left pixel in bytes 0-2, right pixel in bytes 3-5
     return lerp6<false>(a0 | (a1 << 24), a1 >> 8, b0 | (b1 << 24), b1 >> 8, (unsigned)sx & 31u, (unsigned)sy & 31u) | (m << 24);
 }
 
-template <bool HAS_BM, bool DP2A>
+// the same bilinear sum from four pixel words r | g<<8 | b<<16 (byte 3 zero: it doubles as the zero byte of the PRMTs)
+__device__ __forceinline__ unsigned lerp4(unsigned p00, unsigned p01, unsigned p10, unsigned p11, unsigned fx, unsigned fy)
+{
+    const unsigned M = 0x00ff00ffu, hx = 32u - fx, hy = 32u - fy;
+    const unsigned rb0 = (p00 & M) * hx + (p01 & M) * fx;  // [r | b<<16] of row 0
+    const unsigned rb1 = (p10 & M) * hx + (p11 & M) * fx;
+    const unsigned g01 = __byte_perm(p00, p10, 0x7531) * hx + __byte_perm(p01, p11, 0x7531) * fx;  // green [row0 | row1<<16]
+    const unsigned wy = hy | (fy << 8);
+    const unsigned r = __dp2a_lo(__byte_perm(rb0, rb1, 0x5410), wy, 512u);
+    const unsigned b = __dp2a_lo(__byte_perm(rb0, rb1, 0x7632), wy, 512u);
+    const unsigned g = __dp2a_lo(g01, wy, 512u);
+    return (r >> 10) | ((g >> 2) & 0xff00u) | ((b << 6) & 0xff0000u);
+}
+
+// SRC4: the sources are one word per pixel (WarpJob::src4): four aligned loads at two addresses per footprint instead of six
+// loads, two funnel shifts and the byte-address arithmetic of the packed 3-byte layout
+template <bool HAS_BM, bool DP2A, bool SRC4>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_constant__ WarpBatch B)
 {
     grid_dependency_sync();
@@ -324,15 +348,26 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_
         for (int p = 0; p < 2; ++p) {
             sx[p] = (unsigned)__float2int_rn(x32[p]);
             sy[p] = (unsigned)__float2int_rn(y32[p]);
-            const unsigned off = (sy[p] >> 5) * pitch + 3u * (sx[p] >> 5);
-            fetch6(j.src, off, l0[p], h0[p]);
-            fetch6(j.src, off + pitch, l1[p], h1[p]);
+            if (SRC4) {
+                const uint32_t *q = j.src4 + ((sy[p] >> 5) * (unsigned)j.sw + (sx[p] >> 5));
+                l0[p] = __ldg(q);
+                h0[p] = __ldg(q + 1);
+                l1[p] = __ldg(q + j.sw);
+                h1[p] = __ldg(q + j.sw + 1);
+            } else {
+                const unsigned off = (sy[p] >> 5) * pitch + 3u * (sx[p] >> 5);
+                fetch6(j.src, off, l0[p], h0[p]);
+                fetch6(j.src, off + pitch, l1[p], h1[p]);
+            }
         }
 #pragma unroll
-        for (int p = 0; p < 2; ++p) out[p] = lerp6<DP2A>(l0[p], h0[p], l1[p], h1[p], sx[p] & 31u, sy[p] & 31u) | 0xff000000u;
+        for (int p = 0; p < 2; ++p)
+            out[p] = (SRC4 ? lerp4(l0[p], h0[p], l1[p], h1[p], sx[p] & 31u, sy[p] & 31u)
+                           : lerp6<DP2A>(l0[p], h0[p], l1[p], h1[p], sx[p] & 31u, sy[p] & 31u)) | 0xff000000u;
     } else {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) out[p] = sample_general(j.src, j.sw, j.sh, pitch, xn[p], yn[p], zn[p], j.always_divide);
+        for (int p = 0; p < 2; ++p)
+            out[p] = sample_general(j.src, SRC4 ? j.src4 : nullptr, j.sw, j.sh, pitch, xn[p], yn[p], zn[p], j.always_divide);
     }
     if (HAS_BM) {  // the batch has per-pixel extras: exposure gains and / or blend masks (each optional per image)
         if (j.gain_mode) {
@@ -362,6 +397,27 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY, 8) k_warp_rgbm(const __grid_
         d[0] = out[0];
 }
 
+// u8x3 -> one word per pixel, four pixels per thread (12 contiguous bytes in, one 16-byte store out)
+__global__ void __launch_bounds__(256) k_repack_rgbx(const uint8_t *__restrict__ rgb, uint32_t *__restrict__ dst, long long pixels)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = 4 * t;
+    if (p >= pixels) return;
+    if (p + 4 <= pixels) {
+        const unsigned *q = reinterpret_cast<const unsigned *>(rgb) + 3 * t;  // the buffers come from the allocator: 256-byte aligned
+        const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        uint4 o;
+        o.x = w0 & 0x00ffffffu;
+        o.y = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+        o.z = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
+        o.w = w2 >> 8;
+        *reinterpret_cast<uint4 *>(dst + p) = o;
+    } else {
+        for (long long k = p; k < pixels; ++k)
+            dst[k] = (unsigned)rgb[3 * k] | ((unsigned)rgb[3 * k + 1] << 8) | ((unsigned)rgb[3 * k + 2] << 16);
+    }
+}
+
 __global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch, const uint8_t *__restrict__ mask,
                             long long mask_pitch, uint32_t *__restrict__ dst, long long dst_pitch, int w, int h)
 {
@@ -374,6 +430,14 @@ __global__ void k_pack_rgbm(const uint8_t *__restrict__ rgb, long long rgb_pitch
 }
 
 }  // namespace
+
+int launch_repack_rgbx(const uint8_t *rgb, uint32_t *dst, long long pixels, cudaStream_t s)
+{
+    if (pixels <= 0) return SB_OK;
+    const long long threads = (pixels + 3) / 4;
+    launch(k_repack_rgbx, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, s, rgb, dst, pixels);
+    return launch_check("k_repack_rgbx");
+}
 
 int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
 {
@@ -390,18 +454,23 @@ int launch_warp(const WarpJob *jobs_host, int n_jobs, cudaStream_t s)
         if (max_w <= 0 || max_h <= 0) continue;
         dim3 block(WARP_BX, WARP_BY), grid(div_up(max_w, WARP_BX), div_up(max_h, WARP_BY), cnt);
         if (!use_simple_kernels()) {
-            bool rgbm_only = true, has_bm = false;
+            bool rgbm_only = true, has_bm = false, src4 = true;
             for (int i = 0; i < cnt; ++i) {
+                src4 = src4 && B.j[i].src4 != nullptr;
                 rgbm_only = rgbm_only && !B.j[i].xmap && B.j[i].dst_rgbm && !B.j[i].dst_rgb && !B.j[i].dst_mask && B.j[i].sw <= 32767 && B.j[i].sh <= 32767 &&
                             B.j[i].sw >= 2 && B.j[i].sh >= 2 && B.j[i].rgbm_pitch % 2 == 0;
                 has_bm = has_bm || B.j[i].blend_mask || B.j[i].gain_mode;  // per-pixel extras anywhere in the batch
             }
             if (rgbm_only) {
                 dim3 grid2(div_up(max_w, 2 * WARP_BX), div_up(max_h, WARP_BY), cnt);
-                if (has_bm)
-                    launch_pdl(k_warp_rgbm<true, true>, grid2, block, 0, s, B);
+                if (has_bm && src4)
+                    launch_pdl(k_warp_rgbm<true, true, true>, grid2, block, 0, s, B);
+                else if (has_bm)
+                    launch_pdl(k_warp_rgbm<true, true, false>, grid2, block, 0, s, B);
+                else if (src4)
+                    launch_pdl(k_warp_rgbm<false, true, true>, grid2, block, 0, s, B);
                 else
-                    launch_pdl(k_warp_rgbm<false, true>, grid2, block, 0, s, B);
+                    launch_pdl(k_warp_rgbm<false, true, false>, grid2, block, 0, s, B);
             } else {
                 launch(k_warp_wide, grid, block, 0, s, B);
             }

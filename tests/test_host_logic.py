@@ -57,6 +57,26 @@ def test_compositor_matches_oracle(use_emu, oracle):
         c.close()
 
 
+def test_source_layouts_of_the_warp_kernel_agree(use_emu, monkeypatch):
+    """The compositor repacks every uploaded source to one word per pixel for the warp kernel (SB_SRC4, default on); the
+    packed 3-byte path (SB_SRC4=0) is the same arithmetic on the same pixels: identical panoramas, masks and warped images."""
+    cfg = rigs.config("cfg2", 16)
+    cams = cfg["cameras"][:4]
+    sizes = [(cfg["w"], cfg["h"])] * len(cams)
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 40 + i) for i in range(len(cams))]
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SB_SRC4", flag)
+        c = Compositor(cams, sizes, cfg["warper"], cfg["blender"], cfg["strength"])
+        pano, mask = c.composite(imgs)
+        out.append((pano.copy(), mask.copy(), [np.concatenate([a.ravel(), b.ravel()]) for a, b in (c.download_warped(i) for i in range(len(cams)))]))
+        c.close()
+    replay.assert_exact(out[0][0], out[1][0], "pano, word-per-pixel vs packed sources")
+    replay.assert_exact(out[0][1], out[1][1], "mask, word-per-pixel vs packed sources")
+    for a, b in zip(out[0][2], out[1][2]):
+        assert np.array_equal(a, b)
+
+
 def test_unit_weight_shortcuts_are_exact():
     """The two identities the fast collapse kernel uses instead of float work (sb_collapse_fast.cu):
     (short)trunc(L * 1.0f) == L, and (short)trunc(a / fl(1 + 1e-5f)) == a - sign(a) for every int16 a."""
