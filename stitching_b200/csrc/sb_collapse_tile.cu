@@ -29,14 +29,18 @@
 // anywhere even; the tile grid starts at the 64-column boundary at or left of it and quads left of the region are idle).
 // Slabs of partial sums from other ranks (ColDesc kind 1) are items too: nothing is staged for them, every quad adds its
 // four sums straight from global memory.  Producing partial sums, int16 output and the top level stay with
-// k_collapse_fast (launch_collapse_tile says so by returning SB_ERR_STATE).  The emulation build (tests/emu) does not
-// compile this file's kernels.
+// k_collapse_fast (launch_collapse_tile says so by returning SB_ERR_STATE).  The emulation build (tests/emu)
+// compiles the kernel as it is and runs it with one host thread per thread of a CTA (tests/emu: sb_emu_run_block; the
+// asynchronous copies become plain copies) when SB_EMU_BLOCKS is set -- slow, hence on request only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
 #include "sb_launch.h"
 #include "sb_pyramid.cuh"
 
 namespace sb {
 
-#ifndef SB_EMU
 namespace {
 
 constexpr int TW = SB_TILE_W, TH = SB_TILE_H, QX = TW / 2, QY = TH / 2;  // 64 x 16 pixels, 32 x 8 quads
@@ -76,6 +80,7 @@ struct Smem {
 };
 
 // 16-byte asynchronous copy global -> shared; `valid` false: nothing is read and the 16 bytes become zeros
+#ifndef SB_EMU
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
@@ -83,6 +88,18 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else  // the emulation copies at once: the commit groups and waits have nothing left to do
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid)
+{
+    if (valid)
+        std::memcpy(dst, src, 16);
+    else
+        std::memset(dst, 0, 16);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#endif
 
 // One 16-byte chunk of a staged window: source row `row` (valid inside [0, rows_valid)), bytes [xb, xb + 16) of it
 // (valid inside [0, row_bytes)); anything else arrives as zeros.  row_bytes is the valid width rounded UP to 16 bytes:
@@ -158,7 +175,11 @@ template <int LV, bool SLABS>
 __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const __grid_constant__ CollapseArgs A)
 {
     grid_dependency_sync();
+#ifndef SB_EMU
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#else
+    unsigned char *smem_raw = emu_smem;
+#endif
     Smem<LV> &S = *reinterpret_cast<Smem<LV> *>(smem_raw);
     const TileDesc *__restrict__ tile = A.tile;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * QX + tx;
@@ -510,11 +531,15 @@ __global__ void __launch_bounds__(QX *QY, LV == 0 ? 6 : 4) k_collapse_tile(const
 
 bool collapse_tile_enabled()
 {
+#ifdef SB_EMU
+    return getenv("SB_EMU_BLOCKS") != nullptr;  // one host thread per thread of a CTA: correct but slow, on request only
+#else
     static const bool on = [] {
         const char *e = getenv("SB_TILE");
         return !(e && e[0] == '0');
     }();
     return on;
+#endif
 }
 
 int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
@@ -536,6 +561,7 @@ int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
         return SB_ERR_STATE;
     }
     if (A.rw <= 0 || A.rh <= 0) return SB_OK;
+#ifndef SB_EMU
     static bool attr_set = false;
     if (!attr_set) {
         SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<0>)));
@@ -544,20 +570,21 @@ int launch_collapse_tile(const CollapseArgs &A, int l, int nb, cudaStream_t s)
         SB_CUDA(cudaFuncSetAttribute(k_collapse_tile<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<1>)));
         attr_set = true;
     }
+#endif
     dim3 block(QX, QY), grid(div_up(A.rx0 + A.rw - (A.rx0 & ~(TW - 1)), TW), div_up(A.rh, TH));
+#ifdef SB_EMU
+    if (getenv("SB_EMU_TRACE")) fprintf(stderr, "k_collapse_tile<%d, %d> %ux%u tiles, %d items\n", l, A.has_slabs, grid.x, grid.y, A.n);
+#endif
     if (l == 0 && A.has_slabs)
-        launch_pdl(k_collapse_tile<0, true>, grid, block, sizeof(Smem<0>), s, A);
+        launch_block(k_collapse_tile<0, true>, grid, block, sizeof(Smem<0>), s, A);
     else if (l == 0)
-        launch_pdl(k_collapse_tile<0, false>, grid, block, sizeof(Smem<0>), s, A);
+        launch_block(k_collapse_tile<0, false>, grid, block, sizeof(Smem<0>), s, A);
     else if (A.has_slabs)
-        launch_pdl(k_collapse_tile<1, true>, grid, block, sizeof(Smem<1>), s, A);
+        launch_block(k_collapse_tile<1, true>, grid, block, sizeof(Smem<1>), s, A);
     else
-        launch_pdl(k_collapse_tile<1, false>, grid, block, sizeof(Smem<1>), s, A);
+        launch_block(k_collapse_tile<1, false>, grid, block, sizeof(Smem<1>), s, A);
     return launch_check("k_collapse_tile");
 }
-#else   // SB_EMU
-bool collapse_tile_enabled() { return false; }
-int launch_collapse_tile(const CollapseArgs &, int, int, cudaStream_t) { return SB_ERR_STATE; }
-#endif
+
 
 }  // namespace sb

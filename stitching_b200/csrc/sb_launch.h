@@ -27,6 +27,13 @@ inline void launch_lanes(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, 
     count_launch();
     sb_emu_run_lanes(grid, block, [&]() { kern(args...); });
 }
+// kernels whose threads share memory and meet at block barriers: one host thread per thread of a block
+template <typename... KArgs, typename... Args>
+inline void launch_block(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args &&...args)
+{
+    count_launch();
+    sb_emu_run_block(grid, block, smem, [&]() { kern(args...); });
+}
 #else
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
@@ -62,6 +69,11 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 template <typename... KArgs, typename... Args>
 inline void launch_lanes(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    launch_pdl(kern, grid, block, smem, s, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_block(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
 {
     launch_pdl(kern, grid, block, smem, s, std::forward<Args>(args)...);
 }

@@ -2,7 +2,9 @@
 // A CPU stand-in for the few CUDA runtime calls and device builtins libstitch_b200 uses, so that the product's
 // host logic (plans, geometry, C ABI) and the arithmetic of its kernels can be exercised on a GPU-less box
 // (pytest -m "not gpu"): synchronisation-free kernels run as serial loops over the grid (sb_emu_run), kernels whose
-// lanes exchange values through warp shuffles run with 32 host threads as the lanes of a warp (sb_emu_run_lanes).
+// lanes exchange values through warp shuffles run with 32 host threads as the lanes of a warp (sb_emu_run_lanes),
+// kernels whose threads share memory and meet at block barriers run with one host thread per thread of a block
+// (sb_emu_run_block).
 // The product build never sees this header (it is only on the include path of tests/emu/Makefile, which
 // defines SB_EMU), the product loader (stitching_b200/_lib.py) never loads the emu library, and nothing
 // measured or shipped runs through it.
@@ -32,10 +34,31 @@ struct alignas(8) int2 { int x, y; };
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(8) float2 { float x, y; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 // lane-wise 16-bit add / subtract with wrap-around (VIADD.16x2)
 static inline unsigned __vadd2(unsigned a, unsigned b) { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }
 static inline unsigned __vsub2(unsigned a, unsigned b) { return ((a - b) & 0xffffu) | (((a >> 16) - (b >> 16)) << 16); }
+
+// lane-wise signed 16-bit min / max of (a + b) and c (VIADDMNMX.S16x2), lane-wise signed min (VIMNMX.S16x2)
+static inline unsigned emu_lanes2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+static inline int emu_lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+static inline int emu_hi16(unsigned v) { return (int)(short)(v >> 16); }
+static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c)
+{
+    const int lo = (short)(emu_lo16(a) + emu_lo16(b)), hi = (short)(emu_hi16(a) + emu_hi16(b));
+    return emu_lanes2(lo < emu_lo16(c) ? lo : emu_lo16(c), hi < emu_hi16(c) ? hi : emu_hi16(c));
+}
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c)
+{
+    const int lo = (short)(emu_lo16(a) + emu_lo16(b)), hi = (short)(emu_hi16(a) + emu_hi16(b));
+    return emu_lanes2(lo > emu_lo16(c) ? lo : emu_lo16(c), hi > emu_hi16(c) ? hi : emu_hi16(c));
+}
+static inline unsigned __vmins2(unsigned a, unsigned b)
+{
+    return emu_lanes2(emu_lo16(a) < emu_lo16(b) ? emu_lo16(a) : emu_lo16(b), emu_hi16(a) < emu_hi16(b) ? emu_hi16(a) : emu_hi16(b));
+}
 
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -176,6 +199,68 @@ static inline void sb_emu_run_lanes(dim3 grid, dim3 block, F &&body)
                     }
         });
     for (auto &t : lanes) t.join();
+}
+
+// ---- kernels whose threads share memory and meet at block barriers (sb_collapse_tile.cu) --------------------------
+// One host thread per thread of a block; every host thread walks all blocks of the grid in the same order with its
+// threadIdx fixed, __syncthreads is a rendezvous of all of them, the dynamic shared memory is one buffer they all see,
+// and the warps (rows of 32 threads) get their own rendezvous for ballots.  A barrier at the end of every block keeps a
+// fast thread from writing the next block's shared memory while a slow one still reads this block's.
+struct EmuBlockSync {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, waiting = 0;
+    unsigned long long generation = 0;
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned long long g = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != g; });
+        }
+    }
+};
+extern thread_local EmuBlockSync *emu_block;
+extern thread_local unsigned char *emu_smem;
+static inline void __syncthreads()
+{
+    if (!emu_block) std::abort();  // a block-cooperative kernel was launched through the serial runner
+    emu_block->barrier();
+}
+
+template <typename F>
+static inline void sb_emu_run_block(dim3 grid, dim3 block, size_t smem_bytes, F &&body)
+{
+    if (block.x != 32 || block.z != 1) std::abort();
+    EmuBlockSync sync;
+    sync.n = (int)(block.x * block.y);
+    std::vector<EmuWarpSync> warps(block.y);
+    std::vector<unsigned char> smem(smem_bytes + 64);
+    unsigned char *smem_base = smem.data() + ((64 - ((uintptr_t)smem.data() & 63)) & 63);
+    std::vector<std::thread> threads;
+    for (unsigned ty = 0; ty < block.y; ++ty)
+        for (unsigned tx = 0; tx < block.x; ++tx)
+            threads.emplace_back([&, tx, ty]() {
+                emu_block = &sync;
+                emu_warp = &warps[ty];
+                emu_smem = smem_base;
+                gridDim = emuIdx{grid.x, grid.y, grid.z};
+                blockDim = emuIdx{block.x, block.y, block.z};
+                threadIdx = emuIdx{tx, ty, 0};
+                for (unsigned bz = 0; bz < grid.z; ++bz)
+                    for (unsigned by = 0; by < grid.y; ++by)
+                        for (unsigned bx = 0; bx < grid.x; ++bx) {
+                            blockIdx = emuIdx{bx, by, bz};
+                            body();
+                            sync.barrier();
+                        }
+                emu_block = nullptr;
+            });
+    for (auto &t : threads) t.join();
 }
 
 template <typename F>

@@ -284,6 +284,45 @@ def test_warp_collective_kernels_under_lane_emulation(use_emu, oracle, monkeypat
         replay.assert_exact(mask, ref["pmask"], f"{name} mask through the shuffle pyrDown")
 
 
+def test_shared_memory_tile_kernels_under_block_emulation(use_emu, oracle, monkeypatch):
+    """k_collapse_tile (levels 0 and 1 on staged shared-memory tiles, sb_collapse_tile.cu) itself on the CPU: tests/emu plays a
+    CTA with one host thread per thread (256), __syncthreads is their rendezvous, the asynchronous copies are plain copies.
+    Slow, hence small rigs: single-GPU composites against the oracle (rect origins at every alignment the run-time window
+    shifts have to handle, tiles on the pano border, several images per tile), and a three-rank sharded composite whose
+    strips take slabs of partial sums as items from both sides."""
+    import test_sharded
+
+    monkeypatch.setenv("SB_EMU_BLOCKS", "1")
+    launches0 = _launches()
+    for name, sd, ncap, strength in (("cfg2", 25, 4, 5), ("cfg3", 40, 5, 20), ("cfg2", 20, 3, 60)):
+        cfg = dict(rigs.config(name, sd), strength=strength)
+        cams = cfg["cameras"][:ncap]
+        imgs = [rigs.noise_image(cfg["h"], cfg["w"], 600 + i) if i % 2 else rigs.synth_image(cfg["h"], cfg["w"], 600 + i) for i in range(len(cams))]
+        ref = replay.oracle_composite(oracle, cfg, cams, imgs)
+        c = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], strength)
+        assert c.num_bands >= 2, "the tile kernel serves levels 0 and 1 below the top level"
+        pano, mask = c.composite(imgs)
+        c.close()
+        replay.assert_exact(pano, ref["pano"], f"{name}/{sd} pano through the tile kernels")
+        replay.assert_exact(mask, ref["pmask"], f"{name}/{sd} mask through the tile kernels")
+    cfg = rigs.config("cfg2", 20)
+    cams = cfg["cameras"][:6]
+    imgs = [rigs.noise_image(cfg["h"], cfg["w"], 70 + i) for i in range(len(cams))]
+    single = Compositor(cams, [(cfg["w"], cfg["h"])] * len(cams), cfg["warper"], cfg["blender"], cfg["strength"])
+    ref_pano, ref_mask = single.composite(imgs)
+    single.close()
+    pano, mask, moved = test_sharded.run_sharded(cfg, cams, imgs, 3, lambda d, s, n: C.memmove(d, s, n))
+    assert moved > 0 and np.array_equal(mask, ref_mask)
+    assert np.abs(pano.astype(np.int32) - ref_pano.astype(np.int32)).max() <= 1
+    assert _launches() > launches0
+
+
+def _launches():
+    from stitching_b200 import _lib
+
+    return _lib.lib().sb_launch_count()
+
+
 def test_parallel_distance_transform_under_lane_emulation(use_emu, oracle, monkeypatch):
     """The feather weights' L1 distance transform in its parallel form -- ballot words + warp scans along the rows (several
     words per lane for wide rows), chunked prefix minima along the columns -- against the oracle's FeatherBlender on mask
