@@ -803,11 +803,14 @@ int sb_compositor_submit(sb_compositor *c, const uint8_t *const *srcs, const siz
     // (download() is synchronous, so the output buffers need no such guard)
     if (t < SB_PIPE_DEPTH) SB_CUDA(cudaEventRecord(c->e_comp[slot], c->stream));
     SB_CUDA(cudaStreamWaitEvent(c->h2d, c->e_comp[slot], 0));
-    for (int i = 0; i < c->n; ++i) {
+    for (int i = 0; i < c->n; ++i)
         SB_CUDA(sb_copy2d(sdev[i], (size_t)c->src_w[i] * 3, srcs[i], pitches[i], (size_t)c->src_w[i] * 3, c->src_h[i],
                                   cudaMemcpyHostToDevice, c->h2d));
+    // the repack kernels follow the LAST copy (same stream): a kernel between two copies would leave the PCIe link idle
+    // for its launch + run time, eight times per step
+    for (int i = 0; i < c->n; ++i) {
         uint32_t *s4 = slot ? (c->src4_devx[slot - 1].empty() ? nullptr : c->src4_devx[slot - 1][i]) : c->src4_dev[i];
-        if (s4) SB_TRY(launch_repack_rgbx(sdev[i], s4, (long long)c->src_w[i] * c->src_h[i], c->h2d));  // behind its copy, on the copy stream
+        if (s4) SB_TRY(launch_repack_rgbx(sdev[i], s4, (long long)c->src_w[i] * c->src_h[i], c->h2d));
     }
     SB_CUDA(cudaEventRecord(c->e_h2d[slot], c->h2d));
     SB_CUDA(cudaStreamWaitEvent(c->stream, c->e_h2d[slot], 0));
