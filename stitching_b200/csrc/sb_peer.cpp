@@ -9,9 +9,11 @@
 // a second stream beside the pyramid kernels).  Storing the slabs from the kernels straight into the peers' arenas is
 // available too (SB_PEER=direct) -- measured on 2 B200s it LOSES: the 2- and 4-byte scattered stores of that kernel
 // cross NVLink as small partial writes, partial_l0 0.025 -> 0.179 ms, step 0.97 -> 1.21 ms
-// (profiles/bench_r02_e_2gpu_direct_stores.json).  The ranks order themselves with four flags per pair, written and
-// awaited by stream memory operations
-// (cuStreamWriteValue32 / cuStreamWaitValue32: stream-ordered, no host round trip, no spinning kernel):
+// (profiles/bench_r02_e_2gpu_direct_stores.json).  The ranks order themselves with four flags per pair, written by
+// stream memory operations (cuStreamWriteValue32: stream-ordered behind the copy, no host round trip) and awaited by a
+// one-warp polling kernel (k_wait_flags, sb_util.cu) right before the kernel that reads the slab -- cuStreamWaitValue32
+// was measured too and lost: enqueued ahead, the front end evaluates those waits in batches and a step went from
+// 0.92 to 1.86 ms (profiles/bench_r02_e_2gpu_streamwait.json):
 //   data[part][p]  in the RECEIVER's arena: rank p has finished writing part `part` (0: level 0, 1: the coarser
 //                  levels) of step `value`;
 //   consumed[p]    in the SENDER's arena: rank p has read the slabs of step `value` (the next step may overwrite them).

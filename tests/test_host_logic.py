@@ -77,6 +77,39 @@ def test_source_layouts_of_the_warp_kernel_agree(use_emu, monkeypatch):
         assert np.array_equal(a, b)
 
 
+def test_host_pool_reuses_and_bounds_page_locked_memory(use_emu, monkeypatch):
+    """The drop-ins' result arrays come from pooled page-locked buffers (stitching_b200/host_pool.py): a buffer goes back to the
+    pool when its last view dies, the next array of that size class takes it, small arrays and an exhausted pool fall back to
+    np.empty, and the arrays are ordinary writable ndarrays."""
+    import gc
+
+    from stitching_b200 import host_pool
+
+    host_pool.trim()
+    a = host_pool.empty((300, 400, 3), np.uint8)
+    assert a.shape == (300, 400, 3) and a.dtype == np.uint8 and a.flags.writeable and a.flags.c_contiguous
+    a[...] = 7
+    addr = a.ctypes.data
+    view = a[10:20]
+    del a
+    gc.collect()
+    assert sum(len(v) for v in host_pool._free.values()) == 0  # a view keeps the buffer out of the pool
+    del view
+    gc.collect()
+    assert sum(len(v) for v in host_pool._free.values()) == 1
+    b = host_pool.empty((350, 400, 3), np.int16)                 # same 1 MiB size class: the cached buffer is reused
+    assert b.ctypes.data == addr and b.dtype == np.int16
+    small = host_pool.empty((10, 10), np.uint8)                   # not worth pinning
+    assert small.base is None
+    monkeypatch.setenv("SB_PINNED_LIMIT_MB", "1")
+    c = host_pool.empty((2000, 2000), np.uint8)                   # over the limit: pageable
+    assert c.shape == (2000, 2000) and c.base is None
+    del b, c
+    gc.collect()
+    host_pool.trim()
+    assert host_pool._total == 0 and not any(host_pool._free.values())
+
+
 def test_unit_weight_shortcuts_are_exact():
     """The two identities the fast collapse kernel uses instead of float work (sb_collapse_fast.cu):
     (short)trunc(L * 1.0f) == L, and (short)trunc(a / fl(1 + 1e-5f)) == a - sign(a) for every int16 a."""
