@@ -259,3 +259,38 @@ def test_timelapse_run_after_install(reference_stitching, use_emu, tmp_path):
     assert all(0.1 < c.mean() < 0.9 for c in cover)                     # one image per frame, not the panorama
     centres = [np.nonzero(c.any(axis=0))[0].mean() for c in cover]
     assert min(abs(a - b) for i, a in enumerate(centres) for b in centres[i + 1:]) > 100  # three different places on the canvas
+
+
+def test_one_stitcher_for_two_image_sets_and_affine_stitcher_after_install(reference_stitching, use_emu):
+    """tests/test_stitcher.py:283-290 re-uses one Stitcher for two image sets, :173-185 runs AffineStitcher (plane warp
+    through the affine warper, feather-free defaults): both after install(), on the swapped classes."""
+    stitching, cv = reference_stitching
+    import stitching_b200
+
+    stitching_b200.install(stitching)
+    views = synthetic_views(cv)
+    st = stitching.Stitcher(**SETTINGS)
+    first = st.stitch([v.copy() for v in views])
+    second = st.stitch([v.copy() for v in views[:2]])            # a different set through the same object
+    assert first.ndim == 3 and second.ndim == 3 and second.shape[1] < first.shape[1]
+    again = st.stitch([v.copy() for v in views])
+    assert abs(again.shape[0] - first.shape[0]) <= 30 and abs(again.shape[1] - first.shape[1]) <= 30
+
+    # AffineStitcher: flat scans of one scene, shifted and slightly rotated against each other
+    rng = np.random.default_rng(11)
+    scene = cv.resize(rng.integers(0, 256, (30, 40, 3), dtype=np.uint8), (1600, 1200), interpolation=cv.INTER_CUBIC)
+    for _ in range(700):
+        c = tuple(int(v) for v in rng.integers(0, 256, 3))
+        p = (int(rng.integers(0, 1600)), int(rng.integers(0, 1200)))
+        cv.circle(scene, p, int(rng.integers(4, 30)), c, -1)
+    scans = []
+    for dx, ang in ((0, 0.0), (380, 1.5), (760, -1.0)):
+        M = cv.getRotationMatrix2D((400, 500), ang, 1.0)
+        M[0, 2] -= dx
+        scans.append(cv.warpAffine(scene, M, (800, 1000)))
+    try:
+        pano = stitching.AffineStitcher(crop=False, detector="orb", confidence_threshold=0.3).stitch(scans)
+    except stitching.stitching_error.StitchingError as e:  # registration is the reference's business; tell, do not fail
+        pytest.skip(f"the reference could not register the synthetic scans: {e}")
+    assert pano.ndim == 3 and pano.dtype == np.uint8
+    assert pano.shape[1] > 1200 and (pano.sum(axis=2) > 0).mean() > 0.5  # wider than one scan: the scans were composed
