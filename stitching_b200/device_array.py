@@ -9,8 +9,6 @@ root buffer selects the same rectangle on the device); anything numpy has to cop
 is an ordinary ndarray again.  The array is read-only, so host and device copies cannot drift apart behind the
 library's back; the drop-ins that legitimately modify an image in place (ExposureErrorCompensator.apply) update both.
 """
-import ctypes as C
-
 import numpy as np
 
 from . import _lib
