@@ -1,0 +1,120 @@
+"""The oracle against the UNMODIFIED reference classes, live (build container only: needs /root/reference and cv2).
+
+The committed goldens (tests/golden/*.npz) were written by the reference once; this file re-derives the pin on fresh random
+inputs every time it runs, so that "the oracle is pinned" stays a checked statement wherever the reference can be imported:
+every projection of Warper.WARP_TYPE_CHOICES (roi, warped image, warped mask), the three blenders with gray and binary masks,
+and the Timelapser.  On the GPU box (no reference) the whole file skips; the goldens carry the pin there.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import replay
+from stitching_b200 import rigs
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    pytest.importorskip("cv2")
+    if not os.path.isdir(os.path.join(REF, "stitching")):
+        pytest.skip("the reference checkout is not on this box")
+    sys.path.insert(0, REF)
+    for name in [m for m in sys.modules if m == "stitching" or m.startswith("stitching.")]:
+        del sys.modules[name]
+    mod = importlib.import_module("stitching")
+    importlib.import_module("stitching.warper")
+    importlib.import_module("stitching.blender")
+    importlib.import_module("stitching.timelapser")
+    yield mod
+    for name in [m for m in sys.modules if m == "stitching" or m.startswith("stitching.")]:
+        del sys.modules[name]
+    sys.path.remove(REF)
+
+
+def _rng():
+    """A fresh seed per run (SB_FUZZ_SEED pins it); printed, so that a failing draw can be replayed."""
+    seed = int(os.environ.get("SB_FUZZ_SEED", int.from_bytes(os.urandom(4), "little")))
+    print(f"SB_FUZZ_SEED={seed}")
+    return np.random.default_rng(seed)
+
+
+def _rot(rx, ry, rz):
+    cz, sz = np.cos(rz), np.sin(rz)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return (Rz @ rigs.rot_y(ry) @ rigs.rot_x(rx)).astype(np.float32)
+
+
+def test_every_projection_against_the_reference_warper(ref, oracle):
+    rng = _rng()
+    W, H = 88, 66
+    types = ref.warper.Warper.WARP_TYPE_CHOICES
+    assert len(types) == 16
+    checked = 0
+    for wtype in types:
+        for trial in range(3):
+            if wtype == "affine":
+                th, s = rng.uniform(-0.2, 0.2), rng.uniform(0.85, 1.2)
+                R = np.array([[s * np.cos(th), -s * np.sin(th), rng.uniform(-90, 300)], [s * np.sin(th), s * np.cos(th), rng.uniform(-40, 40)],
+                              [0, 0, 1]], np.float32)
+                cam, scale = rigs.Camera(1.0, 1.0, 0.0, 0.0, R), 1.0
+            else:
+                wide = wtype in ("spherical", "cylindrical")
+                R = _rot(rng.uniform(-0.3, 0.3), rng.uniform(-3.0, 3.0) if wide else rng.uniform(-0.45, 0.45), rng.uniform(-0.15, 0.15))
+                cam = rigs.Camera(rng.uniform(70, 120), rng.uniform(0.97, 1.03), W / 2 + rng.uniform(-4, 4), H / 2 + rng.uniform(-3, 3), R)
+                scale = float(rng.uniform(60, 120))
+            aspect = float(rng.choice([1.0, 0.8, 1.25])) if trial == 2 else 1.0
+            img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            wr = ref.warper.Warper(wtype)
+            wr.scale = scale
+            K = ref.warper.Warper.get_K(cam, aspect)
+            roi = tuple(int(v) for v in wr.warp_roi((W, H), cam, aspect))
+            got_roi = oracle.warp_roi(wtype, scale * aspect, K, cam.R, (W, H))
+            assert tuple(got_roi) == roi, (wtype, trial, got_roi, roi)
+            if roi[2] * roi[3] > 4_000_000:
+                continue  # a degenerate draw (horizon in view): the rect is exact, the pixels would take minutes
+            rect, gimg, gmask = oracle.warp(wtype, scale * aspect, K, cam.R, img)
+            replay.assert_exact(gimg, wr.warp_image(img, cam, aspect), f"{wtype} trial {trial}: warped image")
+            replay.assert_exact(gmask, wr.create_and_warp_mask((W, H), cam, aspect), f"{wtype} trial {trial}: warped mask")
+            checked += 1
+    assert checked >= 40
+
+
+def test_blenders_and_timelapser_against_the_reference(ref, oracle):
+    rng = _rng()
+    for trial in range(9):
+        kind = ("multiband", "feather", "no")[trial % 3]
+        strength = float(rng.choice([1, 5, 20, 60]))
+        n = int(rng.integers(2, 5))
+        sizes = [(int(rng.integers(40, 120)), int(rng.integers(30, 90))) for _ in range(n)]
+        corners = [(int(rng.integers(-20, 20)) + 35 * i, int(rng.integers(-15, 15))) for i in range(n)]
+        imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+        masks = []
+        for (w, h) in sizes:
+            m = np.full((h, w), 255, np.uint8)
+            if trial % 2:
+                m[rng.random((h, w)) < 0.1] = 0
+            if trial % 4 == 3:
+                m = (m.astype(np.float32) * rng.random((h, w))).astype(np.uint8)  # gray seam-like masks
+            masks.append(m)
+        a, b = ref.blender.Blender(kind, strength), oracle.Blender(kind, strength)
+        a.prepare(corners, sizes)
+        b.prepare(corners, sizes)
+        for img, m, c in zip(imgs, masks, corners):
+            a.feed(img, m, c)
+            b.feed(img, m, c)
+        (pa, ma), (pb, mb) = a.blend(), b.blend()
+        replay.assert_exact(np.asarray(pb), np.asarray(pa), f"{kind} strength {strength}: panorama")
+        replay.assert_exact(np.asarray(mb), np.asarray(ma.get() if hasattr(ma, "get") else ma), f"{kind} strength {strength}: mask")
+        for tl_kind in ("as_is", "crop"):
+            ta, tb = ref.timelapser.Timelapser(tl_kind), oracle.Timelapser(tl_kind)
+            ta.initialize(corners, sizes)
+            tb.initialize(corners, sizes)
+            for img, c in zip(imgs, corners):
+                ta.process_frame(img, c)
+                tb.process_frame(img, c)
+                replay.assert_exact(tb.get_frame(), ta.get_frame(), f"timelapse {tl_kind}")
