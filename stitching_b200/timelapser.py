@@ -16,6 +16,9 @@ from . import _lib, device_array, host_pool
 from .stitching_error import StitchingError
 
 
+_EMPTY = object()
+
+
 class Timelapser:
     # interface constants of the boundary (timelapser.py:10-16)
     TIMELAPSE_CHOICES = ("no", "as_is", "crop")
@@ -59,7 +62,7 @@ class Timelapser:
             raise StitchingError("Timelapser.process_frame before initialize")
         _, _, cw, ch = self.roi
         if cw <= 0 or ch <= 0:
-            self._frame = np.zeros((max(ch, 0), max(cw, 0), 3), np.uint8)
+            self._frame = _EMPTY  # the reference's get_frame fails on an empty canvas (cv.convertScaleAbs of an empty array)
             return
         roi = (C.c_int * 4)(*self.roi)
         dst = host_pool.empty((ch, cw, 3), np.uint8)
@@ -85,6 +88,10 @@ class Timelapser:
     def get_frame(self):
         if self._frame is None:
             raise StitchingError("Timelapser.get_frame before process_frame")
+        if self._frame is _EMPTY:
+            from .warper import _lib_argument_error
+
+            raise _lib_argument_error("Timelapser.get_frame: the prepared roi is empty (the images' rects touch in a line or a point)")
         return self._frame
 
     # timelapser.py:51-53

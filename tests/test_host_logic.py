@@ -436,6 +436,11 @@ def test_timelapser_drop_in(use_emu, oracle):
     assert not off.do_timelapse and off.timelapser is None
     with pytest.raises(AttributeError):
         off.initialize([(0, 0)], [(4, 4)])
+    touching = Timelapser("crop")  # rects that share only an edge: empty intersection canvas, get_frame fails like the reference's
+    touching.initialize([(0, 0), (40, 0)], [(40, 30), (40, 30)])
+    touching.process_frame(rigs.noise_image(30, 40, 1), (0, 0))
+    with pytest.raises(StitchingError):
+        touching.get_frame()
 
 
 def test_exposure_gain_drop_in_and_fused(use_emu, oracle):

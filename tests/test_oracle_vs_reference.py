@@ -117,4 +117,10 @@ def test_blenders_and_timelapser_against_the_reference(ref, oracle):
             for img, c in zip(imgs, corners):
                 ta.process_frame(img, c)
                 tb.process_frame(img, c)
+                if tb.roi[2] == 0 or tb.roi[3] == 0:  # rects that touch in a line: the reference's get_frame raises on the empty canvas
+                    import cv2
+
+                    with pytest.raises(cv2.error):
+                        ta.get_frame()
+                    continue
                 replay.assert_exact(tb.get_frame(), ta.get_frame(), f"timelapse {tl_kind}")
