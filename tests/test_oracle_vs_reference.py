@@ -124,3 +124,56 @@ def test_blenders_and_timelapser_against_the_reference(ref, oracle):
                         ta.get_frame()
                     continue
                 replay.assert_exact(tb.get_frame(), ta.get_frame(), f"timelapse {tl_kind}")
+
+
+def test_final_resolution_steps_against_the_reference(ref, oracle):
+    """SeamFinder.resize (seam_finder.py:38-43) and Images.resize_img_by_scaler (images.py:120-123) on fresh random shapes;
+    ExposureErrorCompensator.apply (exposure_error_compensator.py:43-45) with gains the reference's own feed() estimated."""
+    import cv2 as cv
+
+    importlib.import_module("stitching.seam_finder")
+    importlib.import_module("stitching.images")
+    importlib.import_module("stitching.exposure_error_compensator")
+    rng = _rng()
+    for t in range(10):
+        sh, sw = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        h, w = int(rng.integers(2, 300)), int(rng.integers(2, 400))
+        seam = (rng.integers(0, 256, (sh, sw), dtype=np.uint8) if t % 2 else (rng.random((sh, sw)) < 0.5).astype(np.uint8) * 255)
+        mask = (rng.random((h, w)) < 0.85).astype(np.uint8) * 255
+        want = ref.seam_finder.SeamFinder.resize(cv.UMat(seam), mask)
+        replay.assert_exact(oracle.seam_resize(seam, mask), want.get() if hasattr(want, "get") else np.asarray(want), f"SeamFinder.resize {sw}x{sh} -> {w}x{h}")
+
+    class Scaler:
+        def __init__(self, size):
+            self.size = size
+
+        def get_scaled_img_size(self, _):
+            return self.size
+
+    for t in range(10):
+        h, w = int(rng.integers(2, 200)), int(rng.integers(2, 260))
+        size = (int(rng.integers(1, 300)), int(rng.integers(1, 240)))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = ref.images.Images.resize_img_by_scaler(Scaler(size), (w, h), img)
+        replay.assert_exact(oracle.resize_linear_exact(img, size), want, f"Images.resize {w}x{h} -> {size}")
+
+    kinds = ref.exposure_error_compensator.ExposureErrorCompensator.COMPENSATOR_CHOICES
+    for t, kind in enumerate(kinds):
+        n = 3
+        sizes = [(int(rng.integers(90, 160)), int(rng.integers(70, 120))) for _ in range(n)]
+        corners = [(40 * i + int(rng.integers(-5, 5)), int(rng.integers(-5, 5))) for i in range(n)]
+        base = rng.integers(30, 220, (200, 400, 3), dtype=np.uint8)
+        imgs = []
+        for i, ((w, h), (x, y)) in enumerate(zip(sizes, corners)):
+            crop = base[20 + y: 20 + y + h, 20 + x: 20 + x + w].astype(np.float32) * (0.8 + 0.2 * i)
+            imgs.append(np.clip(crop + rng.normal(0, 2, crop.shape), 0, 255).astype(np.uint8))
+        masks = [np.full((h, w), 255, np.uint8) for (w, h) in sizes]
+        comp = ref.exposure_error_compensator.ExposureErrorCompensator(kind, 1, 16)
+        comp.feed(corners, imgs, masks)
+        for i in range(n):
+            want = comp.apply(i, corners[i], imgs[i].copy(), masks[i])
+            if kind == "no":
+                replay.assert_exact(imgs[i], want, "compensator no: identity")
+                continue
+            gain = np.asarray(comp.compensator.getMatGains()[i])
+            replay.assert_exact(oracle.gain_apply(imgs[i], gain), want, f"compensator {kind} image {i}")
