@@ -177,3 +177,52 @@ def test_final_resolution_steps_against_the_reference(ref, oracle):
                 continue
             gain = np.asarray(comp.compensator.getMatGains()[i])
             replay.assert_exact(oracle.gain_apply(imgs[i], gain), want, f"compensator {kind} image {i}")
+
+
+def test_drop_in_classes_against_the_reference_classes(ref, use_emu):
+    """The product's own classes (their kernels through tests/emu) side by side with the reference's, same calls, same inputs:
+    Warper (set_scale, warp_rois, warp_images, create_and_warp_masks) -> Blender (prepare, feed, blend) for random rigs of every
+    blender type and a handful of projections, and Timelapser frames of the same warped images."""
+    import stitching_b200
+
+    rng = _rng()
+    W, H = 120, 90
+    for trial, (wtype, btype) in enumerate((("spherical", "multiband"), ("cylindrical", "feather"), ("plane", "no"), ("fisheye", "multiband"),
+                                            ("paniniA2B1", "feather"), ("mercator", "multiband"), ("affine", "multiband"))):
+        n = 3
+        if wtype == "affine":
+            cams = [rigs.Camera(1.0, 1.0, 0.0, 0.0, np.array([[1, 0.01 * i, 70.0 * i + rng.uniform(-3, 3)], [-0.01 * i, 1, rng.uniform(-8, 8)], [0, 0, 1]], np.float32))
+                    for i in range(n)]
+        else:
+            f = rng.uniform(90, 130)
+            cams = [rigs.Camera(f * rng.uniform(0.98, 1.02), 1.0, W / 2, H / 2, _rot(rng.uniform(-0.05, 0.05), 0.45 * (i - 1) + rng.uniform(-0.03, 0.03), rng.uniform(-0.03, 0.03)))
+                    for i in range(n)]
+        imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(n)]
+        sizes = [(W, H)] * n
+        out = []
+        for Warper, Blender, Timelapser in ((ref.warper.Warper, ref.blender.Blender, ref.timelapser.Timelapser),
+                                            (stitching_b200.Warper, stitching_b200.Blender, stitching_b200.Timelapser)):
+            w = Warper(wtype)
+            w.set_scale(cams)
+            warped = list(w.warp_images(imgs, cams))
+            masks = list(w.create_and_warp_masks(sizes, cams))
+            corners, wsizes = w.warp_rois(sizes, cams)
+            b = Blender(btype, 5)
+            b.prepare(corners, wsizes)
+            for img, m, c in zip(warped, masks, corners):
+                b.feed(img, m, c)
+            pano, pmask = b.blend()
+            t = Timelapser("as_is")
+            t.initialize(corners, wsizes)
+            t.process_frame(warped[1], corners[1])
+            out.append(dict(corners=[tuple(int(v) for v in c) for c in corners], sizes=[tuple(int(v) for v in s) for s in wsizes],
+                            warped=[np.asarray(x) for x in warped], masks=[np.asarray(x) for x in masks], pano=np.asarray(pano),
+                            pmask=np.asarray(pmask.get() if hasattr(pmask, "get") else pmask), frame=np.asarray(t.get_frame())))
+        a, b = out
+        assert a["corners"] == b["corners"] and a["sizes"] == b["sizes"], (wtype, a["corners"], b["corners"])
+        for i in range(n):
+            replay.assert_exact(b["warped"][i], a["warped"][i], f"{wtype}: warped image {i}")
+            replay.assert_exact(b["masks"][i], a["masks"][i], f"{wtype}: warped mask {i}")
+        replay.assert_exact(b["pano"], a["pano"], f"{wtype} + {btype}: panorama")
+        replay.assert_exact(b["pmask"], a["pmask"], f"{wtype} + {btype}: panorama mask")
+        replay.assert_exact(b["frame"], a["frame"], f"{wtype}: timelapse frame")
