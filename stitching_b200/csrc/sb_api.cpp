@@ -1,6 +1,7 @@
 // sb_api.cpp -- the C ABI (include/stitch_b200.h): Warper and Blender entry points with host buffers.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <memory>
 #include <vector>
 
@@ -81,6 +82,50 @@ struct sb_devimg {
     int w, h, ch;
 };
 
+// The reference asks for the same roi several times per image -- warp_roi, then warp (image), then warp (mask), each of
+// which runs detectResultRoi again (warper.py:43-82) -- and for eleven of the projections that is a pass over EVERY source
+// pixel.  The result depends on nothing but the arguments, so the last few are remembered (host memory, a few hundred bytes).
+namespace {
+struct RoiKey {
+    int type, w, h;
+    float scale, K[9], R[9];
+};
+struct RoiEntry {
+    RoiKey key;
+    int rect[4];
+};
+std::mutex g_roi_mutex;
+std::vector<RoiEntry> g_roi_cache;  // most recent last
+constexpr size_t ROI_CACHE_ENTRIES = 64;
+
+void cached_roi(const Projector &p, int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h, int rect[4])
+{
+    RoiKey key;
+    std::memset(&key, 0, sizeof key);
+    key.type = warp_type;
+    key.w = src_w;
+    key.h = src_h;
+    key.scale = scale;
+    std::memcpy(key.K, K, sizeof key.K);
+    std::memcpy(key.R, R, sizeof key.R);
+    {
+        std::lock_guard<std::mutex> lock(g_roi_mutex);
+        for (size_t i = g_roi_cache.size(); i-- > 0;)
+            if (!std::memcmp(&g_roi_cache[i].key, &key, sizeof key)) {  // bit patterns: -0.0f and NaNs simply miss
+                std::memcpy(rect, g_roi_cache[i].rect, sizeof g_roi_cache[i].rect);
+                return;
+            }
+    }
+    projector_roi(p, src_w, src_h, rect);
+    RoiEntry e;
+    e.key = key;
+    std::memcpy(e.rect, rect, sizeof e.rect);
+    std::lock_guard<std::mutex> lock(g_roi_mutex);
+    if (g_roi_cache.size() >= ROI_CACHE_ENTRIES) g_roi_cache.erase(g_roi_cache.begin());
+    g_roi_cache.push_back(e);
+}
+}  // namespace
+
 extern "C" {
 
 int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], int src_w, int src_h, int out_rect[4])
@@ -91,7 +136,7 @@ int sb_warp_roi(int warp_type, float scale, const float K[9], const float R[9], 
     }
     Projector p;
     projector_setup(p, warp_type, scale, K, R);
-    projector_roi(p, src_w, src_h, out_rect);
+    cached_roi(p, warp_type, scale, K, R, src_w, src_h, out_rect);
     return SB_OK;
 }
 
@@ -109,7 +154,7 @@ static int warp_impl(int warp_type, float scale, const float K[9], const float R
     Projector p;
     projector_setup(p, warp_type, scale, K, R);
     int rect[4];
-    projector_roi(p, src_w, src_h, rect);
+    cached_roi(p, warp_type, scale, K, R, src_w, src_h, rect);
     std::memcpy(out_rect, rect, sizeof rect);
     if (!dst_img && !dst_mask) return SB_OK;
     const int w = rect[2], h = rect[3];
